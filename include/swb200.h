@@ -1,0 +1,119 @@
+/* swb200 -- B200-native (sm_100a) backend for the Marlin prover hot path of lambdaclass/simpleworks.
+ *
+ * C ABI of libswb200.{a,so}: exactly what a Rust `extern "C"` block in a sibling FFI crate would
+ * bind (simpleworks itself is #![forbid(unsafe_code)], reference src/lib.rs:2).  Plain pointers
+ * and sizes only.  There is no plugin registry in simpleworks / arkworks 0.3 -- dispatch is by
+ * static generics -- so each entry point names the upstream call shape it replaces and the
+ * reference call site that reaches it:
+ *
+ *   swb_msm_g1*            ark_ec::msm::VariableBaseMSM::multi_scalar_mul(&[G1Affine], &[BigInteger256])
+ *                          <- kzg10::commit/open <- MarlinKZG10::commit/open <- Marlin::index/prove
+ *                          <- reference src/marlin/mod.rs:75,92; src/merkle_tree/simple_merkle_tree.rs:83,119
+ *   swb_ntt_fr*            ark_poly::Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place
+ *                          <- AHP indexer + prover rounds <- reference src/marlin/mod.rs:75,92
+ *   swb_fixed_base_powers  ark_ec::msm::FixedBaseMSM::{get_window_table,multi_scalar_mul} + batch
+ *                          normalisation <- KZG10::setup <- Marlin::universal_setup
+ *                          <- reference src/marlin/mod.rs:52; simple_merkle_tree.rs:39
+ *   swb_fr_*, swb_fq_*     ark_ff::Fp256<FrParameters> / Fp384<FqParameters> arithmetic (vector forms)
+ *
+ * Data types are bit-identical to the arkworks in-memory representation (Montgomery form,
+ * little-endian u64 limbs), so a Rust shim passes slices straight through.
+ *
+ * Conventions: every call returns 0 on success or an SWB_E* class; text via swb_last_error().
+ * The library never aborts and never falls back to the CPU: without a CUDA device swb_init
+ * fails with SWB_ECUDA.  A swb_ctx owns one device and one stream; it is single-threaded (one
+ * call in flight); several contexts (one per GPU / process) may coexist.  Pointers named *_host
+ * are ordinary host memory borrowed for the duration of the call; *_dev are device pointers on
+ * the context's device.
+ */
+#ifndef SWB200_H
+#define SWB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } swb_fr;        /* ark_ff::Fp256<FrParameters>, Montgomery   */
+typedef struct { uint64_t l[4]; } swb_bigint256; /* ark_ff::BigInteger256, canonical integer  */
+typedef struct { uint64_t l[6]; } swb_fq;        /* ark_ff::Fp384<FqParameters>, Montgomery   */
+typedef struct { swb_fq x, y; uint8_t infinity; uint8_t _pad[7]; } swb_g1_affine;   /* 104 B  */
+typedef struct { swb_fq x, y, z; } swb_g1_jacobian;                /* 144 B, (X/Z^2, Y/Z^3)    */
+
+typedef struct swb_ctx swb_ctx;
+typedef struct swb_bases swb_bases;
+
+enum { SWB_OK = 0, SWB_ECUDA = 1, SWB_EARG = 2, SWB_ENOMEM = 3, SWB_EINTERNAL = 4 };
+
+/* ---- context ---------------------------------------------------------------------------- */
+int  swb_init(int device, swb_ctx** out);
+void swb_destroy(swb_ctx*);
+const char* swb_last_error(const swb_ctx*);      /* NULL ctx -> last error of a failed swb_init */
+/* run all work of this context on an existing CUDA stream (cudaStream_t), e.g. the caller's
+ * current stream so that its events time the kernels; NULL restores the context's own stream. */
+int  swb_set_stream(swb_ctx*, void* cuda_stream);
+int  swb_sync(swb_ctx*);
+int  swb_device_info(swb_ctx*, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t swb_launch_count(const swb_ctx*);
+
+/* ---- device buffers (thin cudaMalloc/cudaMemcpy wrappers so non-CUDA hosts can stay resident) */
+int  swb_dev_alloc(swb_ctx*, size_t bytes, void** out_dev);
+int  swb_dev_free(swb_ctx*, void* dev);
+int  swb_h2d(swb_ctx*, void* dst_dev, const void* src_host, size_t bytes);
+int  swb_d2h(swb_ctx*, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- field vectors: r[i] = a[i] op b[i]  (device pointers; parity + throughput probes) ---- */
+int  swb_fr_mul_vec_dev(swb_ctx*, swb_fr* r_dev, const swb_fr* a_dev, const swb_fr* b_dev, size_t n);
+int  swb_fr_add_vec_dev(swb_ctx*, swb_fr* r_dev, const swb_fr* a_dev, const swb_fr* b_dev, size_t n);
+int  swb_fr_sub_vec_dev(swb_ctx*, swb_fr* r_dev, const swb_fr* a_dev, const swb_fr* b_dev, size_t n);
+int  swb_fq_mul_vec_dev(swb_ctx*, swb_fq* r_dev, const swb_fq* a_dev, const swb_fq* b_dev, size_t n);
+int  swb_fq_add_vec_dev(swb_ctx*, swb_fq* r_dev, const swb_fq* a_dev, const swb_fq* b_dev, size_t n);
+int  swb_fq_sub_vec_dev(swb_ctx*, swb_fq* r_dev, const swb_fq* a_dev, const swb_fq* b_dev, size_t n);
+/* ark_ff::batch_inversion (zeros stay zero), in place */
+int  swb_fr_batch_inverse_dev(swb_ctx*, swb_fr* v_dev, size_t n);
+/* Measures the achievable 32x32->64 multiply-accumulate ("limb-product") rate of this GPU with
+ * a register-resident Montgomery-multiplication loop: the integer roofline denominator.
+ * field: 0 = Fr (128 limb-products per multiplication), 1 = Fq (288).  Returns limb-products/s
+ * and field multiplications/s measured with CUDA events. */
+int  swb_measure_mul_peak(swb_ctx*, int field, int iters, double* limb_products_per_s, double* muls_per_s);
+
+/* ---- G1 bases (SRS / committer key): upload once, keep resident --------------------------- */
+int  swb_bases_load(swb_ctx*, const swb_g1_affine* host, size_t n, swb_bases** out);
+/* same from a device buffer of swb_g1_affine (104-byte records) */
+int  swb_bases_load_dev(swb_ctx*, const swb_g1_affine* dev, size_t n, swb_bases** out);
+size_t swb_bases_len(const swb_bases*);
+void swb_bases_free(swb_bases*);
+
+/* ---- variable-base MSM: out = sum_{i<n} scalars[i] * bases[offset+i] ---------------------- */
+/* Result is a Jacobian point with Z = 1 (or (0,1,0) for the identity): the unique affine value
+ * arkworks' callers obtain after into_affine(), so results compare bit-for-bit.             */
+int  swb_msm_g1(swb_ctx*, const swb_bases*, size_t offset, const swb_bigint256* scalars_host, size_t n,
+                swb_g1_jacobian* out_host);
+int  swb_msm_g1_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_bigint256* scalars_dev, size_t n,
+                    swb_g1_jacobian* out_host);
+/* scalars given in Montgomery form (Fr), converted on the device -- what kzg10::commit does with
+ * into_repr() on the host today */
+int  swb_msm_g1_fr_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scalars_dev, size_t n,
+                       swb_g1_jacobian* out_host);
+/* window width override for tuning/tests (0 = automatic) */
+int  swb_msm_set_window_bits(swb_ctx*, int c);
+/* sum of n Jacobian points on the host side of the ABI (combining per-GPU partial MSMs) */
+int  swb_g1_sum_jacobian(swb_ctx*, const swb_g1_jacobian* pts_host, size_t n, swb_g1_jacobian* out_host);
+
+/* ---- fixed-base: out[i] = beta^i * g, i < n, affine (KZG10::setup powers_of_g) ------------ */
+int  swb_fixed_base_powers(swb_ctx*, const swb_g1_jacobian* g_host, const swb_fr* beta_host, size_t n,
+                           swb_g1_affine* out_host);
+
+/* ---- radix-2 NTT over Fr, natural order in and out, in place ------------------------------ */
+/* inverse: uses w^-1 and scales by n^-1.  coset: multiplies by 22^j before a forward transform,
+ * by 22^-j after an inverse one.  log_n <= 30 (Fr two-adicity is 47; bounded here by tables).  */
+int  swb_ntt_fr(swb_ctx*, swb_fr* inout_host, uint32_t log_n, int inverse, int coset);
+int  swb_ntt_fr_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, int inverse, int coset);
+int  swb_ntt_fr_batch_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, size_t batch, int inverse, int coset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB200_H */

@@ -1,0 +1,82 @@
+"""ctypes loader for libswb200.so (the C ABI declared in include/swb200.h).
+
+There is no CPU fallback: if the CUDA library is missing or fails to load, importing the
+operators raises.  The library is built in-tree by `python -m simpleworks_b200.build`
+(nvcc -gencode arch=compute_100a,code=sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libswb200.so")
+
+# every symbol include/swb200.h declares; tests/test_abi.py checks the header against this list
+# and that the built library exports each one.
+SYMBOLS = [
+    "swb_init", "swb_destroy", "swb_last_error", "swb_set_stream", "swb_sync", "swb_device_info",
+    "swb_launch_count", "swb_dev_alloc", "swb_dev_free", "swb_h2d", "swb_d2h",
+    "swb_fr_mul_vec_dev", "swb_fr_add_vec_dev", "swb_fr_sub_vec_dev",
+    "swb_fq_mul_vec_dev", "swb_fq_add_vec_dev", "swb_fq_sub_vec_dev",
+    "swb_fr_batch_inverse_dev", "swb_measure_mul_peak",
+    "swb_bases_load", "swb_bases_load_dev", "swb_bases_len", "swb_bases_free",
+    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_set_window_bits", "swb_g1_sum_jacobian",
+    "swb_fixed_base_powers",
+    "swb_ntt_fr", "swb_ntt_fr_dev", "swb_ntt_fr_batch_dev",
+]
+
+_lib = None
+
+
+class SwbError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SwbError(
+            f"{LIB_PATH} not found: build it with `python -m simpleworks_b200.build` "
+            "(there is no CPU fallback for the Marlin hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32
+    pvp = ctypes.POINTER(ctypes.c_void_p)
+    sig = {
+        "swb_init": (i32, [i32, pvp]),
+        "swb_destroy": (None, [vp]),
+        "swb_last_error": (ctypes.c_char_p, [vp]),
+        "swb_set_stream": (i32, [vp, vp]),
+        "swb_sync": (i32, [vp]),
+        "swb_device_info": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(sz)]),
+        "swb_launch_count": (ctypes.c_uint64, [vp]),
+        "swb_dev_alloc": (i32, [vp, sz, pvp]),
+        "swb_dev_free": (i32, [vp, vp]),
+        "swb_h2d": (i32, [vp, vp, vp, sz]),
+        "swb_d2h": (i32, [vp, vp, vp, sz]),
+        "swb_fr_batch_inverse_dev": (i32, [vp, vp, sz]),
+        "swb_measure_mul_peak": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+        "swb_bases_load": (i32, [vp, vp, sz, pvp]),
+        "swb_bases_load_dev": (i32, [vp, vp, sz, pvp]),
+        "swb_bases_len": (sz, [vp]),
+        "swb_bases_free": (None, [vp]),
+        "swb_msm_g1": (i32, [vp, vp, sz, vp, sz, vp]),
+        "swb_msm_g1_dev": (i32, [vp, vp, sz, vp, sz, vp]),
+        "swb_msm_g1_fr_dev": (i32, [vp, vp, sz, vp, sz, vp]),
+        "swb_msm_set_window_bits": (i32, [vp, i32]),
+        "swb_g1_sum_jacobian": (i32, [vp, vp, sz, vp]),
+        "swb_fixed_base_powers": (i32, [vp, vp, vp, sz, vp]),
+        "swb_ntt_fr": (i32, [vp, vp, u32, i32, i32]),
+        "swb_ntt_fr_dev": (i32, [vp, vp, u32, i32, i32]),
+        "swb_ntt_fr_batch_dev": (i32, [vp, vp, u32, sz, i32, i32]),
+    }
+    for name in ("swb_fr_mul_vec_dev", "swb_fr_add_vec_dev", "swb_fr_sub_vec_dev",
+                 "swb_fq_mul_vec_dev", "swb_fq_add_vec_dev", "swb_fq_sub_vec_dev"):
+        sig[name] = (i32, [vp, vp, vp, vp, sz])
+    for name in SYMBOLS:
+        fn = getattr(lib, name)          # AttributeError here = library/headers out of sync
+        fn.restype, fn.argtypes = sig[name]
+    _lib = lib
+    return lib

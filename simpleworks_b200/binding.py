@@ -1,0 +1,194 @@
+"""Thin Python binding over the C ABI (include/swb200.h), used by tests/ and bench.py.
+
+Names follow the upstream operators this backend replaces:
+
+    Backend.msm(bases, scalars)            VariableBaseMSM::multi_scalar_mul
+    Backend.fft_in_place / ifft_in_place / coset_fft_in_place / coset_ifft_in_place
+                                           Radix2EvaluationDomain::*_in_place
+    Backend.fixed_base_powers              FixedBaseMSM (KZG10::setup powers_of_g)
+
+Host arrays are numpy uint64 with the arkworks in-memory layout (n x 4 Fr / BigInteger256, n x 6 Fq, n x 13 affine, n x 18 Jacobian:
+u64 words); device-resident data are torch CUDA tensors of dtype int64 with the same shapes, whose
+data_ptr() is handed to the *_dev entry points.  PyTorch is plumbing only (device memory, streams,
+torch.distributed); every computation happens in libswb200.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import SwbError
+
+
+def _np_ptr(a: np.ndarray):
+    if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"] and a.dtype == np.uint64):
+        raise TypeError("expected a C-contiguous numpy uint64 array")
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Bases:
+    """Device-resident G1 bases (SRS powers / committer key)."""
+
+    def __init__(self, backend: "Backend", handle, n: int):
+        self._b = backend
+        self._h = handle
+        self.n = n
+
+    def free(self):
+        if self._h:
+            self._b._lib.swb_bases_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Backend:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.swb_init(device, ctypes.byref(h))
+        if rc != 0:
+            msg = self._lib.swb_last_error(None)
+            raise SwbError(f"swb_init({device}) failed [{rc}]: {msg.decode() if msg else ''}")
+        self._h = h
+        self.device = device
+
+    # ---- plumbing ----------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.swb_last_error(self._h)
+            raise SwbError(f"libswb200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self._lib.swb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        """Run on torch's current CUDA stream so torch.cuda.Event brackets the kernels."""
+        import torch
+        self._check(self._lib.swb_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def sync(self):
+        self._check(self._lib.swb_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.swb_launch_count(self._h))
+
+    def device_info(self) -> dict:
+        sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        self._check(self._lib.swb_device_info(self._h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    @staticmethod
+    def _dev_ptr(t):
+        import torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype == torch.int64):
+            raise TypeError("expected a contiguous CUDA int64 tensor")
+        return ctypes.c_void_p(t.data_ptr())
+
+    def to_device(self, a: np.ndarray):
+        import torch
+        return torch.from_numpy(a.view(np.int64)).to(f"cuda:{self.device}")
+
+    @staticmethod
+    def to_host(t) -> np.ndarray:
+        return t.cpu().numpy().view(np.uint64)
+
+    # ---- field vector probes ---------------------------------------------------------
+    def _vec(self, name, a, b):
+        import torch
+        r = torch.empty_like(a)
+        self._check(getattr(self._lib, name)(self._h, self._dev_ptr(r), self._dev_ptr(a), self._dev_ptr(b), a.shape[0]))
+        return r
+
+    def fr_mul(self, a, b): return self._vec("swb_fr_mul_vec_dev", a, b)
+    def fr_add(self, a, b): return self._vec("swb_fr_add_vec_dev", a, b)
+    def fr_sub(self, a, b): return self._vec("swb_fr_sub_vec_dev", a, b)
+    def fq_mul(self, a, b): return self._vec("swb_fq_mul_vec_dev", a, b)
+    def fq_add(self, a, b): return self._vec("swb_fq_add_vec_dev", a, b)
+    def fq_sub(self, a, b): return self._vec("swb_fq_sub_vec_dev", a, b)
+
+    def fr_batch_inverse_(self, v):
+        self._check(self._lib.swb_fr_batch_inverse_dev(self._h, self._dev_ptr(v), v.shape[0]))
+        return v
+
+    def measure_mul_peak(self, field: str = "fq", iters: int = 2000) -> dict:
+        lps, mps = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.swb_measure_mul_peak(self._h, 0 if field == "fr" else 1, iters, ctypes.byref(lps), ctypes.byref(mps)))
+        return {"limb_products_per_s": lps.value, "muls_per_s": mps.value}
+
+    # ---- MSM ---------------------------------------------------------------------------
+    def load_bases(self, affine) -> Bases:
+        """affine: (n,13) uint64 numpy array of 104-byte GroupAffine records, or the same as a
+        CUDA int64 tensor."""
+        h = ctypes.c_void_p()
+        n = int(affine.shape[0])
+        if isinstance(affine, np.ndarray):
+            self._check(self._lib.swb_bases_load(self._h, _np_ptr(np.ascontiguousarray(affine)), n, ctypes.byref(h)))
+        else:
+            self._check(self._lib.swb_bases_load_dev(self._h, self._dev_ptr(affine), n, ctypes.byref(h)))
+        return Bases(self, h, n)
+
+    def set_msm_window_bits(self, c: int):
+        self._check(self._lib.swb_msm_set_window_bits(self._h, c))
+
+    def msm(self, bases: Bases, scalars, offset: int = 0, montgomery: bool = False) -> np.ndarray:
+        """VariableBaseMSM::multi_scalar_mul(bases[offset..], scalars) -> (1,18) Jacobian with Z=1.
+        scalars: (n,4) canonical BigInteger256 as numpy (host path, H2D inside the call) or CUDA
+        tensor (resident path); montgomery=True takes Fr elements instead (device only)."""
+        out = np.zeros((1, 18), dtype=np.uint64)
+        n = min(int(scalars.shape[0]), bases.n - offset)      # arkworks truncates to the shorter
+        if isinstance(scalars, np.ndarray):
+            if montgomery:
+                raise TypeError("montgomery scalars are a device-side path")
+            self._check(self._lib.swb_msm_g1(self._h, bases._h, offset, _np_ptr(np.ascontiguousarray(scalars)), n, _np_ptr(out)))
+        elif montgomery:
+            self._check(self._lib.swb_msm_g1_fr_dev(self._h, bases._h, offset, self._dev_ptr(scalars), n, _np_ptr(out)))
+        else:
+            self._check(self._lib.swb_msm_g1_dev(self._h, bases._h, offset, self._dev_ptr(scalars), n, _np_ptr(out)))
+        return out
+
+    def g1_sum(self, jac: np.ndarray) -> np.ndarray:
+        jac = np.ascontiguousarray(jac.reshape(-1, 18))
+        out = np.zeros((1, 18), dtype=np.uint64)
+        self._check(self._lib.swb_g1_sum_jacobian(self._h, _np_ptr(jac), jac.shape[0], _np_ptr(out)))
+        return out
+
+    def fixed_base_powers(self, g_jac: np.ndarray, beta: np.ndarray, n: int) -> np.ndarray:
+        out = np.zeros((n, 13), dtype=np.uint64)
+        self._check(self._lib.swb_fixed_base_powers(self._h, _np_ptr(np.ascontiguousarray(g_jac.reshape(1, 18))),
+                                                    _np_ptr(np.ascontiguousarray(beta.reshape(1, 4))), n, _np_ptr(out)))
+        return out
+
+    # ---- NTT (Radix2EvaluationDomain) ------------------------------------------------
+    def ntt_(self, v, log_n: int, inverse: bool = False, coset: bool = False, batch: int = 1):
+        """In place.  v: (batch * 2^log_n, 4) numpy (host path) or CUDA tensor (resident path)."""
+        if v.shape[0] != (batch << log_n):
+            raise ValueError("ntt: array length must be batch * 2^log_n (zero-pad like arkworks does)")
+        if isinstance(v, np.ndarray):
+            if batch != 1:
+                raise ValueError("host path is single-polynomial")
+            self._check(self._lib.swb_ntt_fr(self._h, _np_ptr(v), log_n, int(inverse), int(coset)))
+        elif batch == 1:
+            self._check(self._lib.swb_ntt_fr_dev(self._h, self._dev_ptr(v), log_n, int(inverse), int(coset)))
+        else:
+            self._check(self._lib.swb_ntt_fr_batch_dev(self._h, self._dev_ptr(v), log_n, batch, int(inverse), int(coset)))
+        return v
+
+    def fft_in_place(self, v, log_n): return self.ntt_(v, log_n, False, False)
+    def ifft_in_place(self, v, log_n): return self.ntt_(v, log_n, True, False)
+    def coset_fft_in_place(self, v, log_n): return self.ntt_(v, log_n, False, True)
+    def coset_ifft_in_place(self, v, log_n): return self.ntt_(v, log_n, True, True)

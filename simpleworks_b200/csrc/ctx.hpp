@@ -1,0 +1,73 @@
+// Internal context shared by the translation units of libswb200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/swb200.h"
+#include "fp.cuh"
+
+struct swb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int msm_window_override = 0;
+
+    // NTT tables (device): three levels of 1024 powers of the 2^30-th root of unity, and of the
+    // coset generator 22 and its inverse.  Built by one kernel at swb_init.
+    swb::Fr* tw_root = nullptr;   // [3][1024]
+    swb::Fr* tw_gen = nullptr;    // [3][1024]
+    swb::Fr* tw_geninv = nullptr; // [3][1024]
+
+    // grow-only scratch arena so repeated calls do not cudaMalloc in the timed path
+    struct Scratch { void* p = nullptr; size_t bytes = 0; };
+    std::map<std::string, Scratch> scratch;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct swb_bases {
+    swb_ctx* ctx = nullptr;
+    swb::Fq* xy = nullptr;   // n records of 96 bytes: x | y ; identity = (0,0)
+    size_t n = 0;
+};
+
+namespace swb {
+
+int set_err(swb_ctx* c, int code, const char* fmt, ...);
+int cuda_fail(swb_ctx* c, cudaError_t e, const char* what);
+// returns device scratch of at least `bytes`, tagged; nullptr + error set on failure
+void* get_scratch(swb_ctx* c, const char* tag, size_t bytes);
+void* get_pinned(swb_ctx* c, size_t bytes);
+
+#define SWB_CUDA(ctx, call)                                                   \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return swb::cuda_fail((ctx), e__, #call);     \
+    } while (0)
+
+#define SWB_LAUNCH_CHECK(ctx, name)                                           \
+    do {                                                                      \
+        (ctx)->launches++;                                                    \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) return swb::cuda_fail((ctx), e__, name);      \
+    } while (0)
+
+#define SWB_REQUIRE(ctx, cond, msg)                                           \
+    do {                                                                      \
+        if (!(cond)) return swb::set_err((ctx), SWB_EARG, "%s", msg);         \
+    } while (0)
+
+// implemented in ntt.cu
+int ntt_build_tables(swb_ctx* c);
+
+}  // namespace swb

@@ -1,0 +1,334 @@
+// Radix-2 evaluation-domain NTT over BLS12-377 Fr.
+//
+// Replaces ark_poly::Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place (ark-poly
+// 0.3 domain/radix2/{mod,fft}.rs), which Marlin's indexer and the three prover rounds call ~20
+// times per proof (reference src/marlin/mod.rs:75,92 -> ark-marlin ahp/{indexer,prover}.rs).
+// Same contract: natural order in and out, w_n = ROOT^(2^(47-log n)), inverse scales by n^-1,
+// coset shift g = 22.  DFT values are unique, so results are bit-identical to arkworks'.
+//
+// Schedule: n = R_1 * R_2 * ... * R_m with every R_s <= 2^8 (multi-radix Cooley-Tukey).  Pass s<m
+// transforms along digit s for a tile of T adjacent columns held in shared memory (coalesced
+// T*32-byte runs), multiplies by the inter-digit twiddles and writes back in place; the last pass
+// transforms contiguous rows and writes them transposed (digit-reversed) so the output is in
+// natural order.  Inside a tile the R-point transform is a decimation-in-frequency network with
+// the bit-reversal folded into the store indices.  Twiddles come from three 1024-entry tables of
+// powers of the 2^30-th root of unity (w^e = T2[e>>20] * T1[(e>>10)&1023] * T0[e&1023]).
+#include "ctx.hpp"
+
+namespace swb {
+
+constexpr int NTT_THREADS = 256;
+constexpr int NTT_TILE_LOG = 11;            // R*T = 2048 elements = 64 KB of shared memory
+constexpr uint32_t NTT_MAX_LOG = 30;
+
+struct NttPass {
+    const Fr* in;
+    Fr* out;
+    uint32_t log_n, log_r, log_t;
+    uint32_t mode;       // 0: column pass (in place layout), 1: final row pass (transposed store)
+    uint32_t log_m;      // column mode: log2 of the trailing block size M_s
+    uint32_t tw_shift;   // column mode: 30 - (log_r + log_m)
+    uint32_t ndig;       // final mode: number of leading digits
+    uint32_t dig_log[4]; // final mode: log2 R_1 .. R_{m-1}
+    uint32_t inverse, pre_coset, post_coset, post_scale;
+    Fr scale;            // n^-1 (Montgomery) when post_scale
+    size_t batch_stride;
+};
+
+__device__ __forceinline__ Fr tw_lookup(const Fr* __restrict__ tab, uint32_t e) {
+    const uint32_t d0 = e & 1023u, d1 = (e >> 10) & 1023u, d2 = e >> 20;
+    Fr r = tab[2048 + d2];
+    if (d1) r = r * tab[1024 + d1];
+    if (d0) r = r * tab[d0];
+    return r;
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t v, uint32_t bits) { return bits ? (__brev(v) >> (32 - bits)) : 0u; }
+
+// shared tile: 16-byte halves of each element kept in two planes so that consecutive elements are
+// consecutive 16-byte words (conflict-free 128-bit accesses).
+struct Tile {
+    uint4* lo;
+    uint4* hi;
+    __device__ __forceinline__ Fr get(uint32_t e) const {
+        Fr r;
+        uint4 a = lo[e], b = hi[e];
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void put(uint32_t e, const Fr& v) const {
+        lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+};
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* __restrict__ tw_root,
+                                                           const Fr* __restrict__ tw_coset) {
+    extern __shared__ uint4 smem[];
+    const uint32_t R = 1u << p.log_r, T = 1u << p.log_t, tile = R * T;
+    Tile tl{smem, smem + tile};
+    const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
+    Fr* out = p.out + (size_t)blockIdx.y * p.batch_stride;
+    const uint32_t tid = threadIdx.x;
+
+    // ---- where this block's tile lives ------------------------------------------------------
+    size_t in_base, out_base, in_j_stride, in_t_stride, out_k_stride, out_t_stride;
+    uint32_t col0 = 0;   // first column index (column mode), for the inter-digit twiddle
+    if (p.mode == 0) {
+        const uint32_t chunks = 1u << (p.log_m - p.log_t);
+        const uint32_t outer = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+        col0 = chunk << p.log_t;
+        in_base = ((size_t)outer << (p.log_r + p.log_m)) + col0;
+        out_base = in_base;
+        in_j_stride = out_k_stride = (size_t)1 << p.log_m;
+        in_t_stride = out_t_stride = 1;
+    } else {
+        // rows rho' = g*T + t in output (natural) row order; their position in the in-place
+        // layout is the digit reversal of rho' over (R_1 .. R_{m-1})
+        const uint32_t rp0 = blockIdx.x << p.log_t;
+        uint32_t rest = rp0, rho = 0;
+        for (uint32_t d = 0; d < p.ndig; d++) {
+            const uint32_t dig = rest & ((1u << p.dig_log[d]) - 1u);
+            rest >>= p.dig_log[d];
+            rho = (rho << p.dig_log[d]) | dig;   // k_1 ends up most significant
+        }
+        in_base = (size_t)rho << p.log_r;
+        in_j_stride = 1;
+        in_t_stride = p.ndig ? ((size_t)1 << (p.log_n - p.dig_log[0])) : 0;
+        out_base = rp0;
+        out_t_stride = 1;
+        out_k_stride = (size_t)1 << (p.log_n - p.log_r);
+    }
+
+    // ---- load (with optional coset pre-scaling by g^i) ---------------------------------------
+    for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
+        uint32_t j, t, e;
+        if (p.mode == 0) { t = idx & (T - 1); j = idx >> p.log_t; e = idx; }
+        else { j = idx & (R - 1); t = idx >> p.log_r; e = idx; }        // final mode tile is [t][j]
+        const size_t gi = in_base + (size_t)j * in_j_stride + (size_t)t * in_t_stride;
+        Fr v = ld_fr(in + gi);
+        if (p.pre_coset) v = v * tw_lookup(tw_coset, (uint32_t)gi);
+        tl.put(e, v);
+    }
+    __syncthreads();
+
+    // ---- R-point DIF network along j ----------------------------------------------------------
+    // element (j,t) sits at j*T+t (column mode) or t*R+j (final mode)
+    const uint32_t js = p.mode == 0 ? T : 1u, ts = p.mode == 0 ? 1u : R;
+    const uint32_t nbf = tile >> 1;
+    for (uint32_t s = 0; s < p.log_r; s++) {
+        const uint32_t log_half = p.log_r - 1 - s, half = 1u << log_half;
+        for (uint32_t idx = tid; idx < nbf; idx += NTT_THREADS) {
+            uint32_t b, t;
+            if (p.mode == 0) { t = idx & (T - 1); b = idx >> p.log_t; }
+            else { b = idx & ((R >> 1) - 1); t = idx >> (p.log_r - 1); }
+            const uint32_t pos = b & (half - 1), grp = b >> log_half;
+            const uint32_t j0 = (grp << (log_half + 1)) + pos;
+            const uint32_t e0 = j0 * js + t * ts, e1 = e0 + half * js;
+            Fr u = tl.get(e0), v = tl.get(e1);
+            Fr sum = u + v, dif = u - v;
+            if (pos) {
+                uint32_t ex = (pos << s) << (NTT_MAX_LOG - p.log_r);
+                if (p.inverse) ex = ((1u << NTT_MAX_LOG) - ex) & ((1u << NTT_MAX_LOG) - 1u);
+                dif = dif * tw_lookup(tw_root, ex);
+            }
+            tl.put(e0, sum);
+            tl.put(e1, dif);
+        }
+        __syncthreads();
+    }
+
+    // ---- store: X[k] is at bit-reversed position; apply inter-digit twiddle / scaling --------
+    if (p.mode == 0) {
+        // thread keeps its column t fixed and walks k; twiddle w^(k*col) advances by w^(dk*col)
+        const uint32_t t = tid & (T - 1);
+        const uint32_t col = col0 + t;
+        const uint32_t k0 = tid >> p.log_t, dk = NTT_THREADS >> p.log_t;
+        const uint32_t mask = (1u << NTT_MAX_LOG) - 1u;
+        uint32_t e_w = (uint32_t)((((uint64_t)k0 * col) << p.tw_shift) & mask);
+        uint32_t e_s = (uint32_t)((((uint64_t)dk * col) << p.tw_shift) & mask);
+        if (p.inverse) { e_w = ((1u << NTT_MAX_LOG) - e_w) & mask; e_s = ((1u << NTT_MAX_LOG) - e_s) & mask; }
+        Fr w = tw_lookup(tw_root, e_w);
+        const Fr step = tw_lookup(tw_root, e_s);
+        for (uint32_t k = k0; k < R; k += dk) {
+            Fr v = tl.get(bitrev(k, p.log_r) * T + t);
+            if (col) v = v * w;
+            st_fr(out + out_base + (size_t)k * out_k_stride + t, v);
+            w = w * step;
+        }
+    } else {
+        for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
+            const uint32_t t = idx & (T - 1), k = idx >> p.log_t;
+            Fr v = tl.get(t * R + bitrev(k, p.log_r));
+            const size_t go = out_base + (size_t)k * out_k_stride + (size_t)t * out_t_stride;
+            if (p.post_coset) v = v * tw_lookup(tw_coset, (uint32_t)go);
+            if (p.post_scale) v = v * p.scale;
+            st_fr(out + go, v);
+        }
+    }
+}
+
+// table[l][j] = base_l ^ j
+__global__ void k_build_pow_table(Fr* __restrict__ tab, Fr b0, Fr b1, Fr b2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * 1024) return;
+    const uint32_t l = i >> 10, j = i & 1023u;
+    const Fr base = l == 0 ? b0 : (l == 1 ? b1 : b2);
+    tab[i] = base.pow_u64(j);
+}
+
+static Fr host_fr_const(const uint32_t (&v)[8]) {
+    Fr r;
+    for (int i = 0; i < 8; i++) r.l[i] = v[i];
+    return r;
+}
+
+int ntt_build_tables(swb_ctx* c) {
+    SWB_CUDA(c, cudaMalloc(&c->tw_root, sizeof(Fr) * 3 * 1024));
+    SWB_CUDA(c, cudaMalloc(&c->tw_gen, sizeof(Fr) * 3 * 1024));
+    SWB_CUDA(c, cudaMalloc(&c->tw_geninv, sizeof(Fr) * 3 * 1024));
+    const uint32_t root_init[8] = SWB_FR_ROOT_OF_UNITY_INIT, gen_init[8] = SWB_FR_GENERATOR_INIT,
+                   geninv_init[8] = SWB_FR_GENERATOR_INV_INIT;
+    Fr w = host_fr_const(root_init);
+    for (uint32_t i = NTT_MAX_LOG; i < SWB_FR_TWO_ADICITY; i++) w = w.sqr();   // 2^30-th root of unity
+    Fr bases[3][3];
+    bases[0][0] = w;
+    bases[1][0] = host_fr_const(gen_init);
+    bases[2][0] = host_fr_const(geninv_init);
+    for (int k = 0; k < 3; k++)
+        for (int l = 1; l < 3; l++) {
+            Fr b = bases[k][l - 1];
+            for (int i = 0; i < 10; i++) b = b.sqr();
+            bases[k][l] = b;
+        }
+    Fr* tabs[3] = {c->tw_root, c->tw_gen, c->tw_geninv};
+    for (int k = 0; k < 3; k++) {
+        k_build_pow_table<<<12, 256, 0, c->stream>>>(tabs[k], bases[k][0], bases[k][1], bases[k][2]);
+        SWB_LAUNCH_CHECK(c, "k_build_pow_table");
+    }
+    SWB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_TILE_LOG) * 32));
+    SWB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SWB_OK;
+}
+
+// plan: digits of at most 8 bits, as even as possible
+static int plan_digits(uint32_t log_n, uint32_t* dig) {
+    if (log_n == 0) { dig[0] = 0; return 1; }
+    int m = (int)((log_n + 7) / 8);
+    for (int s = 0; s < m; s++) dig[s] = log_n / m + ((uint32_t)s < log_n % m ? 1 : 0);
+    return m;
+}
+
+static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inverse, int coset) {
+    SWB_REQUIRE(c, log_n <= NTT_MAX_LOG, "ntt: log_n > 30 not supported");
+    SWB_REQUIRE(c, data != nullptr, "ntt: NULL data");
+    if (batch == 0) return SWB_OK;
+    SWB_REQUIRE(c, batch < 65536, "ntt: batch too large");
+    SWB_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)1 << log_n;
+    uint32_t dig[8];
+    const int m = plan_digits(log_n, dig);
+    SWB_REQUIRE(c, m <= 5, "ntt: internal plan error");
+    Fr* tmp = nullptr;
+    if (m > 1) {
+        tmp = (Fr*)get_scratch(c, "ntt_tmp", sizeof(Fr) * n * batch);
+        if (!tmp) return SWB_ENOMEM;
+    }
+    Fr scale = Fr::one();
+    if (inverse) {
+        // n^-1 = (2^-1)^log_n
+        const uint32_t two_inv[8] = SWB_FR_TWO_INV_INIT;
+        Fr ti = host_fr_const(two_inv);
+        for (uint32_t i = 0; i < log_n; i++) scale = scale * ti;
+    }
+    uint32_t log_m = log_n;   // trailing block size before pass s
+    for (int s = 0; s < m; s++) {
+        NttPass p{};
+        p.log_n = log_n;
+        p.log_r = dig[s];
+        p.inverse = inverse ? 1 : 0;
+        p.batch_stride = n;
+        p.scale = scale;
+        log_m -= dig[s];
+        const bool last = (s == m - 1);
+        p.in = (s == 0) ? data : tmp;
+        p.out = (m == 1) ? data : (last ? data : tmp);
+        p.pre_coset = (s == 0 && coset && !inverse) ? 1 : 0;
+        p.post_coset = (last && coset && inverse) ? 1 : 0;
+        p.post_scale = (last && inverse) ? 1 : 0;
+        uint32_t log_t;
+        size_t blocks;
+        if (!last) {
+            p.mode = 0;
+            p.log_m = log_m;
+            p.tw_shift = NTT_MAX_LOG - (dig[s] + log_m);
+            log_t = NTT_TILE_LOG - dig[s];
+            if (log_t > log_m) log_t = log_m;
+            blocks = n >> (dig[s] + log_t);
+        } else {
+            p.mode = 1;
+            p.ndig = (uint32_t)(m - 1);
+            for (int d = 0; d < m - 1; d++) p.dig_log[d] = dig[d];
+            log_t = NTT_TILE_LOG - dig[s];
+            const uint32_t lim = m > 1 ? dig[0] : 0;
+            if (log_t > lim) log_t = lim;
+            blocks = n >> (dig[s] + log_t);
+        }
+        p.log_t = log_t;
+        const size_t smem = ((size_t)32) << (dig[s] + log_t);
+        const Fr* coset_tab = inverse ? c->tw_geninv : c->tw_gen;
+        dim3 grid((unsigned)blocks, (unsigned)batch);
+        k_ntt_pass<<<grid, NTT_THREADS, smem, c->stream>>>(p, c->tw_root, coset_tab);
+        SWB_LAUNCH_CHECK(c, "k_ntt_pass");
+    }
+    return SWB_OK;
+}
+
+}  // namespace swb
+
+using namespace swb;
+
+extern "C" {
+
+int swb_ntt_fr_dev(swb_ctx* c, swb_fr* inout, uint32_t log_n, int inverse, int coset) {
+    if (!c) return SWB_EARG;
+    return ntt_run(c, (Fr*)inout, log_n, 1, inverse, coset);
+}
+
+int swb_ntt_fr_batch_dev(swb_ctx* c, swb_fr* inout, uint32_t log_n, size_t batch, int inverse, int coset) {
+    if (!c) return SWB_EARG;
+    return ntt_run(c, (Fr*)inout, log_n, batch, inverse, coset);
+}
+
+int swb_ntt_fr(swb_ctx* c, swb_fr* inout_host, uint32_t log_n, int inverse, int coset) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, log_n <= NTT_MAX_LOG, "ntt: log_n > 30 not supported");
+    SWB_REQUIRE(c, inout_host != nullptr, "ntt: NULL data");
+    SWB_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(Fr) << log_n;
+    Fr* d = (Fr*)get_scratch(c, "ntt_io", bytes);
+    if (!d) return SWB_ENOMEM;
+    SWB_CUDA(c, cudaMemcpyAsync(d, inout_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = ntt_run(c, d, log_n, 1, inverse, coset);
+    if (rc != SWB_OK) return rc;
+    SWB_CUDA(c, cudaMemcpyAsync(inout_host, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SWB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SWB_OK;
+}
+
+}  // extern "C"

