@@ -51,8 +51,11 @@ int  swb_init(int device, swb_ctx** out);
 void swb_destroy(swb_ctx*);
 const char* swb_last_error(const swb_ctx*);      /* NULL ctx -> last error of a failed swb_init */
 /* run all work of this context on an existing CUDA stream (cudaStream_t), e.g. the caller's
- * current stream so that its events time the kernels; NULL restores the context's own stream. */
+ * current stream so that its events time the kernels and its later work is ordered after ours;
+ * NULL is the CUDA legacy default stream.  swb_reset_stream returns to the context's own
+ * (non-blocking) stream, which is what a fresh context uses. */
 int  swb_set_stream(swb_ctx*, void* cuda_stream);
+int  swb_reset_stream(swb_ctx*);
 int  swb_sync(swb_ctx*);
 int  swb_device_info(swb_ctx*, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libswb200.so")
 # every symbol include/swb200.h declares; tests/test_abi.py checks the header against this list
 # and that the built library exports each one.
 SYMBOLS = [
-    "swb_init", "swb_destroy", "swb_last_error", "swb_set_stream", "swb_sync", "swb_device_info",
+    "swb_init", "swb_destroy", "swb_last_error", "swb_set_stream", "swb_reset_stream", "swb_sync", "swb_device_info",
     "swb_launch_count", "swb_dev_alloc", "swb_dev_free", "swb_h2d", "swb_d2h",
     "swb_fr_mul_vec_dev", "swb_fr_add_vec_dev", "swb_fr_sub_vec_dev",
     "swb_fq_mul_vec_dev", "swb_fq_add_vec_dev", "swb_fq_sub_vec_dev",
@@ -49,6 +49,7 @@ def load() -> ctypes.CDLL:
         "swb_destroy": (None, [vp]),
         "swb_last_error": (ctypes.c_char_p, [vp]),
         "swb_set_stream": (i32, [vp, vp]),
+        "swb_reset_stream": (i32, [vp]),
         "swb_sync": (i32, [vp]),
         "swb_device_info": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(sz)]),
         "swb_launch_count": (ctypes.c_uint64, [vp]),

@@ -58,6 +58,9 @@ class Backend:
             raise SwbError(f"swb_init({device}) failed [{rc}]: {msg.decode() if msg else ''}")
         self._h = h
         self.device = device
+        # tensors handed to the *_dev entry points are produced and consumed on torch's current
+        # stream, so run there by default (ordering + torch.cuda.Event timing)
+        self.use_torch_stream()
 
     # ---- plumbing ----------------------------------------------------------------------
     def _check(self, rc: int):

@@ -1,5 +1,6 @@
 // Context, error reporting, device buffers.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -98,6 +99,8 @@ int swb_init(int device, swb_ctx** out) {
         return swb::cuda_fail(nullptr, e, "cudaStreamCreate");
     }
     c->stream = c->own_stream;
+    const char* tr = getenv("SWB_TRACE");
+    c->trace = tr ? atoi(tr) : 0;
     int rc = swb::ntt_build_tables(c);
     if (rc != SWB_OK) {
         swb::set_err(nullptr, rc, "%s", c->err.c_str());
@@ -132,7 +135,13 @@ const char* swb_last_error(const swb_ctx* c) {
 
 int swb_set_stream(swb_ctx* c, void* s) {
     if (!c) return SWB_EARG;
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;
+    return SWB_OK;
+}
+
+int swb_reset_stream(swb_ctx* c) {
+    if (!c) return SWB_EARG;
+    c->stream = c->own_stream;
     return SWB_OK;
 }
 

@@ -21,6 +21,7 @@ struct swb_ctx {
     std::string err;
     uint64_t launches = 0;
     int msm_window_override = 0;
+    int trace = 0;            // SWB_TRACE=1: per-stage CUDA-event timings on stderr
 
     // NTT tables (device): three levels of 1024 powers of the 2^30-th root of unity, and of the
     // coset generator 22 and its inverse.  Built by one kernel at swb_init.
@@ -66,6 +67,35 @@ void* get_pinned(swb_ctx* c, size_t bytes);
     do {                                                                      \
         if (!(cond)) return swb::set_err((ctx), SWB_EARG, "%s", msg);         \
     } while (0)
+
+// per-stage CUDA-event timer, active only when ctx->trace is set
+struct StageTimer {
+    swb_ctx* c;
+    const char* what;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    StageTimer(swb_ctx* ctx, const char* w) : c(ctx), what(w) { mark("start"); }
+    void mark(const char* name) {
+        if (!c->trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        marks.emplace_back(name, e);
+    }
+    ~StageTimer() {
+        if (!c->trace || marks.empty()) return;
+        cudaEventSynchronize(marks.back().second);
+        fprintf(stderr, "[swb trace] %s:", what);
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, " %s=%.3fms", marks[i].first, ms);
+        }
+        float tot = 0;
+        cudaEventElapsedTime(&tot, marks.front().second, marks.back().second);
+        fprintf(stderr, " total=%.3fms\n", tot);
+        for (auto& m : marks) cudaEventDestroy(m.second);
+    }
+};
 
 // implemented in ntt.cu
 int ntt_build_tables(swb_ctx* c);

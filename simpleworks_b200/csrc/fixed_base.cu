@@ -9,6 +9,7 @@
 // Device schedule: a 32 x 256 table of d * 2^(8o) * g (8-bit windows, affine), then one thread
 // per power: beta^i by square-and-multiply, 32 mixed additions, one Fermat inversion to affine.
 // Affine results are unique, so they equal arkworks' bit for bit.
+#define SWB_FP_NOINLINE_MUL
 #include "ctx.hpp"
 #include "g1.cuh"
 

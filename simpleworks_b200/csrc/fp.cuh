@@ -242,8 +242,15 @@ struct Fp {
         return r;
     }
 #endif
+#if defined(__CUDACC__)
+    // out-of-line copy for translation units that define SWB_FP_NOINLINE_MUL: cold kernels (bucket
+    // reduction, table building) call the product instead of inlining ~300 instructions per use
+    static __device__ __noinline__ Fp mul_outlined(const Fp& a, const Fp& b) { return mul_limb_schedule(a, b); }
+#endif
     friend SWB_HD Fp operator*(const Fp& a, const Fp& b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(SWB_FP_NOINLINE_MUL)
+        return mul_outlined(a, b);
+#elif defined(__CUDA_ARCH__)
         return mul_limb_schedule(a, b);
 #else
         return mul_host64(a, b);

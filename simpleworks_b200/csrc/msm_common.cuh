@@ -1,0 +1,48 @@
+// Shared declarations of the MSM translation units (see msm.cu for the pipeline overview).
+#pragma once
+#include "ctx.hpp"
+#include "g1.cuh"
+
+namespace swb {
+
+constexpr int MSM_MAX_WINDOWS = 128;
+constexpr int MSM_RED_THREADS = 256;   // segments per window in the bucket reduction
+constexpr int MSM_GATHER_INLINE = 32;  // buckets with more partial sums than this go to the block-wide path
+
+struct MsmPlan {
+    size_t n;            // points
+    int cb;              // window bits
+    int nwin;            // windows
+    uint32_t B;          // buckets per window = 2^(cb-1)
+    uint32_t nb;         // total buckets
+    size_t total;        // n * nwin (bucket, point) pairs
+    uint32_t range_len;  // sorted positions per accumulation thread
+    uint32_t nranges;    // ceil(total / range_len)
+    uint32_t pcap;       // capacity of the partial-sum list (nranges + nb)
+};
+
+struct MsmBuffers {
+    uint32_t* keys;      // [2][total]
+    uint32_t* vals;      // [2][total]
+    uint32_t* range_cnt; // [nranges + 1] runs per range, then its exclusive scan
+    uint32_t* range_off; // [nranges + 1]
+    uint32_t* pkey;      // [pcap] bucket id of each partial sum
+    uint32_t* pstart;    // [nb + 1] first partial of each bucket
+    uint32_t* heavy;     // [1 + nb] counter + list of buckets with many partial sums
+    G1Xyzz* partial;     // [pcap]
+    G1Xyzz* buckets;     // [nb]
+    G1Xyzz* seg;         // [2][MSM_RED_THREADS * nwin]
+    G1Xyzz* wins;        // [MSM_MAX_WINDOWS]
+};
+
+// msm_sort.cu: digits, sort, per-range run counts and their scan
+int msm_launch_digits_sort(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
+                           const uint32_t** sorted_keys, const uint32_t** sorted_vals);
+// msm_accumulate.cu: one thread per range of sorted pairs -> partial sums
+int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,
+                          const uint32_t* sorted_vals, const Fq* bases);
+// msm_reduce.cu: partial sums -> buckets -> window sums
+int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf);
+int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf);
+
+}  // namespace swb

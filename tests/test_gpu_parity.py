@@ -156,12 +156,14 @@ def test_msm_golden(be, golden_dir):
         bases = be.load_bases(O.affine_from_points(pts))
         scalars = O.ints_to_limbs([hx(s) for s in case["scalars"]], 4)
         want = None if case["result"] is None else (hx(case["result"][0]), hx(case["result"][1]))
-        for c in (0, 3, 7):
-            be.set_msm_window_bits(c)
-            assert O.points_from_jacobian(be.msm(bases, scalars))[0] == want, (case["tag"], c)
-            assert O.points_from_jacobian(be.msm(bases, be.to_device(scalars)))[0] == want
-        be.set_msm_window_bits(0)
-        bases.free()
+        try:
+            for c in (0, 3, 7):
+                be.set_msm_window_bits(c)
+                assert O.points_from_jacobian(be.msm(bases, scalars))[0] == want, (case["tag"], c)
+                assert O.points_from_jacobian(be.msm(bases, be.to_device(scalars)))[0] == want
+        finally:
+            be.set_msm_window_bits(0)
+            bases.free()
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 1000, 1 << 14, 1 << 16])
