@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""Headline benchmark of the Marlin-prover hot path on B200: BLS12-377 G1 variable-base MSM.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 26] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one multi-scalar multiplication sum_i s_i * P_i over 2^log_n synthetic (scalar, SRS
+power) pairs -- the operation kzg10::commit / open spends its time in under simpleworks'
+generate_proof (reference src/marlin/mod.rs:70-77) -- BASELINE.json configs[4] at its largest
+single-GPU size.  configs[1..3] (the example circuits) need ark-r1cs-std synthesis, which cannot
+run without a Rust toolchain; the full-proof metric follows once the host prover
+lands.
+
+  value        points/s, whole job, scalars already resident in HBM, CUDA events, max over ranks
+  e2e          the same through the host-buffer ABI call swb_msm_g1 (pinned host scalars -> H2D ->
+               MSM -> result back on the host), every step
+  roofline     dominant kernel k_msm_accumulate: algorithmic limb-products (32x32->64 multiply-
+               accumulates) per launch / its CUDA-event time, against the IMAD.WIDE issue rate
+               measured on this GPU in the same run (the MSM is integer-pipe bound, not HBM bound;
+               the HBM figure is reported beside it as the sanity counter BASELINE.md asks for)
+  cpu_baseline the C restatement of arkworks' VariableBaseMSM (oracle/, OpenMP over windows like
+               rayon) on a bounded sample, host cores of this box            [N = 1, rank 0 only]
+
+N > 1 (strong scaling): the same 2^log_n problem, bases and scalars sharded by contiguous index
+range across ranks, one NCCL all-gather of the 144-byte partial results, final sum on every rank.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BETA_SEED = 0x5357423230300001          # "SWB200" || 1 : SRS trapdoor of the synthetic bases
+LIMB_PRODUCTS_PER_FQ_MUL = 288          # 12x12 product + 12x12 Montgomery reduction, 32-bit limbs
+FQ_MUL_PER_MIXED_ADD = 10               # XYZZ madd-2008-s: 8M + 2S
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def synth_scalars_host(n: int, seed: int) -> np.ndarray:
+    """uniform canonical scalars below 2^252 (< r), (n,4) uint64"""
+    rs = np.random.Generator(np.random.PCG64(seed))
+    a = rs.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    return a
+
+
+def msm_plan(n: int) -> tuple[int, int]:
+    """mirror of pick_window() in csrc/msm.cu: window bits and number of windows"""
+    lg = max(0, (n - 1).bit_length())
+    c = min(16, max(4, lg - 6))
+    return c, (254 + c - 1) // c
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port of arkworks' VariableBaseMSM, all host threads)."""
+    from oracle import pyoracle as O
+    from simpleworks_b200 import _gen
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log_s = min(args.log_n, args.cpu_log_n)
+    n = 1 << log_s
+    g = O.g1_mul(O.g1_generator(), 1)
+    bases = O.fixed_base_powers(g, _gen.fr_mont(BETA_SEED), n)
+    scalars = synth_scalars_host(n, 1234)
+    threads = O.num_threads()
+    for _ in range(args.warmup):
+        O.msm_variable_base(bases, scalars)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.msm_variable_base(bases, scalars)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt
+    line = {
+        "impl": "reference", "metric": "msm_g1_points_per_sec", "value": val, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32-limbs(Fq 377-bit, Fr 253-bit)",
+        "data": "synthetic",
+        "config": {"workload": f"bls12-377 G1 variable-base MSM 2^{args.log_n}", "sample": f"2^{log_s} points per step"},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": f"2^{log_s}-point MSM (first 2^{log_s} SRS powers, uniform scalars), "
+                                   "arkworks-equivalent C (not arkworks: no Rust toolchain in this image)"},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="swb200", choices=["swb200", "reference"])
+    ap.add_argument("--log-n", type=int, default=int(os.environ.get("SWB_BENCH_LOG_N", "26")))
+    ap.add_argument("--cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_CPU_LOG_N", "20")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from simpleworks_b200 import _gen, build
+    from simpleworks_b200.binding import Backend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libswb200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    be = Backend(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+
+    n_total = 1 << args.log_n
+    assert n_total % world == 0
+    n_local = n_total // world
+    lo = rank * n_local
+    c_bits, n_win = msm_plan(n_local)
+
+    # ---- synthetic inputs: bases = beta^i * G (the SRS shape), this rank's index slice ---------
+    # slice [lo, lo+n_local) of the powers = powers of beta applied to g' = beta^lo * G
+    g = _gen.g1_generator_jacobian()
+    beta = _gen.fr_mont(BETA_SEED)
+    if lo:
+        r_mod = _gen.R_MOD
+        shift = pow(BETA_SEED, lo, r_mod)
+        tmp = be.bases_from_powers(g, _gen.fr_mont(shift), 2)          # [G, beta^lo * G]
+        g = np.concatenate([be.export_bases(tmp, 1, 1)[:, :12], _gen.fq_mont(1)], axis=1)
+        tmp.free()
+    t0 = time.perf_counter()
+    bases = be.bases_from_powers(g, beta, n_local)
+    t_bases = time.perf_counter() - t0
+    scalars_host = synth_scalars_host(n_local, 1234 + rank)
+    pinned = torch.from_numpy(scalars_host.view(np.int64)).pin_memory()
+    scalars_dev = pinned.to(dev)
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)   # written between steps to flush L2
+
+    def combine(partial: np.ndarray) -> np.ndarray:
+        if world == 1:
+            return partial
+        t = torch.from_numpy(partial.view(np.int64).copy()).to(dev)
+        allp = torch.empty((world, 18), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allp, t.reshape(1, 18))
+        return be.g1_sum(allp.cpu().numpy().view(np.uint64))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing ("value") ------------------------------------------------------------
+    be.profile(True)
+    result = None
+    for _ in range(args.warmup):
+        result = combine(be.msm(bases, scalars_dev))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = be.launch_count()
+    step_ms, acc_ms, stage_sum = [], [], {}
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        result = combine(be.msm(bases, scalars_dev))
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        st = be.last_stages()
+        acc_ms.append(st.get("accumulate", float("nan")))
+        for k, v in st.items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
+    launches = be.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_local = sum(step_ms) / 1e3
+    tt = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_total = float(tt.item())
+    ms_per_step = t_total * 1e3 / args.steps
+    value = n_total * args.steps / t_total
+
+    # ---- end-to-end through the host-buffer ABI ----------------------------------------------------
+    host_view = pinned.numpy().view(np.uint64)
+    for _ in range(min(args.warmup, 2)):
+        combine(be.msm(bases, host_view))
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        result_e2e = combine(be.msm(bases, host_view))
+        e1.record()
+        barrier()
+        e2e_ms.append(e0.elapsed_time(e1))
+    assert np.array_equal(result_e2e, result), "host-buffer and resident paths disagree"
+    te = torch.tensor([sum(e2e_ms) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * args.steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    imad_wide = be.measure_imad_peak("wide", 20000)           # IMAD.WIDE/s = limb-products/s the pipe can issue
+    imad_lo = be.measure_imad_peak("lo", 20000)
+    mont = be.measure_mul_peak("fq", 4000)
+    acc_avg_s = (sum(acc_ms) / len(acc_ms)) / 1e3
+    alg_lp = float(n_local) * n_win * FQ_MUL_PER_MIXED_ADD * LIMB_PRODUCTS_PER_FQ_MUL
+    achieved = alg_lp / acc_avg_s
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback"
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tr.get(f"k_msm_accumulate@2^{args.log_n}/{world}")
+    except Exception:
+        pass
+    alg_bytes = 128.0 * n_local
+    roofline = {
+        "kernel": "k_msm_accumulate", "bound": "int32 IMAD pipe (not hbm/tensor: 377-bit modular arithmetic)",
+        "achieved": achieved / 1e12, "peak": imad_wide / 1e12, "unit": "T limb-products/s", "frac": achieved / imad_wide,
+        "peak_source": "IMAD.WIDE issue rate measured in this run (swb_measure_imad_peak)",
+        "frac_of_montgomery_loop_peak": achieved / mont["limb_products_per_s"],
+        "imad32_peak_tops": imad_lo / 1e12, "montgomery_loop_peak_tlps": mont["limb_products_per_s"] / 1e12,
+        "kernel_ms": acc_avg_s * 1e3, "kernel_share_of_step": acc_avg_s * 1e3 / ms_per_step,
+        "algorithmic_units": f"{n_local} points x {n_win} windows (c={c_bits}) x 10 Fq mul x 288 limb-products",
+        "traffic": traffic,
+        "hbm": {"bound": "hbm", "achieved": alg_bytes / (ms_per_step / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "note": "128 B/point algorithmic over the whole step; sanity counter only"},
+    }
+
+    # ---- CPU baseline on a bounded sample ---------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle as O
+        log_s = min(args.log_n, args.cpu_log_n)
+        ns = 1 << log_s
+        hb = be.export_bases(bases, 0, ns)
+        hs = np.ascontiguousarray(scalars_host[:ns])
+        t0 = time.perf_counter()
+        ref = O.msm_variable_base(hb, hs)
+        dt = time.perf_counter() - t0
+        got = be.msm(bases, hs)
+        assert np.array_equal(O.g1_to_affine(got), O.g1_to_affine(ref)), "GPU MSM != CPU oracle on the baseline sample"
+        cpu = {"value": ns / dt, "unit": "points/s", "cores": O.num_threads(), "kind": "port",
+               "sample": f"2^{log_s}-point MSM, first 2^{log_s} of the same bases/scalars, {dt:.2f} s; "
+                         "arkworks-equivalent C port (oracle/), result checked equal to the GPU's"}
+
+    extra = {}
+    if not args.no_extra:
+        # NTT throughput beside the headline (BASELINE.json metric names both)
+        log_ntt = 24
+        x = torch.randint(-2 ** 63, 2 ** 63 - 1, (1 << log_ntt, 4), dtype=torch.int64, device=dev)
+        x[:, 3] &= 0x0FFFFFFFFFFFFFFF
+        for _ in range(3):
+            be.ntt_(x, log_ntt)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            be.ntt_(x, log_ntt)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sum(ts) / len(ts)
+        nn = 1 << log_ntt
+        extra["ntt_fr"] = {
+            "log_n": log_ntt, "ms": ms, "elems_per_s": nn / ms * 1e3,
+            "hbm_gbs_algorithmic": 64.0 * nn / ms / 1e6, "hbm_frac": 64.0 * nn / ms / 1e6 / hbm_peak,
+            "limb_products_per_s": (nn / 2) * log_ntt * 128 / ms * 1e3,
+            "int_frac": (nn / 2) * log_ntt * 128 / ms * 1e3 / imad_wide, "passes": be.last_stages()}
+        extra["setup_bases_s"] = t_bases
+        extra["stages_ms_avg"] = {k: v / args.steps for k, v in stage_sum.items()}
+
+    line = {
+        "metric": "msm_g1_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32-limbs(Fq 377-bit, Fr 253-bit)", "data": "synthetic",
+        "config": {"workload": f"bls12-377 G1 variable-base MSM 2^{args.log_n}", "points_per_gpu": n_local,
+                   "window_bits": c_bits, "windows": n_win, "scalars": "uniform < 2^252",
+                   "bases": "SRS powers beta^i*G generated on device", "parallelism": f"index-sharded x{world}",
+                   "l2": "256 MiB buffer rewritten between steps; inputs (>= 2 GiB) exceed L2"},
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_local) * 32 * world,
+                "d2h_bytes_per_step": (144 + n_win * 192) * world, "ms_per_step": sum(e2e_ms) / len(e2e_ms)},
+        "gpu_launches": int(launches), "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

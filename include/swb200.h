@@ -82,10 +82,25 @@ int  swb_fr_batch_inverse_dev(swb_ctx*, swb_fr* v_dev, size_t n);
  * and field multiplications/s measured with CUDA events. */
 int  swb_measure_mul_peak(swb_ctx*, int field, int iters, double* limb_products_per_s, double* muls_per_s);
 
+/* Raw integer-pipe probe: independent multiply-accumulate chains held in registers.
+ * kind 0: 32-bit IMAD (mad.lo.u32), kind 1: 32x32+64 IMAD.WIDE (mad.wide.u32).  ops/s by CUDA events. */
+int  swb_measure_imad_peak(swb_ctx*, int kind, int iters, double* ops_per_s);
+
+/* ---- per-stage timings of the last MSM / NTT call (CUDA events on the context's stream) ----- */
+/* enable != 0 makes every later call record events at its stage boundaries (a few microseconds);
+ * swb_profile_last copies up to cap (name, milliseconds) pairs of the most recent call.         */
+int  swb_profile_enable(swb_ctx*, int enable);
+int  swb_profile_last(swb_ctx*, const char** names, double* ms, int cap, int* count);
+
 /* ---- G1 bases (SRS / committer key): upload once, keep resident --------------------------- */
 int  swb_bases_load(swb_ctx*, const swb_g1_affine* host, size_t n, swb_bases** out);
 /* same from a device buffer of swb_g1_affine (104-byte records) */
 int  swb_bases_load_dev(swb_ctx*, const swb_g1_affine* dev, size_t n, swb_bases** out);
+/* bases[i] = beta^i * g generated on the device and kept there (KZG10::setup's powers_of_g without
+ * the round trip through the host) */
+int  swb_bases_from_powers(swb_ctx*, const swb_g1_jacobian* g_host, const swb_fr* beta_host, size_t n, swb_bases** out);
+/* copy n bases starting at offset back to the host as 104-byte GroupAffine records */
+int  swb_bases_export(swb_ctx*, const swb_bases*, size_t offset, size_t n, swb_g1_affine* out_host);
 size_t swb_bases_len(const swb_bases*);
 void swb_bases_free(swb_bases*);
 

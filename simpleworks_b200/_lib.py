@@ -19,8 +19,9 @@ SYMBOLS = [
     "swb_launch_count", "swb_dev_alloc", "swb_dev_free", "swb_h2d", "swb_d2h",
     "swb_fr_mul_vec_dev", "swb_fr_add_vec_dev", "swb_fr_sub_vec_dev",
     "swb_fq_mul_vec_dev", "swb_fq_add_vec_dev", "swb_fq_sub_vec_dev",
-    "swb_fr_batch_inverse_dev", "swb_measure_mul_peak",
-    "swb_bases_load", "swb_bases_load_dev", "swb_bases_len", "swb_bases_free",
+    "swb_fr_batch_inverse_dev", "swb_measure_mul_peak", "swb_measure_imad_peak",
+    "swb_profile_enable", "swb_profile_last",
+    "swb_bases_load", "swb_bases_load_dev", "swb_bases_from_powers", "swb_bases_export", "swb_bases_len", "swb_bases_free",
     "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_set_window_bits", "swb_g1_sum_jacobian",
     "swb_fixed_base_powers",
     "swb_ntt_fr", "swb_ntt_fr_dev", "swb_ntt_fr_batch_dev",
@@ -59,6 +60,11 @@ def load() -> ctypes.CDLL:
         "swb_d2h": (i32, [vp, vp, vp, sz]),
         "swb_fr_batch_inverse_dev": (i32, [vp, vp, sz]),
         "swb_measure_mul_peak": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+        "swb_measure_imad_peak": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_double)]),
+        "swb_profile_enable": (i32, [vp, i32]),
+        "swb_profile_last": (i32, [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double), i32, ctypes.POINTER(i32)]),
+        "swb_bases_from_powers": (i32, [vp, vp, vp, sz, pvp]),
+        "swb_bases_export": (i32, [vp, vp, sz, sz, vp]),
         "swb_bases_load": (i32, [vp, vp, sz, pvp]),
         "swb_bases_load_dev": (i32, [vp, vp, sz, pvp]),
         "swb_bases_len": (sz, [vp]),

@@ -133,7 +133,34 @@ class Backend:
         self._check(self._lib.swb_measure_mul_peak(self._h, 0 if field == "fr" else 1, iters, ctypes.byref(lps), ctypes.byref(mps)))
         return {"limb_products_per_s": lps.value, "muls_per_s": mps.value}
 
+    def measure_imad_peak(self, kind: str = "wide", iters: int = 20000) -> float:
+        ops = ctypes.c_double()
+        self._check(self._lib.swb_measure_imad_peak(self._h, 1 if kind == "wide" else 0, iters, ctypes.byref(ops)))
+        return ops.value
+
+    def profile(self, on: bool = True):
+        self._check(self._lib.swb_profile_enable(self._h, int(on)))
+
+    def last_stages(self) -> dict:
+        names = (ctypes.c_char_p * 16)()
+        ms = (ctypes.c_double * 16)()
+        cnt = ctypes.c_int()
+        self._check(self._lib.swb_profile_last(self._h, names, ms, 16, ctypes.byref(cnt)))
+        return {names[i].decode(): ms[i] for i in range(cnt.value)}
+
     # ---- MSM ---------------------------------------------------------------------------
+    def bases_from_powers(self, g_jac: np.ndarray, beta: np.ndarray, n: int) -> Bases:
+        """Resident bases[i] = beta^i * g generated on the device (no host round trip)."""
+        h = ctypes.c_void_p()
+        self._check(self._lib.swb_bases_from_powers(self._h, _np_ptr(np.ascontiguousarray(g_jac.reshape(1, 18))),
+                                                    _np_ptr(np.ascontiguousarray(beta.reshape(1, 4))), n, ctypes.byref(h)))
+        return Bases(self, h, n)
+
+    def export_bases(self, bases: Bases, offset: int, n: int) -> np.ndarray:
+        out = np.zeros((n, 13), dtype=np.uint64)
+        self._check(self._lib.swb_bases_export(self._h, bases._h, offset, n, _np_ptr(out)))
+        return out
+
     def load_bases(self, affine) -> Bases:
         """affine: (n,13) uint64 numpy array of 104-byte GroupAffine records, or the same as a
         CUDA int64 tensor."""

@@ -162,6 +162,25 @@ int swb_device_info(swb_ctx* c, int* sm_count, int* cc_major, int* cc_minor, siz
 
 uint64_t swb_launch_count(const swb_ctx* c) { return c ? c->launches : 0; }
 
+int swb_profile_enable(swb_ctx* c, int enable) {
+    if (!c) return SWB_EARG;
+    c->profile = enable ? 1 : 0;
+    return SWB_OK;
+}
+
+int swb_profile_last(swb_ctx* c, const char** names, double* ms, int cap, int* count) {
+    if (!c || !count) return SWB_EARG;
+    int k = 0;
+    for (auto& st : c->last_stages) {
+        if (k >= cap) break;
+        if (names) names[k] = st.first;
+        if (ms) ms[k] = st.second;
+        k++;
+    }
+    *count = k;
+    return SWB_OK;
+}
+
 int swb_dev_alloc(swb_ctx* c, size_t bytes, void** out) {
     if (!c || !out) return SWB_EARG;
     SWB_CUDA(c, cudaSetDevice(c->device));

@@ -22,6 +22,8 @@ struct swb_ctx {
     uint64_t launches = 0;
     int msm_window_override = 0;
     int trace = 0;            // SWB_TRACE=1: per-stage CUDA-event timings on stderr
+    int profile = 0;          // swb_profile_enable: keep the last call's stage timings
+    std::vector<std::pair<const char*, double>> last_stages;
 
     // NTT tables (device): three levels of 1024 powers of the 2^30-th root of unity, and of the
     // coset generator 22 and its inverse.  Built by one kernel at swb_init.
@@ -75,24 +77,27 @@ struct StageTimer {
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
     StageTimer(swb_ctx* ctx, const char* w) : c(ctx), what(w) { mark("start"); }
     void mark(const char* name) {
-        if (!c->trace) return;
+        if (!c->trace && !c->profile) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, c->stream);
         marks.emplace_back(name, e);
     }
     ~StageTimer() {
-        if (!c->trace || marks.empty()) return;
+        if ((!c->trace && !c->profile) || marks.empty()) return;
         cudaEventSynchronize(marks.back().second);
-        fprintf(stderr, "[swb trace] %s:", what);
+        c->last_stages.clear();
+        if (c->trace) fprintf(stderr, "[swb trace] %s:", what);
         for (size_t i = 1; i < marks.size(); i++) {
             float ms = 0;
             cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
-            fprintf(stderr, " %s=%.3fms", marks[i].first, ms);
+            c->last_stages.emplace_back(marks[i].first, (double)ms);
+            if (c->trace) fprintf(stderr, " %s=%.3fms", marks[i].first, ms);
         }
         float tot = 0;
         cudaEventElapsedTime(&tot, marks.front().second, marks.back().second);
-        fprintf(stderr, " total=%.3fms\n", tot);
+        c->last_stages.emplace_back("total", (double)tot);
+        if (c->trace) fprintf(stderr, " total=%.3fms\n", tot);
         for (auto& m : marks) cudaEventDestroy(m.second);
     }
 };

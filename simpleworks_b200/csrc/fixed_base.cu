@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(128) k_fb_table(G1Aff* __restrict__ table, con
     table[e] = xyzz_to_affine(acc);
 }
 
+// RECORD = 104: ABI GroupAffine records (x | y | infinity flag); RECORD = 96: resident base layout
+template <int RECORD>
 __global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, const G1Aff* __restrict__ table, Fr beta, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -59,12 +61,27 @@ __global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, co
         }
     }
     const G1Aff a = xyzz_to_affine(acc);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(out + i * 104);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + i * RECORD);
 #pragma unroll
     for (int k = 0; k < 12; k++) dst[k] = a.x.l[k];
 #pragma unroll
     for (int k = 0; k < 12; k++) dst[12 + k] = a.y.l[k];
-    dst[24] = a.is_identity() ? 1u : 0u;
+    if (RECORD == 104) {
+        dst[24] = a.is_identity() ? 1u : 0u;
+        dst[25] = 0u;
+    }
+}
+
+// resident 96-byte records -> 104-byte ABI records
+__global__ void k_bases_export(uint8_t* __restrict__ out, const Fq* __restrict__ xy, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(xy + 2 * i);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + i * 104);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 24; k++) { dst[k] = src[k]; any |= src[k]; }
+    dst[24] = any ? 0u : 1u;
     dst[25] = 0u;
 }
 
@@ -72,11 +89,8 @@ __global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, co
 
 using namespace swb;
 
-extern "C" int swb_fixed_base_powers(swb_ctx* c, const swb_g1_jacobian* g_host, const swb_fr* beta_host, size_t n,
-                                     swb_g1_affine* out_host) {
-    if (!c) return SWB_EARG;
-    SWB_REQUIRE(c, g_host && beta_host && (n == 0 || out_host), "fixed_base_powers: NULL argument");
-    if (n == 0) return SWB_OK;
+// builds the window table for g on the device; returns it in *table
+static int fb_prepare(swb_ctx* c, const swb_g1_jacobian* g_host, const swb_fr* beta_host, G1Aff** table, Fr* beta) {
     SWB_CUDA(c, cudaSetDevice(c->device));
     // host: 2^k * g for k < 256, affine
     G1Xyzz p;
@@ -101,17 +115,77 @@ extern "C" int swb_fixed_base_powers(swb_ctx* c, const swb_g1_jacobian* g_host, 
         }
         p = p.dbl();
     }
-    Fr beta;
-    memcpy(beta.l, beta_host->l, 32);
+    memcpy(beta->l, beta_host->l, 32);
     G1Aff* d_pow2 = (G1Aff*)get_scratch(c, "fb_pow2", sizeof(G1Aff) * pow2.size());
     G1Aff* d_table = (G1Aff*)get_scratch(c, "fb_table", sizeof(G1Aff) * FB_OUTER * 256);
-    uint8_t* d_out = (uint8_t*)get_scratch(c, "fb_out", n * 104);
-    if (!d_pow2 || !d_table || !d_out) return SWB_ENOMEM;
+    if (!d_pow2 || !d_table) return SWB_ENOMEM;
     SWB_CUDA(c, cudaMemcpyAsync(d_pow2, pow2.data(), sizeof(G1Aff) * pow2.size(), cudaMemcpyHostToDevice, c->stream));
+    SWB_CUDA(c, cudaStreamSynchronize(c->stream));   // pow2 is a local
     k_fb_table<<<FB_OUTER * 256 / 128, 128, 0, c->stream>>>(d_table, d_pow2);
     SWB_LAUNCH_CHECK(c, "k_fb_table");
-    k_fb_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_out, d_table, beta, n);
+    *table = d_table;
+    return SWB_OK;
+}
+
+extern "C" int swb_fixed_base_powers(swb_ctx* c, const swb_g1_jacobian* g_host, const swb_fr* beta_host, size_t n,
+                                     swb_g1_affine* out_host) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, g_host && beta_host && (n == 0 || out_host), "fixed_base_powers: NULL argument");
+    if (n == 0) return SWB_OK;
+    G1Aff* d_table = nullptr;
+    Fr beta;
+    int rc = fb_prepare(c, g_host, beta_host, &d_table, &beta);
+    if (rc != SWB_OK) return rc;
+    uint8_t* d_out = (uint8_t*)get_scratch(c, "fb_out", n * 104);
+    if (!d_out) return SWB_ENOMEM;
+    k_fb_powers<104><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_out, d_table, beta, n);
     SWB_LAUNCH_CHECK(c, "k_fb_powers");
+    SWB_CUDA(c, cudaMemcpyAsync(out_host, d_out, n * 104, cudaMemcpyDeviceToHost, c->stream));
+    SWB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SWB_OK;
+}
+
+extern "C" int swb_bases_from_powers(swb_ctx* c, const swb_g1_jacobian* g_host, const swb_fr* beta_host, size_t n,
+                                     swb_bases** out) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, g_host && beta_host && out, "bases_from_powers: NULL argument");
+    G1Aff* d_table = nullptr;
+    Fr beta;
+    int rc = fb_prepare(c, g_host, beta_host, &d_table, &beta);
+    if (rc != SWB_OK) return rc;
+    swb_bases* b = new swb_bases();
+    b->ctx = c;
+    b->n = n;
+    cudaError_t e = cudaMalloc(&b->xy, (n ? n : 1) * 96);
+    if (e != cudaSuccess) {
+        delete b;
+        return set_err(c, SWB_ENOMEM, "bases_from_powers: cudaMalloc(%zu) failed: %s", n * 96, cudaGetErrorString(e));
+    }
+    if (n) {
+        k_fb_powers<96><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((uint8_t*)b->xy, d_table, beta, n);
+        c->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(b->xy);
+            delete b;
+            return cuda_fail(c, e, "k_fb_powers");
+        }
+    }
+    *out = b;
+    return SWB_OK;
+}
+
+extern "C" int swb_bases_export(swb_ctx* c, const swb_bases* b, size_t offset, size_t n, swb_g1_affine* out_host) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, b && (n == 0 || out_host), "bases_export: NULL argument");
+    SWB_REQUIRE(c, offset <= b->n && n <= b->n - offset, "bases_export: range exceeds the loaded bases");
+    if (n == 0) return SWB_OK;
+    SWB_CUDA(c, cudaSetDevice(c->device));
+    uint8_t* d_out = (uint8_t*)get_scratch(c, "fb_out", n * 104);
+    if (!d_out) return SWB_ENOMEM;
+    k_bases_export<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_out, b->xy + 2 * offset, n);
+    SWB_LAUNCH_CHECK(c, "k_bases_export");
     SWB_CUDA(c, cudaMemcpyAsync(out_host, d_out, n * 104, cudaMemcpyDeviceToHost, c->stream));
     SWB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SWB_OK;

@@ -257,6 +257,8 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
         for (uint32_t i = 0; i < log_n; i++) scale = scale * ti;
     }
     uint32_t log_m = log_n;   // trailing block size before pass s
+    static const char* const pass_names[8] = {"pass0", "pass1", "pass2", "pass3", "pass4", "pass5", "pass6", "pass7"};
+    StageTimer tm(c, "ntt");
     for (int s = 0; s < m; s++) {
         NttPass p{};
         p.log_n = log_n;
@@ -295,6 +297,7 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
         dim3 grid((unsigned)blocks, (unsigned)batch);
         k_ntt_pass<<<grid, NTT_THREADS, smem, c->stream>>>(p, c->tw_root, coset_tab);
         SWB_LAUNCH_CHECK(c, "k_ntt_pass");
+        tm.mark(pass_names[s]);
     }
     return SWB_OK;
 }

@@ -78,6 +78,55 @@ __global__ void __launch_bounds__(256) k_mul_peak(F* __restrict__ out, const F* 
     if (acc.l[0] == 0x12345678u && acc.l[1] == 0x9abcdef0u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// raw pipe probes: 16 independent accumulators per thread, no memory traffic
+template <int KIND>
+__global__ void __launch_bounds__(256) k_imad_peak(uint64_t* __restrict__ out, uint32_t a0, uint32_t b0, int iters) {
+    uint64_t acc[16];
+    uint32_t a = a0 + threadIdx.x, b = b0 ^ (blockIdx.x * 2654435761u);
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = (uint64_t)k * 0x9e3779b97f4a7c15ull + threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (KIND == 1) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+            } else {
+                uint32_t lo = (uint32_t)acc[k];
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
+                acc[k] = lo;
+            }
+        }
+    }
+    uint64_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) x ^= acc[k];
+    if (x == 0x1234567812345678ull) out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+template <int KIND>
+static int measure_imad(swb_ctx* c, int iters, double* ops) {
+    SWB_CUDA(c, cudaSetDevice(c->device));
+    const int threads = 256, blocks = c->sm_count * 8;
+    uint64_t* buf = (uint64_t*)get_scratch(c, "peak", sizeof(uint64_t) * (size_t)threads * blocks + 4096);
+    if (!buf) return SWB_ENOMEM;
+    cudaEvent_t e0, e1;
+    SWB_CUDA(c, cudaEventCreate(&e0));
+    SWB_CUDA(c, cudaEventCreate(&e1));
+    k_imad_peak<KIND><<<blocks, threads, 0, c->stream>>>(buf, 12345u, 678910u, iters / 4 + 1);
+    c->launches++;
+    SWB_CUDA(c, cudaEventRecord(e0, c->stream));
+    k_imad_peak<KIND><<<blocks, threads, 0, c->stream>>>(buf, 12345u, 678910u, iters);
+    SWB_LAUNCH_CHECK(c, "k_imad_peak");
+    SWB_CUDA(c, cudaEventRecord(e1, c->stream));
+    SWB_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    SWB_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops = (double)threads * blocks * (double)iters * 16.0 / (ms * 1e-3);
+    return SWB_OK;
+}
+
 template <class F, int ILP>
 static int measure_peak(swb_ctx* c, int iters, double* lps, double* mps) {
     SWB_CUDA(c, cudaSetDevice(c->device));
@@ -137,6 +186,12 @@ int swb_fr_batch_inverse_dev(swb_ctx* c, swb_fr* v, size_t n) {
     k_fr_batch_inverse<CH><<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>((Fr*)v, n);
     SWB_LAUNCH_CHECK(c, "k_fr_batch_inverse");
     return SWB_OK;
+}
+
+int swb_measure_imad_peak(swb_ctx* c, int kind, int iters, double* ops) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, iters > 0 && ops && (kind == 0 || kind == 1), "measure_imad_peak: bad arguments");
+    return kind == 0 ? measure_imad<0>(c, iters, ops) : measure_imad<1>(c, iters, ops);
 }
 
 int swb_measure_mul_peak(swb_ctx* c, int field, int iters, double* lps, double* mps) {
