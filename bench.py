@@ -17,8 +17,9 @@ lands.
                MSM -> result back on the host), every step
   roofline     dominant kernel k_msm_accumulate: algorithmic limb-products (32x32->64 multiply-
                accumulates) per launch / its CUDA-event time, against the IMAD.WIDE issue rate
-               measured on this GPU in the same run (the MSM is integer-pipe bound, not HBM bound;
-               the HBM figure is reported beside it as the sanity counter BASELINE.md asks for)
+               measured on this GPU in the same run by a register-only probe (the MSM is
+               integer-pipe bound, not HBM bound; the HBM figure is reported beside it as the
+               sanity counter BASELINE.md asks for)
   cpu_baseline the C restatement of arkworks' VariableBaseMSM (oracle/, OpenMP over windows like
                rayon) on a bounded sample, host cores of this box            [N = 1, rank 0 only]
 
@@ -165,7 +166,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from simpleworks_b200 import _gen, build
+    from simpleworks_b200 import _gen, binding, build
     from simpleworks_b200.binding import Backend
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,12 +209,7 @@ def main():
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)   # written between steps to flush L2
 
     def combine(partial: np.ndarray) -> np.ndarray:
-        if world == 1:
-            return partial
-        t = torch.from_numpy(partial.view(np.int64).copy()).to(dev)
-        allp = torch.empty((world, 18), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allp, t.reshape(1, 18))
-        return be.g1_sum(allp.cpu().numpy().view(np.uint64))
+        return binding.combine_partials(partial, world, dev)
 
     def barrier():
         if world > 1:
@@ -281,7 +277,9 @@ def main():
         return
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
-    imad_wide = be.measure_imad_peak("wide", 20000)           # IMAD.WIDE/s = limb-products/s the pipe can issue
+    # limb-products/s the integer pipe can issue: IMAD.WIDE.U32 (one 32x32+64 per instruction),
+    # plain and in carry chains -- both half the 32-bit IMAD rate on B200 (4 heavy-pipe cycles)
+    imad_wide = max(be.measure_imad_peak("wide", 20000), be.measure_imad_peak("wide_carry", 20000))
     imad_lo = be.measure_imad_peak("lo", 20000)
     mont = be.measure_mul_peak("fq", 4000)
     acc_avg_s = (sum(acc_ms) / len(acc_ms)) / 1e3

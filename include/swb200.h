@@ -83,7 +83,9 @@ int  swb_fr_batch_inverse_dev(swb_ctx*, swb_fr* v_dev, size_t n);
 int  swb_measure_mul_peak(swb_ctx*, int field, int iters, double* limb_products_per_s, double* muls_per_s);
 
 /* Raw integer-pipe probe: independent multiply-accumulate chains held in registers.
- * kind 0: 32-bit IMAD (mad.lo.u32), kind 1: 32x32+64 IMAD.WIDE (mad.wide.u32).  ops/s by CUDA events. */
+ * kind 0: 32-bit IMAD (mad.lo.u32), kind 1: 32x32+64 IMAD.WIDE (mad.wide.u32), kind 2: IMAD.WIDE.U32.X
+ * carry chains of length four (mad.lo.cc / madc.hi.cc pairs), kind 3: IADD3.X add-with-carry
+ * chains (ALU pipe).  ops/s by CUDA events. */
 int  swb_measure_imad_peak(swb_ctx*, int kind, int iters, double* ops_per_s);
 
 /* ---- per-stage timings of the last MSM / NTT call (CUDA events on the context's stream) ----- */
@@ -117,7 +119,8 @@ int  swb_msm_g1_fr_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* 
                        swb_g1_jacobian* out_host);
 /* window width override for tuning/tests (0 = automatic) */
 int  swb_msm_set_window_bits(swb_ctx*, int c);
-/* sum of n Jacobian points on the host side of the ABI (combining per-GPU partial MSMs) */
+/* sum of n Jacobian points on the host side of the ABI (combining per-GPU partial MSMs); pure
+ * host arithmetic, ctx may be NULL */
 int  swb_g1_sum_jacobian(swb_ctx*, const swb_g1_jacobian* pts_host, size_t n, swb_g1_jacobian* out_host);
 
 /* ---- fixed-base: out[i] = beta^i * g, i < n, affine (KZG10::setup powers_of_g) ------------ */

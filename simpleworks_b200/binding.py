@@ -28,6 +28,41 @@ def _np_ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def g1_sum(jac: np.ndarray) -> np.ndarray:
+    """Sum of Jacobian points (n,18) -> (1,18) with Z = 1; host arithmetic inside libswb200, needs
+    no GPU.  This is how per-GPU partial MSM results are combined."""
+    lib = _lib.load()
+    jac = np.ascontiguousarray(jac.reshape(-1, 18))
+    out = np.zeros((1, 18), dtype=np.uint64)
+    rc = lib.swb_g1_sum_jacobian(None, _np_ptr(jac), jac.shape[0], _np_ptr(out))
+    if rc != 0:
+        raise SwbError(f"swb_g1_sum_jacobian failed [{rc}]")
+    return out
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous index slice of rank `rank` when n (scalar, base) pairs are split over `world`
+    GPUs; the remainder goes to the first ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def combine_partials(partial: np.ndarray, world: int, device=None) -> np.ndarray:
+    """All-gather the 144-byte partial MSM results of every rank (torch.distributed, NCCL on GPU
+    tensors or gloo on CPU tensors) and add them up; every rank returns the full result."""
+    if world == 1:
+        return partial
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(partial.view(np.int64).copy()).reshape(1, 18)
+    if device is not None:
+        t = t.to(device)
+    allp = torch.empty((world, 18), dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(allp, t)
+    return g1_sum(allp.cpu().numpy().view(np.uint64))
+
+
 class Bases:
     """Device-resident G1 bases (SRS powers / committer key)."""
 
@@ -130,12 +165,12 @@ class Backend:
 
     def measure_mul_peak(self, field: str = "fq", iters: int = 2000) -> dict:
         lps, mps = ctypes.c_double(), ctypes.c_double()
-        self._check(self._lib.swb_measure_mul_peak(self._h, 0 if field == "fr" else 1, iters, ctypes.byref(lps), ctypes.byref(mps)))
+        self._check(self._lib.swb_measure_mul_peak(self._h, {"fr": 0, "fq": 1}[field], iters, ctypes.byref(lps), ctypes.byref(mps)))
         return {"limb_products_per_s": lps.value, "muls_per_s": mps.value}
 
     def measure_imad_peak(self, kind: str = "wide", iters: int = 20000) -> float:
         ops = ctypes.c_double()
-        self._check(self._lib.swb_measure_imad_peak(self._h, 1 if kind == "wide" else 0, iters, ctypes.byref(ops)))
+        self._check(self._lib.swb_measure_imad_peak(self._h, {"lo": 0, "wide": 1, "wide_carry": 2, "addc": 3}[kind], iters, ctypes.byref(ops)))
         return ops.value
 
     def profile(self, on: bool = True):
@@ -192,10 +227,7 @@ class Backend:
         return out
 
     def g1_sum(self, jac: np.ndarray) -> np.ndarray:
-        jac = np.ascontiguousarray(jac.reshape(-1, 18))
-        out = np.zeros((1, 18), dtype=np.uint64)
-        self._check(self._lib.swb_g1_sum_jacobian(self._h, _np_ptr(jac), jac.shape[0], _np_ptr(out)))
-        return out
+        return g1_sum(jac)
 
     def fixed_base_powers(self, g_jac: np.ndarray, beta: np.ndarray, n: int) -> np.ndarray:
         out = np.zeros((n, 13), dtype=np.uint64)

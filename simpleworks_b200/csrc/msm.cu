@@ -241,8 +241,8 @@ int swb_msm_g1(swb_ctx* c, const swb_bases* b, size_t offset, const swb_bigint25
 }
 
 int swb_g1_sum_jacobian(swb_ctx* c, const swb_g1_jacobian* pts, size_t n, swb_g1_jacobian* out) {
-    if (!c) return SWB_EARG;
-    SWB_REQUIRE(c, out && (n == 0 || pts), "g1_sum: NULL argument");
+    // pure host arithmetic: the context is only used for error text and may be NULL
+    if (!(out && (n == 0 || pts))) return set_err(c, SWB_EARG, "%s", "g1_sum: NULL argument");
     G1Xyzz acc = G1Xyzz::identity();
     for (size_t i = 0; i < n; i++) {
         G1Xyzz p;

@@ -75,32 +75,59 @@ __global__ void __launch_bounds__(256) k_mul_peak(F* __restrict__ out, const F* 
 #pragma unroll
     for (int k = 0; k < ILP; k++) acc = acc + y[k];
     // keep the result observable without meaningful memory traffic
-    if (acc.l[0] == 0x12345678u && acc.l[1] == 0x9abcdef0u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (acc.l[0] == 0x12345678u && acc.l[1] == 0x1abcdef0u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
 // raw pipe probes: 16 independent accumulators per thread, no memory traffic
 template <int KIND>
 __global__ void __launch_bounds__(256) k_imad_peak(uint64_t* __restrict__ out, uint32_t a0, uint32_t b0, int iters) {
-    uint64_t acc[16];
+    uint32_t lo[16], hi[16];
     uint32_t a = a0 + threadIdx.x, b = b0 ^ (blockIdx.x * 2654435761u);
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = (uint64_t)k * 0x9e3779b97f4a7c15ull + threadIdx.x;
+    for (int k = 0; k < 16; k++) {
+        lo[k] = k * 0x9e3779b9u + threadIdx.x;
+        hi[k] = k * 0x7f4a7c15u + blockIdx.x;
+    }
     for (int it = 0; it < iters; it++) {
+        if (KIND == 2) {
+            // carry chains of four IMAD.WIDE.U32.X each, the shape the Montgomery rows have
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (KIND == 1) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
-            } else {
-                uint32_t lo = (uint32_t)acc[k];
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
-                acc[k] = lo;
+            for (int k = 0; k < 16; k += 4) {
+                asm volatile(
+                    "mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1;"
+                    "madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.cc.u32 %3, %8, %9, %3;"
+                    "madc.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5;"
+                    "madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
+                    : "+r"(lo[k]), "+r"(hi[k]), "+r"(lo[k + 1]), "+r"(hi[k + 1]), "+r"(lo[k + 2]), "+r"(hi[k + 2]),
+                      "+r"(lo[k + 3]), "+r"(hi[k + 3])
+                    : "r"(a), "r"(b));
             }
+        } else if (KIND == 1) {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                // multiplicand = the accumulator's own low word, so the product cannot be hoisted
+                asm volatile("{.reg .u64 t; mov.b64 t, {%0, %1}; mad.wide.u32 t, %0, %2, t; mov.b64 {%0, %1}, t;}"
+                             : "+r"(lo[k]), "+r"(hi[k]) : "r"(b));
+        } else if (KIND == 3) {
+            // add-with-carry chains of four (IADD3.X), the ALU-pipe side of the arithmetic
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+                asm volatile(
+                    "add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %8; addc.cc.u32 %3, %3, %9;"
+                    "addc.cc.u32 %4, %4, %8; addc.cc.u32 %5, %5, %9; addc.cc.u32 %6, %6, %8; addc.u32 %7, %7, %9;"
+                    : "+r"(lo[k]), "+r"(hi[k]), "+r"(lo[k + 1]), "+r"(hi[k + 1]), "+r"(lo[k + 2]), "+r"(hi[k + 2]),
+                      "+r"(lo[k + 3]), "+r"(hi[k + 3])
+                    : "r"(a), "r"(b));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo[k]) : "r"(b), "r"(a));
         }
     }
-    uint64_t x = 0;
+    uint32_t x = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) x ^= acc[k];
-    if (x == 0x1234567812345678ull) out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    for (int k = 0; k < 16; k++) x ^= lo[k] ^ hi[k];
+    if (x == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 
 template <int KIND>
@@ -123,11 +150,11 @@ static int measure_imad(swb_ctx* c, int iters, double* ops) {
     SWB_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *ops = (double)threads * blocks * (double)iters * 16.0 / (ms * 1e-3);
+    *ops = (double)threads * blocks * (double)iters * (KIND == 3 ? 32.0 : 16.0) / (ms * 1e-3);
     return SWB_OK;
 }
 
-template <class F, int ILP>
+template <class F, int ILP, int LIMBS32>
 static int measure_peak(swb_ctx* c, int iters, double* lps, double* mps) {
     SWB_CUDA(c, cudaSetDevice(c->device));
     const int threads = 256;
@@ -139,6 +166,7 @@ static int measure_peak(swb_ctx* c, int iters, double* lps, double* mps) {
     for (int i = 0; i < 32; i++) {
         h[i] = F::one();
         for (int j = 0; j <= i; j++) h[i] = h[i] + h[i] + F::one();
+        h[i] = h[i] * h[i] * h[i];
     }
     F* seed = buf + (size_t)threads * blocks;
     SWB_CUDA(c, cudaMemcpyAsync(seed, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
@@ -157,7 +185,7 @@ static int measure_peak(swb_ctx* c, int iters, double* lps, double* mps) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     double muls = (double)threads * blocks * (double)iters * ILP * 2.0;
-    double per_mul = 2.0 * F::N * F::N;
+    double per_mul = 2.0 * LIMBS32 * LIMBS32;    // counted in 32-bit-limb products whatever the representation
     if (mps) *mps = muls / (ms * 1e-3);
     if (lps) *lps = muls * per_mul / (ms * 1e-3);
     return SWB_OK;
@@ -190,14 +218,19 @@ int swb_fr_batch_inverse_dev(swb_ctx* c, swb_fr* v, size_t n) {
 
 int swb_measure_imad_peak(swb_ctx* c, int kind, int iters, double* ops) {
     if (!c) return SWB_EARG;
-    SWB_REQUIRE(c, iters > 0 && ops && (kind == 0 || kind == 1), "measure_imad_peak: bad arguments");
-    return kind == 0 ? measure_imad<0>(c, iters, ops) : measure_imad<1>(c, iters, ops);
+    SWB_REQUIRE(c, iters > 0 && ops && kind >= 0 && kind <= 3, "measure_imad_peak: bad arguments");
+    switch (kind) {
+        case 0: return measure_imad<0>(c, iters, ops);
+        case 1: return measure_imad<1>(c, iters, ops);
+        case 2: return measure_imad<2>(c, iters, ops);
+        default: return measure_imad<3>(c, iters, ops);
+    }
 }
 
 int swb_measure_mul_peak(swb_ctx* c, int field, int iters, double* lps, double* mps) {
     if (!c) return SWB_EARG;
     SWB_REQUIRE(c, iters > 0 && (field == 0 || field == 1), "measure_mul_peak: bad arguments");
-    return field == 0 ? measure_peak<Fr, 4>(c, iters, lps, mps) : measure_peak<Fq, 2>(c, iters, lps, mps);
+    return field == 0 ? measure_peak<Fr, 4, 8>(c, iters, lps, mps) : measure_peak<Fq, 2, 12>(c, iters, lps, mps);
 }
 
 }  // extern "C"

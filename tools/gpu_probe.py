@@ -40,6 +40,8 @@ def main():
     out["device"] = be.device_info()
     for f in ("fr", "fq"):
         out["peak_" + f] = be.measure_mul_peak(f, 4000)
+    for k in ("lo", "wide", "wide_carry", "addc"):
+        out["imad_" + k] = be.measure_imad_peak(k, 20000)
     print(json.dumps(out), flush=True)
     sizes = [int(s) for s in os.environ.get("NTT_LOGS", "16,20,22,24").split(",")]
     for log_n in sizes:
