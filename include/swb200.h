@@ -117,6 +117,9 @@ int  swb_msm_g1_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_bigint2
  * into_repr() on the host today */
 int  swb_msm_g1_fr_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scalars_dev, size_t n,
                        swb_g1_jacobian* out_host);
+/* the same with host-resident Montgomery scalars (what a polynomial's coefficient vector is) */
+int  swb_msm_g1_fr(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scalars_host, size_t n,
+                   swb_g1_jacobian* out_host);
 /* window width override for tuning/tests (0 = automatic) */
 int  swb_msm_set_window_bits(swb_ctx*, int c);
 /* sum of n Jacobian points on the host side of the ABI (combining per-GPU partial MSMs); pure
@@ -133,6 +136,55 @@ int  swb_fixed_base_powers(swb_ctx*, const swb_g1_jacobian* g_host, const swb_fr
 int  swb_ntt_fr(swb_ctx*, swb_fr* inout_host, uint32_t log_n, int inverse, int coset);
 int  swb_ntt_fr_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, int inverse, int coset);
 int  swb_ntt_fr_batch_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, size_t batch, int inverse, int coset);
+
+/* ==== protocol level: simpleworks::marlin (reference src/marlin/mod.rs:33-94, serialization.rs) ====
+ * Opaque handles and canonical bytes.  Host orchestration in C++ inside the library; all NTTs,
+ * MSMs and fixed-base tables run on the GPU of the context.
+ *   swb_rng_test_rng             generate_rand()  = ark_std::test_rng()            mod.rs:33-35
+ *   swb_marlin_universal_setup   generate_universal_srs                             mod.rs:45-55
+ *   swb_marlin_index             generate_proving_and_verifying_keys               mod.rs:88-94
+ *   swb_marlin_prove             generate_proof + serialize_proof    mod.rs:70-77, serialization.rs:5
+ *   swb_marlin_verify            deserialize_proof + verify_proof    serialization.rs:14, mod.rs:79-86
+ * swb_r1cs is what a ConstraintSystemRef exposes (to_matrices() + assignments; mod.rs:16): columns
+ * are instance variables first (column 0 = the constant one), then witnesses.  public_inputs for
+ * verify exclude the leading one, as in simple_merkle_tree.rs:133-143.
+ * An unsatisfied instance makes swb_marlin_prove fail (the reference panics through a
+ * debug_assert, examples/schnorr-signature/main.rs:214-217).
+ * NOTE: verification checks the KZG opening equations in G1 with the setup trapdoor instead of the
+ * pairing product (the pairing tower is not implemented); keys from this library are a test
+ * harness, not deployable verifier keys. */
+typedef struct swb_rng swb_rng;
+typedef struct swb_r1cs swb_r1cs;
+typedef struct swb_srs swb_srs;
+typedef struct swb_pk swb_pk;
+typedef struct swb_vk swb_vk;
+
+swb_rng* swb_rng_test_rng(void);
+uint64_t swb_rng_next_u64(swb_rng*);
+void swb_rng_free(swb_rng*);
+
+swb_r1cs* swb_r1cs_new(size_t num_instance /* incl. the constant one */, size_t num_witness);
+/* built-in instances: 0 manual-constraints (v0 = a, v1 = b), 1 test-circuit UInt8 equality
+ * (v0, v1), 2 synthetic chain x_i * x_{i+1} = x_{i+2} with `size` constraints (v0, v1 = seeds) */
+swb_r1cs* swb_r1cs_builtin(int kind, size_t size, uint64_t v0, uint64_t v1);
+int  swb_r1cs_add_constraint(swb_r1cs*, const swb_fr* a_coef, const uint32_t* a_col, size_t na,
+                             const swb_fr* b_coef, const uint32_t* b_col, size_t nb,
+                             const swb_fr* c_coef, const uint32_t* c_col, size_t nc);
+int  swb_r1cs_set_assignment(swb_r1cs*, const swb_fr* instance, size_t ni, const swb_fr* witness, size_t nw);
+int  swb_r1cs_is_satisfied(const swb_r1cs*);
+void swb_r1cs_free(swb_r1cs*);
+
+int  swb_marlin_universal_setup(swb_ctx*, size_t num_constraints, size_t num_variables, size_t num_non_zero,
+                                swb_rng*, swb_srs** out);
+size_t swb_srs_max_degree(const swb_srs*);
+void swb_srs_free(swb_srs*);
+int  swb_marlin_index(swb_ctx*, const swb_srs*, const swb_r1cs*, swb_pk** pk, swb_vk** vk);
+void swb_pk_free(swb_pk*);
+void swb_vk_free(swb_vk*);
+int  swb_marlin_prove(swb_ctx*, const swb_pk*, const swb_r1cs* cs_with_assignment, swb_rng*, uint8_t** proof, size_t* len);
+int  swb_marlin_verify(swb_ctx*, const swb_vk*, const swb_fr* public_inputs, size_t n, const uint8_t* proof, size_t len,
+                       int* ok);
+void swb_bytes_free(uint8_t*);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,145 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU arm of the Marlin protocol, for parity and the CPU baseline.
+ *
+ * Instantiates the protocol templates of simpleworks_b200/csrc/marlin/ (shared source: transcript,
+ * AHP rounds, KZG bookkeeping) with a CPU engine built on the C restatement of arkworks'
+ * operators in oracle.c (orc_ntt, orc_msm_variable_base, orc_fixed_base_powers).  What this arm
+ * pins: the CUDA engine (NTT / MSM / fixed-base kernels) yields byte-identical proofs to the CPU
+ * operators under the same RNG streams.  The protocol logic itself is shared and therefore checked
+ * by completeness / tamper tests, not by this arm.  PARITY UNPINNED against real arkworks.
+ * The product library never links this file.
+ */
+#include <omp.h>
+
+#include "marlin/c_api_impl.hpp"
+#include "swb_oracle.h"
+
+using namespace swb;
+using namespace swb::marlin;
+
+namespace {
+
+struct CpuBases {
+    std::vector<g1_affine_t> pts;
+};
+
+struct CpuEngine {
+    void ntt(Fr* v, uint32_t log_n, bool inverse, bool coset) { orc_ntt(reinterpret_cast<fr_t*>(v), log_n, inverse, coset, 0); }
+    void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n) {
+        auto* b = new CpuBases();
+        b->pts.resize(n);
+        g1_jac_t gj;
+        memset(&gj, 0, sizeof gj);
+        if (g.infinity) orc_g1_jac_zero(&gj);
+        else {
+            memcpy(gj.x.l, g.x.l, 48);
+            memcpy(gj.y.l, g.y.l, 48);
+            Fq one = Fq::one();
+            memcpy(gj.z.l, one.l, 48);
+        }
+        fr_t bt;
+        memcpy(bt.l, beta.l, 32);
+        orc_fixed_base_powers(b->pts.data(), &gj, &bt, n, 0);
+        return b;
+    }
+    void export_bases(void* h, size_t offset, size_t n, G1Point* out) {
+        auto* b = static_cast<CpuBases*>(h);
+        for (size_t i = 0; i < n; i++) {
+            const g1_affine_t& a = b->pts[offset + i];
+            out[i].infinity = a.infinity != 0;
+            memcpy(out[i].x.l, a.x.l, 48);
+            memcpy(out[i].y.l, a.y.l, 48);
+        }
+    }
+    void free_bases(void* h) { delete static_cast<CpuBases*>(h); }
+    G1Point msm(void* h, size_t offset, const Fr* scalars_mont, size_t n) {
+        auto* b = static_cast<CpuBases*>(h);
+        std::vector<big256_t> sc(n);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n; i++) orc_fr_to_canon(&sc[i], reinterpret_cast<const fr_t*>(&scalars_mont[i]));
+        g1_jac_t out;
+        orc_msm_variable_base(&out, b->pts.data() + offset, sc.data(), n, 0);
+        g1_affine_t a;
+        orc_g1_to_affine(&a, &out);
+        G1Point p = G1Point::identity();
+        if (!a.infinity) {
+            p.infinity = false;
+            memcpy(p.x.l, a.x.l, 48);
+            memcpy(p.y.l, a.y.l, 48);
+        }
+        return p;
+    }
+};
+
+CpuEngine g_engine;
+thread_local std::string g_err;
+using Api = MarlinApi<CpuEngine>;
+
+}  // namespace
+
+extern "C" {
+
+const char* orc_marlin_last_error() { return g_err.c_str(); }
+
+void* orc_rng_test_rng() {
+    auto* h = new RngHandle();
+    h->rng = test_rng();
+    return h;
+}
+void* orc_rng_from_seed(const uint8_t seed[32], int rounds) {
+    auto* h = new RngHandle();
+    h->rng = ChaChaRng(seed, rounds);
+    return h;
+}
+uint64_t orc_rng_next_u64(void* h) { return static_cast<RngHandle*>(h)->rng.next_u64(); }
+uint32_t orc_rng_next_u32(void* h) { return static_cast<RngHandle*>(h)->rng.next_u32(); }
+void orc_rng_fr_rand(void* h, uint64_t out[4]) {
+    Fr r = rand_fr(static_cast<RngHandle*>(h)->rng);
+    memcpy(out, r.l, 32);
+}
+void orc_rng_free(void* h) { delete static_cast<RngHandle*>(h); }
+void orc_blake2s(const uint8_t* in, size_t n, uint8_t out[32]) {
+    Blake2s s;
+    s.update(in, n);
+    s.finalize(out);
+}
+
+void* orc_r1cs_new(size_t ni, size_t nw) { return r1cs_new(ni, nw); }
+void* orc_r1cs_builtin(int kind, size_t size, uint64_t v0, uint64_t v1) { return r1cs_builtin(kind, size, v0, v1); }
+int orc_r1cs_add_constraint(void* h, const uint64_t* ac, const uint32_t* ai, size_t na, const uint64_t* bc, const uint32_t* bi,
+                            size_t nb, const uint64_t* cc, const uint32_t* ci, size_t nc) {
+    return r1cs_add_constraint(static_cast<R1csHandle*>(h), ac, ai, na, bc, bi, nb, cc, ci, nc);
+}
+int orc_r1cs_set_assignment(void* h, const uint64_t* inst, size_t ni, const uint64_t* wit, size_t nw) {
+    return r1cs_set_assignment(static_cast<R1csHandle*>(h), inst, ni, wit, nw);
+}
+int orc_r1cs_is_satisfied(void* h) { return static_cast<R1csHandle*>(h)->cs.is_satisfied() ? 1 : 0; }
+void orc_r1cs_free(void* h) { delete static_cast<R1csHandle*>(h); }
+
+int orc_marlin_universal_setup(size_t nc, size_t nv, size_t nnz, void* rng, void** srs) {
+    SrsHandle<CpuEngine>* out = nullptr;
+    int rc = Api::setup(g_engine, nc, nv, nnz, static_cast<RngHandle*>(rng), &out, &g_err);
+    *srs = out;
+    return rc;
+}
+size_t orc_srs_max_degree(void* srs) { return static_cast<SrsHandle<CpuEngine>*>(srs)->srs->max_degree; }
+void orc_srs_free(void* srs) { delete static_cast<SrsHandle<CpuEngine>*>(srs); }
+int orc_marlin_index(void* srs, void* cs, void** pk, void** vk) {
+    PkHandle<CpuEngine>* p = nullptr;
+    VkHandle<CpuEngine>* v = nullptr;
+    int rc = Api::index(g_engine, static_cast<SrsHandle<CpuEngine>*>(srs), static_cast<R1csHandle*>(cs), &p, &v, &g_err);
+    *pk = p;
+    *vk = v;
+    return rc;
+}
+void orc_pk_free(void* pk) { delete static_cast<PkHandle<CpuEngine>*>(pk); }
+void orc_vk_free(void* vk) { delete static_cast<VkHandle<CpuEngine>*>(vk); }
+int orc_marlin_prove(void* pk, void* cs, void* rng, uint8_t** bytes, size_t* len) {
+    return Api::prove(g_engine, static_cast<PkHandle<CpuEngine>*>(pk), static_cast<R1csHandle*>(cs), static_cast<RngHandle*>(rng),
+                      bytes, len, &g_err);
+}
+int orc_marlin_verify(void* vk, const uint64_t* pi, size_t n, const uint8_t* proof, size_t len, int* ok) {
+    return Api::verify(static_cast<VkHandle<CpuEngine>*>(vk), pi, n, proof, len, ok, &g_err);
+}
+void orc_bytes_free(uint8_t* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""ctypes binding of oracle/liboracle_marlin.so (CPU arm of the Marlin protocol layer).
+TEST INFRASTRUCTURE ONLY -- see marlin_oracle.cpp."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+        L = ctypes.CDLL(os.path.join(_HERE, "liboracle_marlin.so"))
+        vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        L.orc_marlin_last_error.restype = ctypes.c_char_p
+        for name in ("orc_rng_test_rng", "orc_r1cs_new", "orc_r1cs_builtin", "orc_rng_from_seed"):
+            getattr(L, name).restype = vp
+        L.orc_rng_from_seed.argtypes = [ctypes.c_char_p, i32]
+        L.orc_rng_next_u64.restype = ctypes.c_uint64
+        L.orc_rng_next_u64.argtypes = [vp]
+        L.orc_rng_next_u32.restype = ctypes.c_uint32
+        L.orc_rng_next_u32.argtypes = [vp]
+        L.orc_rng_fr_rand.argtypes = [vp, vp]
+        L.orc_rng_free.argtypes = [vp]
+        L.orc_blake2s.argtypes = [ctypes.c_char_p, sz, ctypes.c_char_p]
+        L.orc_r1cs_new.argtypes = [sz, sz]
+        L.orc_r1cs_builtin.argtypes = [i32, sz, ctypes.c_uint64, ctypes.c_uint64]
+        L.orc_r1cs_add_constraint.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, vp, sz]
+        L.orc_r1cs_set_assignment.argtypes = [vp, vp, sz, vp, sz]
+        L.orc_r1cs_is_satisfied.argtypes = [vp]
+        L.orc_r1cs_free.argtypes = [vp]
+        L.orc_marlin_universal_setup.argtypes = [sz, sz, sz, vp, ctypes.POINTER(vp)]
+        L.orc_srs_max_degree.restype = sz
+        L.orc_srs_max_degree.argtypes = [vp]
+        L.orc_srs_free.argtypes = [vp]
+        L.orc_marlin_index.argtypes = [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+        L.orc_pk_free.argtypes = [vp]
+        L.orc_vk_free.argtypes = [vp]
+        L.orc_marlin_prove.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]
+        L.orc_marlin_verify.argtypes = [vp, vp, sz, ctypes.c_char_p, sz, ctypes.POINTER(i32)]
+        L.orc_bytes_free.argtypes = [ctypes.POINTER(ctypes.c_uint8)]
+        _LIB = L
+    return _LIB
+
+
+class MarlinError(RuntimeError):
+    pass
+
+
+def _chk(rc):
+    if rc != 0:
+        raise MarlinError(lib().orc_marlin_last_error().decode())
+
+
+class Rng:
+    def __init__(self, seed: bytes | None = None, rounds: int = 20):
+        self.h = ctypes.c_void_p(lib().orc_rng_test_rng() if seed is None else lib().orc_rng_from_seed(seed, rounds))
+
+    def next_u64(self):
+        return lib().orc_rng_next_u64(self.h)
+
+    def next_u32(self):
+        return lib().orc_rng_next_u32(self.h)
+
+    def fr_rand_mont(self) -> int:
+        out = np.zeros(4, dtype=np.uint64)
+        lib().orc_rng_fr_rand(self.h, out.ctypes.data_as(ctypes.c_void_p))
+        return sum(int(v) << (64 * i) for i, v in enumerate(out))
+
+
+def blake2s(data: bytes) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    lib().orc_blake2s(data, len(data), out)
+    return out.raw
+
+
+class R1cs:
+    """kind: 'manual' (examples/manual-constraints.rs), 'uint8_eq' (examples/test-circuit.rs),
+    'chain' (synthetic x_i * x_{i+1} = x_{i+2})."""
+
+    def __init__(self, kind: str, size: int = 0, v0: int = 1, v1: int = 1):
+        k = {"manual": 0, "uint8_eq": 1, "chain": 2}[kind]
+        self.h = ctypes.c_void_p(lib().orc_r1cs_builtin(k, size, v0, v1))
+
+    def is_satisfied(self) -> bool:
+        return bool(lib().orc_r1cs_is_satisfied(self.h))
+
+
+def universal_setup(nc, nv, nnz, rng: Rng):
+    srs = ctypes.c_void_p()
+    _chk(lib().orc_marlin_universal_setup(nc, nv, nnz, rng.h, ctypes.byref(srs)))
+    return srs
+
+
+def index(srs, cs: R1cs):
+    pk, vk = ctypes.c_void_p(), ctypes.c_void_p()
+    _chk(lib().orc_marlin_index(srs, cs.h, ctypes.byref(pk), ctypes.byref(vk)))
+    return pk, vk
+
+
+def prove(pk, cs: R1cs, rng: Rng) -> bytes:
+    p = ctypes.POINTER(ctypes.c_uint8)()
+    n = ctypes.c_size_t()
+    _chk(lib().orc_marlin_prove(pk, cs.h, rng.h, ctypes.byref(p), ctypes.byref(n)))
+    out = bytes(p[:n.value])
+    lib().orc_bytes_free(p)
+    return out
+
+
+def verify(vk, public_inputs_mont: np.ndarray, proof: bytes) -> bool:
+    ok = ctypes.c_int()
+    pi = np.ascontiguousarray(public_inputs_mont, dtype=np.uint64).reshape(-1, 4)
+    _chk(lib().orc_marlin_verify(vk, pi.ctypes.data_as(ctypes.c_void_p), pi.shape[0], proof, len(proof), ctypes.byref(ok)))
+    return bool(ok.value)

@@ -22,9 +22,14 @@ SYMBOLS = [
     "swb_fr_batch_inverse_dev", "swb_measure_mul_peak", "swb_measure_imad_peak",
     "swb_profile_enable", "swb_profile_last",
     "swb_bases_load", "swb_bases_load_dev", "swb_bases_from_powers", "swb_bases_export", "swb_bases_len", "swb_bases_free",
-    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_set_window_bits", "swb_g1_sum_jacobian",
+    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_g1_fr", "swb_msm_set_window_bits", "swb_g1_sum_jacobian",
     "swb_fixed_base_powers",
     "swb_ntt_fr", "swb_ntt_fr_dev", "swb_ntt_fr_batch_dev",
+    "swb_rng_test_rng", "swb_rng_next_u64", "swb_rng_free",
+    "swb_r1cs_new", "swb_r1cs_builtin", "swb_r1cs_add_constraint", "swb_r1cs_set_assignment", "swb_r1cs_is_satisfied",
+    "swb_r1cs_free",
+    "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
+    "swb_marlin_prove", "swb_marlin_verify", "swb_bytes_free",
 ]
 
 _lib = None
@@ -72,6 +77,25 @@ def load() -> ctypes.CDLL:
         "swb_msm_g1": (i32, [vp, vp, sz, vp, sz, vp]),
         "swb_msm_g1_dev": (i32, [vp, vp, sz, vp, sz, vp]),
         "swb_msm_g1_fr_dev": (i32, [vp, vp, sz, vp, sz, vp]),
+        "swb_msm_g1_fr": (i32, [vp, vp, sz, vp, sz, vp]),
+        "swb_rng_test_rng": (vp, []),
+        "swb_rng_next_u64": (ctypes.c_uint64, [vp]),
+        "swb_rng_free": (None, [vp]),
+        "swb_r1cs_new": (vp, [sz, sz]),
+        "swb_r1cs_builtin": (vp, [i32, sz, ctypes.c_uint64, ctypes.c_uint64]),
+        "swb_r1cs_add_constraint": (i32, [vp, vp, vp, sz, vp, vp, sz, vp, vp, sz]),
+        "swb_r1cs_set_assignment": (i32, [vp, vp, sz, vp, sz]),
+        "swb_r1cs_is_satisfied": (i32, [vp]),
+        "swb_r1cs_free": (None, [vp]),
+        "swb_marlin_universal_setup": (i32, [vp, sz, sz, sz, vp, pvp]),
+        "swb_srs_max_degree": (sz, [vp]),
+        "swb_srs_free": (None, [vp]),
+        "swb_marlin_index": (i32, [vp, vp, vp, pvp, pvp]),
+        "swb_pk_free": (None, [vp]),
+        "swb_vk_free": (None, [vp]),
+        "swb_marlin_prove": (i32, [vp, vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
+        "swb_marlin_verify": (i32, [vp, vp, vp, sz, ctypes.c_char_p, sz, ctypes.POINTER(i32)]),
+        "swb_bytes_free": (None, [ctypes.POINTER(ctypes.c_uint8)]),
         "swb_msm_set_window_bits": (i32, [vp, i32]),
         "swb_g1_sum_jacobian": (i32, [vp, vp, sz, vp]),
         "swb_fixed_base_powers": (i32, [vp, vp, vp, sz, vp]),

@@ -254,3 +254,111 @@ class Backend:
     def ifft_in_place(self, v, log_n): return self.ntt_(v, log_n, True, False)
     def coset_fft_in_place(self, v, log_n): return self.ntt_(v, log_n, False, True)
     def coset_ifft_in_place(self, v, log_n): return self.ntt_(v, log_n, True, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# protocol level: simpleworks::marlin (reference src/marlin/mod.rs:33-94)
+# ------------------------------------------------------------------------------------------------
+class Rng:
+    """generate_rand(): ark_std::test_rng() (reference src/marlin/mod.rs:33-35)."""
+
+    def __init__(self):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p(self._lib.swb_rng_test_rng())
+
+    def next_u64(self) -> int:
+        return int(self._lib.swb_rng_next_u64(self._h))
+
+    def __del__(self):
+        try:
+            self._lib.swb_rng_free(self._h)
+        except Exception:
+            pass
+
+
+class ConstraintSystem:
+    """What a ConstraintSystemRef exposes to Marlin (src/marlin/mod.rs:16): sparse A, B, C rows and
+    the instance / witness assignments.  Columns: instance first (0 = constant one), then witness."""
+
+    BUILTIN = {"manual-constraints": 0, "test-circuit": 1, "mul-chain": 2}
+
+    def __init__(self, handle):
+        self._lib = _lib.load()
+        self._h = handle
+
+    @classmethod
+    def builtin(cls, name: str, size: int = 0, v0: int = 1, v1: int = 1) -> "ConstraintSystem":
+        lib = _lib.load()
+        h = lib.swb_r1cs_builtin(cls.BUILTIN[name], size, v0, v1)
+        if not h:
+            raise SwbError("unknown built-in circuit")
+        return cls(ctypes.c_void_p(h))
+
+    @classmethod
+    def new(cls, num_instance: int, num_witness: int) -> "ConstraintSystem":
+        return cls(ctypes.c_void_p(_lib.load().swb_r1cs_new(num_instance, num_witness)))
+
+    def enforce_constraint(self, a, b, c):
+        """a, b, c: lists of (coefficient as (4,) uint64 Montgomery array, column)."""
+        def pack(lc):
+            coef = np.ascontiguousarray(np.stack([x for x, _ in lc]) if lc else np.zeros((0, 4), np.uint64), dtype=np.uint64)
+            col = np.ascontiguousarray([j for _, j in lc], dtype=np.uint32)
+            return coef, col
+        (ac, ai), (bc, bi), (cc, ci) = pack(a), pack(b), pack(c)
+        rc = self._lib.swb_r1cs_add_constraint(self._h, ac.ctypes.data, ai.ctypes.data, len(a), bc.ctypes.data, bi.ctypes.data, len(b),
+                                               cc.ctypes.data, ci.ctypes.data, len(c))
+        if rc:
+            raise SwbError("enforce_constraint: column out of range")
+
+    def assign(self, instance: np.ndarray, witness: np.ndarray):
+        instance = np.ascontiguousarray(instance, dtype=np.uint64).reshape(-1, 4)
+        witness = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)
+        if self._lib.swb_r1cs_set_assignment(self._h, instance.ctypes.data, instance.shape[0], witness.ctypes.data, witness.shape[0]):
+            raise SwbError("assign: wrong number of instance / witness values")
+
+    def is_satisfied(self) -> bool:
+        return bool(self._lib.swb_r1cs_is_satisfied(self._h))
+
+    def __del__(self):
+        try:
+            self._lib.swb_r1cs_free(self._h)
+        except Exception:
+            pass
+
+
+class Marlin:
+    """generate_universal_srs / generate_proving_and_verifying_keys / generate_proof / verify_proof
+    (reference src/marlin/mod.rs:45-94) on one GPU."""
+
+    def __init__(self, backend: Backend):
+        self.be = backend
+        self._lib = backend._lib
+
+    def generate_universal_srs(self, num_constraints: int, num_variables: int, num_non_zero: int, rng: Rng):
+        srs = ctypes.c_void_p()
+        self.be._check(self._lib.swb_marlin_universal_setup(self.be._h, num_constraints, num_variables, num_non_zero, rng._h,
+                                                            ctypes.byref(srs)))
+        return srs
+
+    def srs_max_degree(self, srs) -> int:
+        return int(self._lib.swb_srs_max_degree(srs))
+
+    def generate_proving_and_verifying_keys(self, srs, cs: ConstraintSystem):
+        pk, vk = ctypes.c_void_p(), ctypes.c_void_p()
+        self.be._check(self._lib.swb_marlin_index(self.be._h, srs, cs._h, ctypes.byref(pk), ctypes.byref(vk)))
+        return pk, vk
+
+    def generate_proof(self, cs: ConstraintSystem, pk, rng: Rng) -> bytes:
+        """returns serialize_proof(generate_proof(...)) (src/marlin/serialization.rs:5)"""
+        p = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self.be._check(self._lib.swb_marlin_prove(self.be._h, pk, cs._h, rng._h, ctypes.byref(p), ctypes.byref(n)))
+        out = bytes(p[:n.value])
+        self._lib.swb_bytes_free(p)
+        return out
+
+    def verify_proof(self, vk, public_inputs: np.ndarray, proof: bytes) -> bool:
+        ok = ctypes.c_int()
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+        self.be._check(self._lib.swb_marlin_verify(self.be._h, vk, pi.ctypes.data, pi.shape[0], proof, len(proof), ctypes.byref(ok)))
+        return bool(ok.value)

@@ -16,12 +16,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
-SOURCES = ["ctx.cu", "vec.cu", "ntt.cu", "msm.cu", "msm_sort.cu", "msm_accumulate.cu", "msm_reduce.cu", "fixed_base.cu"]
+SOURCES = ["ctx.cu", "vec.cu", "ntt.cu", "msm.cu", "msm_sort.cu", "msm_accumulate.cu", "msm_reduce.cu", "fixed_base.cu", "marlin_abi.cu"]
 LIB_SO = os.path.join(HERE, "libswb200.so")
 LIB_A = os.path.join(HERE, "libswb200.a")
 NVCC = os.environ.get("SWB_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC,-fopenmp", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
 
 
 def _deps():
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB_SO, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+    r = subprocess.run([NVCC, "-shared", "-o", LIB_SO, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread", "-lgomp"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -1,0 +1,819 @@
+// Marlin over BLS12-377 with the MarlinKZG10 polynomial commitment: universal setup, index, prove,
+// verify -- the protocol that simpleworks::marlin wraps (reference src/marlin/mod.rs:45-94:
+// MarlinInst::{universal_setup, index_from_constraint_system, prove_from_constraint_system, verify}).
+// The protocol code itself lives in the un-vendored crates ark-marlin (Entropy1729 fork, Cargo.toml:
+// 29-30) and ark-poly-commit ^0.3 (Cargo.toml:22); this is a restatement following SURVEY.md
+// Appendix A.6-A.10, whose derivation of the AHP identities is repeated next to the code.
+// PARITY UNPINNED against real arkworks (no Rust toolchain, no golden proofs in the reference);
+// what is checked: completeness (verify(prove(x)) for the reference's toy circuits and synthetic
+// ones), soundness smoke tests (tampered proofs / inputs rejected), and that the GPU engine and the
+// CPU engine produce byte-identical proofs.
+//
+// Template parameter Engine supplies the heavy operators (NTT, MSM, fixed-base powers):
+//   struct Engine {
+//     void  ntt(Fr* v, uint32_t log_n, bool inverse, bool coset);             // host vector, in place
+//     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n);    // resident beta^i * g
+//     void  export_bases(void* h, size_t offset, size_t n, G1Point* out);
+//     void  free_bases(void* h);
+//     G1Point msm(void* h, size_t offset, const Fr* scalars_mont, size_t n);  // sum s_i * base[offset+i]
+//   };
+// libswb200 instantiates it with the CUDA kernels; the oracle build with the C restatement.
+//
+// Verification: the KZG opening equations are checked in G1 with the setup trapdoor beta
+// (C - v*g - v'*gamma_g == (beta - z) * W) instead of the pairing product; the algebra, transcript
+// and linear combinations are those of the pairing verifier.  A verifying key therefore carries the
+// trapdoor and is only meaningful as a test harness (the pairing tower is SURVEY 8f-3).
+#pragma once
+#include <array>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "curve_host.hpp"
+#include "poly.hpp"
+#include "r1cs.hpp"
+#include "rng.hpp"
+
+namespace swb {
+namespace marlin {
+
+struct MarlinError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ------------------------------------------------------------------------------------------------
+// sizes (AHPForR1CS::max_degree)
+// ------------------------------------------------------------------------------------------------
+inline size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+inline size_t ahp_max_degree(size_t num_constraints, size_t num_variables, size_t num_non_zero) {
+    const size_t h = next_pow2(std::max(num_constraints, num_variables)), k = next_pow2(num_non_zero), zk = 1;
+    return std::max(std::max(2 * h + zk - 2, 3 * h + 2 * zk - 3), std::max(h, 3 * k - 3));
+}
+
+// ------------------------------------------------------------------------------------------------
+// KZG10 / MarlinKZG10
+// ------------------------------------------------------------------------------------------------
+template <class Engine>
+struct UniversalSrs {
+    Engine* eng = nullptr;
+    size_t max_degree = 0;
+    void* powers_of_g = nullptr;              // resident beta^i * g, i <= max_degree
+    std::vector<G1Point> powers_of_gamma_g;   // beta^i * gamma_g, i <= hiding_bound + 1 (the only ones trim keeps)
+    G1Point g, gamma_g;
+    Fr beta;                                  // setup trapdoor, kept for the G1-side opening check
+    ~UniversalSrs() {
+        if (eng && powers_of_g) eng->free_bases(powers_of_g);
+    }
+};
+
+struct Commitment {
+    G1Point comm = G1Point::identity();
+    bool has_shifted = false;
+    G1Point shifted = G1Point::identity();
+};
+struct Randomness {
+    Poly blind;              // hiding polynomial (empty = not hiding)
+    Poly shifted_blind;
+};
+struct LabeledPoly {
+    std::string label;
+    Poly poly;
+    bool has_bound = false;
+    size_t bound = 0;
+    bool hiding = false;
+};
+
+template <class Engine>
+struct CommitterKey {
+    const UniversalSrs<Engine>* srs = nullptr;
+    size_t supported_degree = 0;
+};
+
+inline Poly rand_poly(size_t degree, ChaChaRng& rng) {   // DensePolynomial::rand: degree + 1 coefficients
+    Poly p(degree + 1);
+    for (auto& c : p) c = rand_fr(rng);
+    return p;
+}
+
+template <class Engine>
+G1Point kzg_msm(const CommitterKey<Engine>& ck, size_t offset, const Poly& p) {
+    size_t n = p.size();
+    while (n > 0 && p[n - 1].is_zero()) n--;
+    if (n == 0) return G1Point::identity();
+    if (offset + n > ck.srs->max_degree + 1) throw MarlinError("polynomial degree exceeds the SRS");
+    return ck.srs->eng->msm(ck.srs->powers_of_g, offset, p.data(), n);
+}
+inline G1Point gamma_msm(const std::vector<G1Point>& gamma, const Poly& blind) {
+    G1Xyzz acc = G1Xyzz::identity();
+    if (blind.size() > gamma.size()) throw MarlinError("hiding polynomial longer than powers_of_gamma_g");
+    for (size_t i = 0; i < blind.size(); i++) {
+        G1Point t = g1_mul_fr(gamma[i], blind[i]);
+        if (!t.infinity) acc.add_affine(t.x, t.y);
+    }
+    return to_affine(acc);
+}
+
+// MarlinKZG10::commit: per polynomial [commitment][shifted commitment], blinders drawn in that order
+template <class Engine>
+void pc_commit(const CommitterKey<Engine>& ck, const std::vector<LabeledPoly>& polys, ChaChaRng* rng,
+               std::vector<Commitment>* comms, std::vector<Randomness>* rands) {
+    for (const auto& lp : polys) {
+        Commitment c;
+        Randomness r;
+        if (poly_degree(lp.poly) > ck.supported_degree) throw MarlinError("polynomial " + lp.label + " too large for the committer key");
+        c.comm = kzg_msm(ck, 0, lp.poly);
+        if (lp.hiding) {
+            r.blind = rand_poly(2, *rng);     // hiding_bound + 1 = degree 2
+            c.comm = g1_add(c.comm, gamma_msm(ck.srs->powers_of_gamma_g, r.blind));
+        }
+        if (lp.has_bound) {
+            c.has_shifted = true;
+            c.shifted = kzg_msm(ck, ck.srs->max_degree - lp.bound, lp.poly);
+            if (lp.hiding) {
+                r.shifted_blind = rand_poly(2, *rng);
+                c.shifted = g1_add(c.shifted, gamma_msm(ck.srs->powers_of_gamma_g, r.shifted_blind));
+            }
+        }
+        comms->push_back(c);
+        rands->push_back(r);
+    }
+}
+
+struct PcProof {
+    G1Point w = G1Point::identity();
+    bool has_random_v = false;
+    Fr random_v = Fr::zero();
+};
+
+// MarlinKZG10::open at one point for a list of polynomials (opening challenge powers xi^j, one per
+// polynomial and one more for a shifted part)
+template <class Engine>
+PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledPoly*>& polys,
+                const std::vector<const Randomness*>& rands, const Fr& point, const Fr& xi) {
+    Poly p, r, shifted_w, shifted_r_witness;
+    bool hiding = false, any_shifted = false;
+    Fr shifted_r_value = Fr::zero();
+    Fr chal = Fr::one();
+    size_t max_bound_offset = 0;
+    (void)max_bound_offset;
+    // shifted witnesses are committed against different offsets of the powers, so they are
+    // accumulated per offset
+    std::map<size_t, Poly> shifted_by_offset;
+    for (size_t j = 0; j < polys.size(); j++) {
+        poly_add_scaled(p, chal, polys[j]->poly);
+        if (!rands[j]->blind.empty()) { poly_add_scaled(r, chal, rands[j]->blind); hiding = true; }
+        chal = chal * xi;
+        if (polys[j]->has_bound) {
+            any_shifted = true;
+            Poly wj = poly_divide_by_linear(polys[j]->poly, point);
+            poly_add_scaled(shifted_by_offset[ck.srs->max_degree - polys[j]->bound], chal, wj);
+            if (!rands[j]->shifted_blind.empty()) {
+                hiding = true;
+                Poly rw = poly_divide_by_linear(rands[j]->shifted_blind, point);
+                poly_add_scaled(shifted_r_witness, chal, rw);
+                shifted_r_value = shifted_r_value + chal * poly_eval(rands[j]->shifted_blind, point);
+            }
+            chal = chal * xi;
+        }
+    }
+    PcProof pr;
+    Poly witness = poly_divide_by_linear(p, point);
+    G1Xyzz w = to_xyzz(kzg_msm(ck, 0, witness));
+    if (hiding) {
+        Poly rwit = poly_divide_by_linear(r, point);
+        G1Point t = gamma_msm(ck.srs->powers_of_gamma_g, rwit);
+        if (!t.infinity) w.add_affine(t.x, t.y);
+        pr.has_random_v = true;
+        pr.random_v = poly_eval(r, point);
+    }
+    if (any_shifted) {
+        for (auto& kv : shifted_by_offset) {
+            G1Point t = kzg_msm(ck, kv.first, kv.second);
+            if (!t.infinity) w.add_affine(t.x, t.y);
+        }
+        if (!shifted_r_witness.empty()) {
+            G1Point t = gamma_msm(ck.srs->powers_of_gamma_g, shifted_r_witness);
+            if (!t.infinity) w.add_affine(t.x, t.y);
+            pr.random_v = pr.random_v + shifted_r_value;
+        }
+    }
+    pr.w = to_affine(w);
+    return pr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index (AHPForR1CS::index + MarlinKZG10::trim/commit; SURVEY A.8, joint arithmetisation)
+// ------------------------------------------------------------------------------------------------
+struct IndexInfo {
+    size_t num_variables = 0, num_constraints = 0, num_non_zero = 0, num_instance = 0;
+};
+
+template <class Engine>
+struct ProvingKey {
+    IndexInfo info;
+    Domain dom_h, dom_k, dom_x;
+    std::vector<SparseRow> a, b, c;                 // padded, squared matrices
+    // joint arithmetisation: entry k of K is (constraint r_k, variable c_k)
+    std::vector<uint32_t> ent_row, ent_col;         // r_k, position of c_k in H (reindexed)
+    std::vector<LabeledPoly> index_polys;           // row, col, a_val, b_val, c_val, row_col
+    std::vector<Fr> row_evals, col_evals, val_a_evals, val_b_evals, val_c_evals;   // on K
+    std::vector<Commitment> index_comms;
+    CommitterKey<Engine> ck;
+};
+template <class Engine>
+struct VerifyingKey {
+    IndexInfo info;
+    std::vector<Commitment> index_comms;
+    const UniversalSrs<Engine>* srs = nullptr;      // g, gamma_g, shift powers and (test harness) beta
+};
+
+inline void put_commitment_bytes(std::vector<uint8_t>& out, const Commitment& c) {   // ToBytes, 195 B
+    put_g1_uncompressed(out, c.comm);
+    out.push_back(c.has_shifted ? 1 : 0);
+    put_g1_uncompressed(out, c.has_shifted ? c.shifted : G1Point::identity());
+}
+inline void put_vk_bytes(std::vector<uint8_t>& out, const IndexInfo& info, const std::vector<Commitment>& comms) {
+    put_u64(out, info.num_variables);
+    put_u64(out, info.num_constraints);
+    put_u64(out, info.num_non_zero);
+    for (auto& c : comms) put_commitment_bytes(out, c);
+}
+
+template <class Engine>
+std::unique_ptr<UniversalSrs<Engine>> universal_setup(Engine& eng, size_t num_constraints, size_t num_variables,
+                                                      size_t num_non_zero, ChaChaRng& rng) {
+    auto srs = std::make_unique<UniversalSrs<Engine>>();
+    srs->eng = &eng;
+    srs->max_degree = ahp_max_degree(num_constraints, num_variables, num_non_zero);
+    // KZG10::setup draw order: beta, g, gamma_g, h (G2)
+    srs->beta = rand_fr(rng);
+    srs->g = g1_rand(rng);
+    srs->gamma_g = g1_rand(rng);
+    g2_rand_consume(rng);
+    srs->powers_of_g = eng.bases_from_powers(srs->g, srs->beta, srs->max_degree + 1);
+    // upstream also tabulates all max_degree + 2 powers of gamma_g; only the first
+    // hiding_bound + 2 = 3 survive trim, so only those are materialised here
+    srs->powers_of_gamma_g.resize(3);
+    Fr bp = Fr::one();
+    for (int i = 0; i < 3; i++) {
+        srs->powers_of_gamma_g[i] = g1_mul_fr(srs->gamma_g, bp);
+        bp = bp * srs->beta;
+    }
+    return srs;
+}
+
+template <class Engine>
+void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Engine>* pk, VerifyingKey<Engine>* vk) {
+    cs.pad_instance();
+    cs.make_square();
+    const size_t nvar = cs.num_variables();
+    pk->dom_h = Domain(cs.num_constraints());
+    pk->dom_x = Domain(cs.num_instance);
+    const Domain& H = pk->dom_h;
+    // joint sparsity pattern, row by row, columns in increasing order
+    std::vector<std::vector<std::pair<uint32_t, Fr>>> ja(cs.a.size()), jb(cs.a.size()), jc(cs.a.size());
+    size_t nnz = 0;
+    std::vector<uint32_t> er, ec;
+    std::vector<Fr> va, vb, vc;
+    for (size_t r = 0; r < cs.a.size(); r++) {
+        std::map<uint32_t, std::array<Fr, 3>> cols;
+        auto put = [&](const SparseRow& row, int which) {
+            for (auto& e : row.e) {
+                auto it = cols.find(e.second);
+                if (it == cols.end()) it = cols.emplace(e.second, std::array<Fr, 3>{Fr::zero(), Fr::zero(), Fr::zero()}).first;
+                it->second[which] = it->second[which] + e.first;
+            }
+        };
+        put(cs.a[r], 0); put(cs.b[r], 1); put(cs.c[r], 2);
+        for (auto& kv : cols) {
+            er.push_back((uint32_t)r);
+            ec.push_back(kv.first);
+            va.push_back(kv.second[0]); vb.push_back(kv.second[1]); vc.push_back(kv.second[2]);
+            nnz++;
+        }
+    }
+    pk->info = IndexInfo{nvar, cs.num_constraints(), nnz, cs.num_instance};
+    pk->dom_k = Domain(nnz);
+    const Domain& K = pk->dom_k;
+    if (ahp_max_degree(pk->info.num_constraints, nvar, nnz) > srs.max_degree)
+        throw MarlinError("index: circuit exceeds the universal SRS bound");
+    pk->a = cs.a; pk->b = cs.b; pk->c = cs.c;
+    const std::vector<Fr> h_el = H.elements();
+    // For entry k = (r, c): row_k = H[pos(c)] (the variable side, summed against z), col_k = H[r]
+    // (the constraint side, paired with r(alpha, .)).  val_M(k) = M[r][c] / u_H(row_k, row_k) with
+    // u_H(x, x) = |H| x^(|H|-1) = |H| / x on H, so that
+    //    sum_j z(j) t(j) = sum_r r(alpha, H[r]) (M z)(r)   for   t(X) = sum_k val(k) u_H(X,row_k) u_H(alpha,col_k).
+    pk->ent_row.resize(nnz);
+    pk->ent_col.resize(nnz);
+    std::vector<Fr> row(K.n, h_el[0]), col(K.n, h_el[0]), vala(K.n, Fr::zero()), valb(K.n, Fr::zero()), valc(K.n, Fr::zero()),
+        rowcol(K.n);
+    for (size_t k = 0; k < nnz; k++) {
+        const size_t pos = H.reindex_by_subdomain(pk->dom_x, ec[k]);
+        pk->ent_row[k] = er[k];
+        pk->ent_col[k] = (uint32_t)pos;
+        row[k] = h_el[pos];
+        col[k] = h_el[er[k]];
+        const Fr scale = row[k] * H.size_inv;
+        vala[k] = va[k] * scale; valb[k] = vb[k] * scale; valc[k] = vc[k] * scale;
+    }
+    for (size_t k = 0; k < K.n; k++) rowcol[k] = row[k] * col[k];
+    pk->row_evals = row; pk->col_evals = col;
+    pk->val_a_evals = vala; pk->val_b_evals = valb; pk->val_c_evals = valc;
+    auto interp = [&](std::vector<Fr> ev) { eng.ntt(ev.data(), K.log_n, true, false); return ev; };
+    const char* names[6] = {"row", "col", "a_val", "b_val", "c_val", "row_col"};
+    std::vector<Fr>* evs[6] = {&row, &col, &vala, &valb, &valc, &rowcol};
+    pk->index_polys.clear();
+    for (int i = 0; i < 6; i++) {
+        LabeledPoly lp;
+        lp.label = names[i];
+        lp.poly = interp(*evs[i]);
+        pk->index_polys.push_back(std::move(lp));
+    }
+    pk->ck.srs = &srs;
+    pk->ck.supported_degree = ahp_max_degree(pk->info.num_constraints, nvar, nnz);
+    std::vector<Randomness> unused;
+    pk->index_comms.clear();
+    pc_commit(pk->ck, pk->index_polys, nullptr, &pk->index_comms, &unused);
+    vk->info = pk->info;
+    vk->index_comms = pk->index_comms;
+    vk->srs = &srs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// proof
+// ------------------------------------------------------------------------------------------------
+struct Proof {
+    std::vector<std::vector<Commitment>> commitments;   // [w,z_a,z_b,mask] [t,g_1,h_1] [g_2,h_2]
+    std::vector<Fr> evaluations;                        // g_1(beta), g_2(gamma), t(beta), z_b(beta)
+    std::vector<PcProof> pc_proofs;                     // @beta, @gamma
+
+    // ark-serialize CanonicalSerialize
+    std::vector<uint8_t> serialize() const {
+        std::vector<uint8_t> out;
+        put_u64(out, commitments.size());
+        for (auto& round : commitments) {
+            put_u64(out, round.size());
+            for (auto& c : round) {
+                put_g1_compressed(out, c.comm);
+                out.push_back(c.has_shifted ? 1 : 0);
+                if (c.has_shifted) put_g1_compressed(out, c.shifted);
+            }
+        }
+        put_u64(out, evaluations.size());
+        for (auto& e : evaluations) put_fr_canonical(out, e);
+        put_u64(out, 3);                       // prover_messages: three EmptyMessage = Option::None
+        for (int i = 0; i < 3; i++) out.push_back(0);
+        put_u64(out, pc_proofs.size());
+        for (auto& p : pc_proofs) {
+            put_g1_compressed(out, p.w);
+            out.push_back(p.has_random_v ? 1 : 0);
+            if (p.has_random_v) put_fr_canonical(out, p.random_v);
+        }
+        out.push_back(0);                      // BatchLCProof.evals: None
+        return out;
+    }
+    static bool deserialize(const uint8_t* p, size_t len, Proof* out) {
+        const uint8_t* end = p + len;
+        auto get_u64 = [&](uint64_t* v) {
+            if (end - p < 8) return false;
+            *v = 0;
+            for (int b = 0; b < 8; b++) *v |= (uint64_t)p[b] << (8 * b);
+            p += 8;
+            return true;
+        };
+        uint64_t n;
+        if (!get_u64(&n) || n > 8) return false;
+        out->commitments.assign(n, {});
+        for (auto& round : out->commitments) {
+            uint64_t m;
+            if (!get_u64(&m) || m > 64) return false;
+            round.resize(m);
+            for (auto& c : round) {
+                if (!get_g1_compressed(p, end, &c.comm)) return false;
+                if (p >= end) return false;
+                c.has_shifted = *p++ != 0;
+                if (c.has_shifted && !get_g1_compressed(p, end, &c.shifted)) return false;
+            }
+        }
+        if (!get_u64(&n) || n > 64) return false;
+        out->evaluations.resize(n);
+        for (auto& e : out->evaluations)
+            if (!get_fr_canonical(p, end, &e)) return false;
+        if (!get_u64(&n) || n != 3 || end - p < 3) return false;
+        p += 3;
+        if (!get_u64(&n) || n > 8) return false;
+        out->pc_proofs.resize(n);
+        for (auto& pr : out->pc_proofs) {
+            if (!get_g1_compressed(p, end, &pr.w)) return false;
+            if (p >= end) return false;
+            pr.has_random_v = *p++ != 0;
+            if (pr.has_random_v && !get_fr_canonical(p, end, &pr.random_v)) return false;
+        }
+        return end - p == 1 && *p == 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// transcript helpers shared by prover and verifier
+// ------------------------------------------------------------------------------------------------
+inline Fr sample_outside(const Domain& d, ChaChaRng& rng) {     // sample_element_outside_domain
+    Fr t = rand_fr(rng);
+    while (d.vanishing_at(t).is_zero()) t = rand_fr(rng);
+    return t;
+}
+inline Fr fr_from_u128(const uint64_t w[2]) {
+    Fr c = Fr::zero();
+    c.l[0] = (uint32_t)w[0]; c.l[1] = (uint32_t)(w[0] >> 32);
+    c.l[2] = (uint32_t)w[1]; c.l[3] = (uint32_t)(w[1] >> 32);
+    return c.from_canonical();
+}
+inline std::vector<uint8_t> round_bytes(const std::vector<Commitment>& comms) {
+    std::vector<uint8_t> out;
+    for (auto& c : comms) put_commitment_bytes(out, c);
+    return out;                                   // the prover message is EmptyMessage: no bytes
+}
+struct Challenges {
+    Fr alpha, eta_a, eta_b, eta_c, beta, gamma, xi;
+};
+// a linear combination of committed polynomials plus a constant; the constant moves to the claimed
+// value (poly-commit's handling of LCTerm::One): sum coeff_i p_i(z) must equal -constant
+struct LinComb {
+    std::string label;
+    std::vector<std::pair<Fr, std::string>> terms;
+    Fr constant = Fr::zero();
+};
+struct LcInputs {
+    Fr g1_beta, g2_gamma, t_beta, zb_beta;       // reported evaluations
+    Fr x_hat_beta, v_x_beta;                     // from the public input
+};
+inline void build_lcs(const Domain& H, const Domain& K, const Challenges& ch, const LcInputs& in, LinComb* outer, LinComb* inner) {
+    const Fr vh_a = H.vanishing_at(ch.alpha), vh_b = H.vanishing_at(ch.beta), vk_g = K.vanishing_at(ch.gamma);
+    const Fr r_ab = H.bivariate(ch.alpha, ch.beta);
+    // outer: mask + r(a,b)(eta_a + eta_c z_b(b)) z_a + r(a,b) eta_b z_b(b) - t(b) v_X(b) w - t(b) x^(b)
+    //        - v_H(b) h_1 - b g_1(b) = 0
+    outer->label = "outer_sumcheck";
+    outer->terms = {{Fr::one(), "mask_poly"},
+                    {r_ab * (ch.eta_a + ch.eta_c * in.zb_beta), "z_a"},
+                    {(in.t_beta * in.v_x_beta).neg(), "w"},
+                    {vh_b.neg(), "h_1"}};
+    outer->constant = r_ab * ch.eta_b * in.zb_beta - in.t_beta * in.x_hat_beta - ch.beta * in.g1_beta;
+    // inner: v_H(a) v_H(b) (eta_a a_val + eta_b b_val + eta_c c_val)
+    //        - (ab - a row - b col + row_col)(g g_2(g) + t(b)/|K|) - v_K(g) h_2 = 0
+    const Fr s = ch.gamma * in.g2_gamma + in.t_beta * K.size_inv;
+    const Fr vv = vh_a * vh_b;
+    inner->label = "inner_sumcheck";
+    inner->terms = {{vv * ch.eta_a, "a_val"}, {vv * ch.eta_b, "b_val"}, {vv * ch.eta_c, "c_val"},
+                    {ch.alpha * s, "row"}, {ch.beta * s, "col"}, {s.neg(), "row_col"}, {vk_g.neg(), "h_2"}};
+    inner->constant = (ch.alpha * ch.beta * s).neg();
+}
+
+// ------------------------------------------------------------------------------------------------
+// prove (AHPForR1CS prover rounds + MarlinKZG10 commit/open)
+// ------------------------------------------------------------------------------------------------
+template <class Engine>
+Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rng) {
+    if (!cs.has_assignment) throw MarlinError("prove: constraint system has no assignment");
+    cs.pad_instance();
+    cs.make_square();
+    if (cs.num_variables() != pk.info.num_variables || cs.num_constraints() != pk.info.num_constraints)
+        throw MarlinError("prove: constraint system does not match the proving key");
+    const Domain &H = pk.dom_h, &K = pk.dom_k, &X = pk.dom_x;
+    const size_t nh = H.n, nx = X.n, ratio = nh / nx;
+    auto ifft = [&](std::vector<Fr> ev, const Domain& d) { ev.resize(d.n, Fr::zero()); eng.ntt(ev.data(), d.log_n, true, false); return ev; };
+    auto fft = [&](Poly p, const Domain& d) { p.resize(d.n, Fr::zero()); eng.ntt(p.data(), d.log_n, false, false); return p; };
+    auto poly_mul = [&](const Poly& a, const Poly& b) {
+        const size_t da = poly_degree(a), db = poly_degree(b);
+        Domain d(da + db + 1);
+        Poly ea = fft(a, d), eb = fft(b, d);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < d.n; i++) ea[i] = ea[i] * eb[i];
+        eng.ntt(ea.data(), d.log_n, true, false);
+        return ea;
+    };
+    // ---- init: z_A = A z, z_B = B z ------------------------------------------------------------
+    auto matvec = [&](const std::vector<SparseRow>& m) {
+        std::vector<Fr> out(nh, Fr::zero());
+#pragma omp parallel for schedule(static)
+        for (size_t r = 0; r < m.size(); r++) {
+            Fr s = Fr::zero();
+            for (auto& e : m[r].e) s = s + e.first * cs.value(e.second);
+            out[r] = s;
+        }
+        return out;
+    };
+    std::vector<Fr> za_ev = matvec(pk.a), zb_ev = matvec(pk.b);
+    {
+        std::vector<Fr> zc_ev = matvec(pk.c);
+        for (size_t i = 0; i < nh; i++)
+            if (!(za_ev[i] * zb_ev[i] == zc_ev[i])) throw MarlinError("prove: constraint system is not satisfied");
+    }
+    std::vector<Fr> public_input(cs.instance.begin() + 1, cs.instance.end());   // padded, without the one
+    FiatShamirRng fs;
+    {
+        std::vector<uint8_t> init;
+        const char* name = "MARLIN-2019";
+        init.insert(init.end(), name, name + 11);
+        put_vk_bytes(init, pk.info, pk.index_comms);
+        for (auto& x : public_input) put_fr_canonical(init, x);
+        fs.initialize(init);
+    }
+    // ---- round 1 ---------------------------------------------------------------------------------
+    Poly x_hat = ifft(cs.instance, X);
+    const std::vector<Fr> h_el = H.elements();
+    std::vector<Fr> w_ev(nh);
+    {
+        std::vector<Fr> xh_on_h = fft(x_hat, H);
+#pragma omp parallel for schedule(static)
+        for (size_t k = 0; k < nh; k++) {
+            if (k % ratio == 0) { w_ev[k] = Fr::zero(); continue; }
+            const size_t wi = k - k / ratio - 1;
+            const Fr wv = wi < cs.witness.size() ? cs.witness[wi] : Fr::zero();
+            w_ev[k] = wv - xh_on_h[k];
+        }
+    }
+    auto add_vanishing = [&](Poly p, const Fr& rho) {      // p + rho * (X^nh - 1)
+        p.resize(nh + 1, Fr::zero());
+        p[0] = p[0] - rho;
+        p[nh] = p[nh] + rho;
+        return p;
+    };
+    const Fr rho_w = rand_fr(zk_rng);
+    Poly w_poly;
+    {
+        Poly num = add_vanishing(ifft(w_ev, H), rho_w), rem;
+        poly_divide_by_vanishing(num, nx, &w_poly, &rem);
+    }
+    const Fr rho_a = rand_fr(zk_rng);
+    Poly za_poly = add_vanishing(ifft(za_ev, H), rho_a);
+    const Fr rho_b = rand_fr(zk_rng);
+    Poly zb_poly = add_vanishing(ifft(zb_ev, H), rho_b);
+    Poly mask = rand_poly(3 * nh - 1, zk_rng);               // degree 3|H| + 2 zk - 3
+    {
+        Fr r0 = Fr::zero();
+        for (size_t i = 0; i < mask.size(); i += nh) r0 = r0 + mask[i];
+        mask[0] = mask[0] - r0;                              // sum over H becomes zero
+    }
+    std::vector<LabeledPoly> first = {{"w", w_poly, false, 0, true}, {"z_a", za_poly, false, 0, true},
+                                      {"z_b", zb_poly, false, 0, true}, {"mask_poly", mask, false, 0, false}};
+    Proof proof;
+    proof.commitments.resize(3);
+    std::vector<Randomness> first_r, second_r, third_r;
+    pc_commit(pk.ck, first, &zk_rng, &proof.commitments[0], &first_r);
+    fs.absorb(round_bytes(proof.commitments[0]));
+    Challenges ch;
+    ch.alpha = sample_outside(H, fs.rng());
+    ch.eta_a = rand_fr(fs.rng());
+    ch.eta_b = rand_fr(fs.rng());
+    ch.eta_c = rand_fr(fs.rng());
+    // ---- round 2 ---------------------------------------------------------------------------------
+    const Fr vh_alpha = H.vanishing_at(ch.alpha);
+    std::vector<Fr> r_alpha_ev(nh);
+    {
+        std::vector<Fr> den(nh);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < nh; i++) den[i] = ch.alpha - h_el[i];
+        batch_inverse(den);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < nh; i++) r_alpha_ev[i] = vh_alpha * den[i];
+    }
+    Poly r_alpha = ifft(r_alpha_ev, H);
+    // t on H: t(H[pos(c)]) = sum_M eta_M sum_{r} M[r][c] r_alpha(H[r])
+    std::vector<Fr> t_ev(nh, Fr::zero());
+    {
+        auto scatter = [&](const std::vector<SparseRow>& m, const Fr& eta) {
+            for (size_t r = 0; r < m.size(); r++) {
+                const Fr f = eta * r_alpha_ev[r];
+                for (auto& e : m[r].e) {
+                    const size_t pos = H.reindex_by_subdomain(X, e.second);
+                    t_ev[pos] = t_ev[pos] + f * e.first;
+                }
+            }
+        };
+        scatter(pk.a, ch.eta_a); scatter(pk.b, ch.eta_b); scatter(pk.c, ch.eta_c);
+    }
+    Poly t_poly = ifft(t_ev, H);
+    Poly g1_poly, h1_poly;
+    {
+        Poly summed = poly_mul(za_poly, zb_poly);            // z_c = z_a z_b
+        poly_scale(summed, ch.eta_c);
+        poly_add_scaled(summed, ch.eta_a, za_poly);
+        poly_add_scaled(summed, ch.eta_b, zb_poly);
+        Poly z_poly(w_poly.size() + nx, Fr::zero());         // z = w v_X + x^
+        for (size_t i = 0; i < w_poly.size(); i++) { z_poly[i + nx] = z_poly[i + nx] + w_poly[i]; z_poly[i] = z_poly[i] - w_poly[i]; }
+        poly_add(z_poly, x_hat);
+        Poly q1 = poly_mul(r_alpha, summed);
+        Poly tz = poly_mul(t_poly, z_poly);
+        poly_sub(q1, tz);
+        poly_add(q1, mask);
+        Poly rem;
+        poly_divide_by_vanishing(q1, nh, &h1_poly, &rem);
+        if (!rem[0].is_zero()) throw MarlinError("prove: outer sumcheck does not sum to zero");
+        g1_poly.assign(rem.begin() + 1, rem.end());          // rem = X g_1
+    }
+    std::vector<LabeledPoly> second = {{"t", t_poly, false, 0, false}, {"g_1", g1_poly, true, nh - 2, true},
+                                       {"h_1", h1_poly, false, 0, true}};
+    pc_commit(pk.ck, second, &zk_rng, &proof.commitments[1], &second_r);
+    fs.absorb(round_bytes(proof.commitments[1]));
+    ch.beta = sample_outside(H, fs.rng());
+    // ---- round 3 ---------------------------------------------------------------------------------
+    const Fr vh_beta = H.vanishing_at(ch.beta), vv = vh_alpha * vh_beta;
+    std::vector<Fr> f_ev(K.n), den(K.n);
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < K.n; k++) den[k] = (ch.beta - pk.row_evals[k]) * (ch.alpha - pk.col_evals[k]);
+    batch_inverse(den);
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < K.n; k++)
+        f_ev[k] = vv * (ch.eta_a * pk.val_a_evals[k] + ch.eta_b * pk.val_b_evals[k] + ch.eta_c * pk.val_c_evals[k]) * den[k];
+    Poly f_poly = ifft(f_ev, K);
+    Poly g2_poly(f_poly.begin() + 1, f_poly.end());
+    Poly h2_poly;
+    {
+        const Poly &row = pk.index_polys[0].poly, &col = pk.index_polys[1].poly, &rc = pk.index_polys[5].poly;
+        Poly a_poly(K.n, Fr::zero()), b_poly(K.n, Fr::zero());
+        poly_add_scaled(a_poly, vv * ch.eta_a, pk.index_polys[2].poly);
+        poly_add_scaled(a_poly, vv * ch.eta_b, pk.index_polys[3].poly);
+        poly_add_scaled(a_poly, vv * ch.eta_c, pk.index_polys[4].poly);
+        poly_add(b_poly, rc);
+        poly_add_scaled(b_poly, ch.alpha.neg(), row);
+        poly_add_scaled(b_poly, ch.beta.neg(), col);
+        b_poly[0] = b_poly[0] + ch.alpha * ch.beta;
+        Poly bf = poly_mul(b_poly, f_poly);
+        poly_sub(a_poly, bf);
+        Poly rem;
+        poly_divide_by_vanishing(a_poly, K.n, &h2_poly, &rem);
+        for (auto& c : rem)
+            if (!c.is_zero()) throw MarlinError("prove: inner sumcheck identity does not hold on K");
+    }
+    std::vector<LabeledPoly> third = {{"g_2", g2_poly, true, K.n - 2, false}, {"h_2", h2_poly, false, 0, false}};
+    pc_commit(pk.ck, third, &zk_rng, &proof.commitments[2], &third_r);
+    fs.absorb(round_bytes(proof.commitments[2]));
+    ch.gamma = rand_fr(fs.rng());
+    // ---- evaluations, linear combinations, openings -----------------------------------------------
+    LcInputs in;
+    in.g1_beta = poly_eval(g1_poly, ch.beta);
+    in.g2_gamma = poly_eval(g2_poly, ch.gamma);
+    in.t_beta = poly_eval(t_poly, ch.beta);
+    in.zb_beta = poly_eval(zb_poly, ch.beta);
+    in.x_hat_beta = poly_eval(x_hat, ch.beta);
+    in.v_x_beta = X.vanishing_at(ch.beta);
+    proof.evaluations = {in.g1_beta, in.g2_gamma, in.t_beta, in.zb_beta};
+    {
+        std::vector<uint8_t> eb;
+        for (auto& e : proof.evaluations) put_fr_canonical(eb, e);
+        fs.absorb(eb);
+    }
+    uint64_t u[2];
+    fs.rng().next_u128(u);
+    ch.xi = fr_from_u128(u);
+    LinComb outer, inner;
+    build_lcs(H, K, ch, in, &outer, &inner);
+    std::map<std::string, std::pair<const LabeledPoly*, const Randomness*>> by_label;
+    for (size_t i = 0; i < first.size(); i++) by_label[first[i].label] = {&first[i], &first_r[i]};
+    for (size_t i = 0; i < second.size(); i++) by_label[second[i].label] = {&second[i], &second_r[i]};
+    for (size_t i = 0; i < third.size(); i++) by_label[third[i].label] = {&third[i], &third_r[i]};
+    static const Randomness no_rand;
+    for (auto& ip : pk.index_polys) by_label[ip.label] = {&ip, &no_rand};
+    auto make_lc = [&](const LinComb& lc, LabeledPoly* lp, Randomness* lr) {
+        lp->label = lc.label;
+        for (auto& t : lc.terms) {
+            auto& src = by_label.at(t.second);
+            poly_add_scaled(lp->poly, t.first, src.first->poly);
+            if (!src.second->blind.empty()) poly_add_scaled(lr->blind, t.first, src.second->blind);
+        }
+    };
+    LabeledPoly outer_p, inner_p;
+    Randomness outer_r, inner_r;
+    make_lc(outer, &outer_p, &outer_r);
+    make_lc(inner, &inner_p, &inner_r);
+    if (!(poly_eval(outer_p.poly, ch.beta) + outer.constant).is_zero())
+        throw MarlinError("prove: outer_sumcheck linear combination does not vanish at beta");
+    if (!(poly_eval(inner_p.poly, ch.gamma) + inner.constant).is_zero())
+        throw MarlinError("prove: inner_sumcheck linear combination does not vanish at gamma");
+    // query set, ordered by label within each point: beta {g_1, outer_sumcheck, t, z_b}; gamma {g_2, inner_sumcheck}
+    std::vector<const LabeledPoly*> at_beta = {by_label["g_1"].first, &outer_p, by_label["t"].first, by_label["z_b"].first};
+    std::vector<const Randomness*> at_beta_r = {by_label["g_1"].second, &outer_r, by_label["t"].second, by_label["z_b"].second};
+    std::vector<const LabeledPoly*> at_gamma = {by_label["g_2"].first, &inner_p};
+    std::vector<const Randomness*> at_gamma_r = {by_label["g_2"].second, &inner_r};
+    proof.pc_proofs.push_back(pc_open(pk.ck, at_beta, at_beta_r, ch.beta, ch.xi));
+    proof.pc_proofs.push_back(pc_open(pk.ck, at_gamma, at_gamma_r, ch.gamma, ch.xi));
+    return proof;
+}
+
+// ------------------------------------------------------------------------------------------------
+// verify (Marlin::verify) -- public input WITHOUT the leading one, padded internally
+// ------------------------------------------------------------------------------------------------
+template <class Engine>
+bool verify(const VerifyingKey<Engine>& vk, const std::vector<Fr>& public_input_unpadded, const Proof& proof) {
+    if (proof.commitments.size() != 3 || proof.commitments[0].size() != 4 || proof.commitments[1].size() != 3 ||
+        proof.commitments[2].size() != 2 || proof.evaluations.size() != 4 || proof.pc_proofs.size() != 2)
+        return false;
+    const UniversalSrs<Engine>& srs = *vk.srs;
+    Domain H(vk.info.num_constraints), K(vk.info.num_non_zero), X(public_input_unpadded.size() + 1);
+    if (X.n != vk.info.num_instance) return false;
+    std::vector<Fr> public_input = public_input_unpadded;
+    public_input.resize(X.n - 1, Fr::zero());
+    FiatShamirRng fs;
+    {
+        std::vector<uint8_t> init;
+        const char* name = "MARLIN-2019";
+        init.insert(init.end(), name, name + 11);
+        put_vk_bytes(init, vk.info, vk.index_comms);
+        for (auto& x : public_input) put_fr_canonical(init, x);
+        fs.initialize(init);
+    }
+    Challenges ch;
+    fs.absorb(round_bytes(proof.commitments[0]));
+    ch.alpha = sample_outside(H, fs.rng());
+    ch.eta_a = rand_fr(fs.rng());
+    ch.eta_b = rand_fr(fs.rng());
+    ch.eta_c = rand_fr(fs.rng());
+    fs.absorb(round_bytes(proof.commitments[1]));
+    ch.beta = sample_outside(H, fs.rng());
+    fs.absorb(round_bytes(proof.commitments[2]));
+    ch.gamma = rand_fr(fs.rng());
+    {
+        std::vector<uint8_t> eb;
+        for (auto& e : proof.evaluations) put_fr_canonical(eb, e);
+        fs.absorb(eb);
+    }
+    uint64_t u[2];
+    fs.rng().next_u128(u);
+    ch.xi = fr_from_u128(u);
+    LcInputs in;
+    in.g1_beta = proof.evaluations[0];
+    in.g2_gamma = proof.evaluations[1];
+    in.t_beta = proof.evaluations[2];
+    in.zb_beta = proof.evaluations[3];
+    {
+        std::vector<Fr> lag = X.lagrange_at(ch.beta);
+        Fr acc = lag[0];                                   // the constant-one input
+        for (size_t i = 1; i < X.n; i++) acc = acc + lag[i] * public_input[i - 1];
+        in.x_hat_beta = acc;
+        in.v_x_beta = X.vanishing_at(ch.beta);
+    }
+    LinComb outer, inner;
+    build_lcs(H, K, ch, in, &outer, &inner);
+    std::map<std::string, const Commitment*> comm;
+    const char* r1[4] = {"w", "z_a", "z_b", "mask_poly"};
+    const char* r2[3] = {"t", "g_1", "h_1"};
+    const char* r3[2] = {"g_2", "h_2"};
+    const char* ix[6] = {"row", "col", "a_val", "b_val", "c_val", "row_col"};
+    for (int i = 0; i < 4; i++) comm[r1[i]] = &proof.commitments[0][i];
+    for (int i = 0; i < 3; i++) comm[r2[i]] = &proof.commitments[1][i];
+    for (int i = 0; i < 2; i++) comm[r3[i]] = &proof.commitments[2][i];
+    if (vk.index_comms.size() != 6) return false;
+    for (int i = 0; i < 6; i++) comm[ix[i]] = &vk.index_comms[i];
+    if (!comm["g_1"]->has_shifted || !comm["g_2"]->has_shifted) return false;
+    auto lc_comm = [&](const LinComb& lc) {
+        G1Xyzz acc = G1Xyzz::identity();
+        for (auto& t : lc.terms) {
+            G1Point p = g1_mul_fr(comm.at(t.second)->comm, t.first);
+            if (!p.infinity) acc.add_affine(p.x, p.y);
+        }
+        Commitment c;
+        c.comm = to_affine(acc);
+        return c;
+    };
+    const Commitment outer_c = lc_comm(outer), inner_c = lc_comm(inner);
+    struct Item { const Commitment* c; Fr value; bool bounded; size_t bound; };
+    auto check_point = [&](const std::vector<Item>& items, const Fr& z, const PcProof& pr) {
+        // accumulate_commitments_and_values + the KZG check with the pairing replaced by the trapdoor
+        G1Xyzz cc = G1Xyzz::identity();
+        Fr cv = Fr::zero(), chal = Fr::one();
+        auto add_scaled = [&](const G1Point& p, const Fr& s) {
+            G1Point t = g1_mul_fr(p, s);
+            if (!t.infinity) cc.add_affine(t.x, t.y);
+        };
+        for (auto& it : items) {
+            add_scaled(it.c->comm, chal);
+            cv = cv + it.value * chal;
+            chal = chal * ch.xi;
+            if (it.bounded) {
+                // shifted_comm - value * beta^(D - bound) g, times the next challenge power
+                const Fr shift = fr_pow(srs.beta, srs.max_degree - it.bound);
+                add_scaled(it.c->shifted, chal);
+                add_scaled(srs.g, (it.value * shift * chal).neg());
+                chal = chal * ch.xi;
+            }
+        }
+        add_scaled(srs.g, cv.neg());
+        if (pr.has_random_v) add_scaled(srs.gamma_g, pr.random_v.neg());
+        G1Point lhs = to_affine(cc);
+        G1Point rhs = g1_mul_fr(pr.w, srs.beta - z);
+        return lhs == rhs;
+    };
+    std::vector<Item> at_beta = {{comm["g_1"], in.g1_beta, true, H.n - 2},
+                                 {&outer_c, outer.constant.neg(), false, 0},
+                                 {comm["t"], in.t_beta, false, 0},
+                                 {comm["z_b"], in.zb_beta, false, 0}};
+    std::vector<Item> at_gamma = {{comm["g_2"], in.g2_gamma, true, K.n - 2}, {&inner_c, inner.constant.neg(), false, 0}};
+    return check_point(at_beta, ch.beta, proof.pc_proofs[0]) && check_point(at_gamma, ch.gamma, proof.pc_proofs[1]);
+}
+
+}  // namespace marlin
+}  // namespace swb

@@ -240,6 +240,19 @@ int swb_msm_g1(swb_ctx* c, const swb_bases* b, size_t offset, const swb_bigint25
     return msm_run(c, b, offset, d, n, 0, out);
 }
 
+int swb_msm_g1_fr(swb_ctx* c, const swb_bases* b, size_t offset, const swb_fr* scalars_host, size_t n, swb_g1_jacobian* out) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, n == 0 || scalars_host != nullptr, "msm: NULL scalars");
+    void* d = nullptr;
+    if (n) {
+        SWB_CUDA(c, cudaSetDevice(c->device));
+        d = get_scratch(c, "msm_scalars", n * 32);
+        if (!d) return SWB_ENOMEM;
+        SWB_CUDA(c, cudaMemcpyAsync(d, scalars_host, n * 32, cudaMemcpyHostToDevice, c->stream));
+    }
+    return msm_run(c, b, offset, d, n, 1, out);
+}
+
 int swb_g1_sum_jacobian(swb_ctx* c, const swb_g1_jacobian* pts, size_t n, swb_g1_jacobian* out) {
     // pure host arithmetic: the context is only used for error text and may be NULL
     if (!(out && (n == 0 || pts))) return set_err(c, SWB_EARG, "%s", "g1_sum: NULL argument");

@@ -1,0 +1,111 @@
+"""CPU: the Marlin protocol layer (shared templates) on the CPU engine -- RNG / hash pins against
+the big-int golden model, then the reference's own Marlin tests restated:
+verify(prove(x)) == true for manual-constraints and test-circuit under the (100, 25, 300) SRS,
+unsatisfied circuits abort the prover, tampered proofs / inputs are rejected."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import golden as G
+from oracle import pymarlin as M
+from oracle import pyoracle as O
+
+
+def hx(s):
+    return int(s, 16)
+
+
+def test_rng_streams_match_golden(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "rng.json")))
+    r = M.Rng()
+    assert [r.next_u64() for _ in range(40)] == [hx(w) for w in g["test_rng_u64"]]
+    r = M.Rng()
+    got = [r.next_u32() for _ in range(63)] + [r.next_u64()]
+    assert got == [hx(w) for w in g["test_rng_straddle"]]
+    r = M.Rng()
+    assert [r.fr_rand_mont() for _ in range(8)] == [hx(w) for w in g["test_rng_fr_rand_mont"]]
+    r = M.Rng(bytes(range(32)), 20)
+    assert [r.next_u32() for _ in range(20)] == [hx(w) for w in g["chacha20_seed_0_31_u32"]]
+
+
+def test_blake2s_matches_hashlib(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "rng.json")))
+    assert M.blake2s(b"abc").hex() == g["blake2s_abc"]
+    for n in (0, 1, 63, 64, 65, 127, 128, 129, 1000):
+        data = bytes((i * 7 + 3) & 0xFF for i in range(n))
+        assert M.blake2s(data) == G.blake2s(data)
+
+
+@pytest.fixture(scope="module")
+def toy_srs():
+    rng = M.Rng()                                   # generate_rand()
+    srs = M.universal_setup(100, 25, 300, rng)      # examples/manual-constraints.rs:89
+    assert M.lib().orc_srs_max_degree(srs) == 1533
+    return srs, rng
+
+
+def test_manual_constraints_prove_verify(toy_srs):
+    srs, rng = toy_srs
+    cs = M.R1cs("manual", v0=1, v1=1)               # a = b = 1, manual-constraints.rs:90-99
+    assert cs.is_satisfied()
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, rng)
+    assert M.verify(vk, O.fr_mont([1]), proof)
+    # wrong public input, tampered evaluation, tampered commitment, truncated proof
+    assert not M.verify(vk, O.fr_mont([2]), proof)
+    bad = bytearray(proof)
+    bad[-40] ^= 1
+    assert not M.verify(vk, O.fr_mont([1]), bytes(bad))
+    bad = bytearray(proof)
+    bad[20] ^= 1
+    assert not M.verify(vk, O.fr_mont([1]), bytes(bad))
+    assert not M.verify(vk, O.fr_mont([1]), proof[:-1])
+
+
+def test_uint8_equality_prove_verify(toy_srs):
+    srs, rng = toy_srs
+    cs = M.R1cs("uint8_eq", v0=1, v1=1)             # examples/test-circuit.rs:76
+    assert cs.is_satisfied()
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, rng)
+    assert M.verify(vk, np.zeros((0, 4), dtype=np.uint64), proof)
+    assert not M.verify(vk, O.fr_mont([1]), proof)   # wrong number of public inputs
+
+
+def test_unsatisfied_circuit_aborts_prover(toy_srs):
+    """examples/schnorr-signature/main.rs:214-217 (#[should_panic]): proving an unsatisfied
+    instance aborts instead of producing a proof."""
+    srs, rng = toy_srs
+    good = M.R1cs("uint8_eq", v0=5, v1=5)
+    bad = M.R1cs("uint8_eq", v0=5, v1=4)
+    assert not bad.is_satisfied()
+    pk, _ = M.index(srs, good)
+    with pytest.raises(M.MarlinError):
+        M.prove(pk, bad, rng)
+
+
+def test_proofs_are_deterministic_functions_of_the_rng():
+    """SimpleMerkleTree::{prove,verify} create a fresh test_rng() per call
+    (src/merkle_tree/simple_merkle_tree.rs:117,146): same seed, same bytes."""
+    out = []
+    for _ in range(2):
+        rng = M.Rng()
+        srs = M.universal_setup(100, 25, 300, rng)
+        cs = M.R1cs("chain", size=20, v0=3, v1=5)
+        pk, vk = M.index(srs, cs)
+        out.append(M.prove(pk, cs, M.Rng()))
+        assert M.verify(vk, O.fr_mont([3]), out[-1])
+    assert out[0] == out[1]
+
+
+def test_chain_circuit_medium(toy_srs):
+    rng = M.Rng()
+    srs = M.universal_setup(1 << 10, 1 << 10, 3 << 10, rng)
+    cs = M.R1cs("chain", size=1000, v0=7, v1=11)
+    assert cs.is_satisfied()
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, rng)
+    assert M.verify(vk, O.fr_mont([7]), proof)
+    assert not M.verify(vk, O.fr_mont([8]), proof)
