@@ -113,6 +113,51 @@ def msm_plan(n: int) -> tuple[int, int]:
     return c, (254 + c - 1) // c
 
 
+def marlin_extra(be, args) -> dict:
+    """End-to-end Marlin (BASELINE configs[3]): synthetic mul-chain R1CS, setup / index / prove /
+    verify through the protocol-level C ABI on this GPU; the CPU arm (same protocol source on the
+    oracle's CPU operators) proves a bounded smaller instance and the byte-identical proof check is
+    repeated on it."""
+    from oracle import pymarlin as C
+    from simpleworks_b200 import _gen
+    from simpleworks_b200.binding import ConstraintSystem, Marlin, Rng
+    m = Marlin(be)
+    out = {"circuit": "mul-chain x_i*x_{i+1}=x_{i+2}, 1 public input", "verifier": "G1-side trapdoor check (no pairing)"}
+
+    def gpu_run(lg, proofs):
+        n = (1 << lg) - 2
+        rng = Rng()
+        t0 = time.perf_counter(); srs = m.generate_universal_srs(1 << lg, 1 << lg, 3 << lg, rng); t1 = time.perf_counter()
+        cs = ConstraintSystem.builtin("mul-chain", n, 3, 5)
+        t2 = time.perf_counter(); pk, vk = m.generate_proving_and_verifying_keys(srs, cs); t3 = time.perf_counter()
+        ts, proof = [], None
+        for _ in range(proofs):
+            ta = time.perf_counter(); proof = m.generate_proof(cs, pk, Rng()); ts.append(time.perf_counter() - ta)
+        tv = time.perf_counter(); ok = m.verify_proof(vk, _gen.fr_mont(3), proof); tv = time.perf_counter() - tv
+        return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t3 - t2, "prove_s": min(ts), "prove_s_all": ts,
+                "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts), "proof_bytes": len(proof)}, proof
+
+    big, _ = gpu_run(args.marlin_log_n, 3)
+    out["gpu"] = big
+    small, proof_small = gpu_run(args.marlin_cpu_log_n, 2)
+    out["gpu_at_cpu_size"] = small
+    lg = args.marlin_cpu_log_n
+    crng = C.Rng()
+    t0 = time.perf_counter(); csrs = C.universal_setup(1 << lg, 1 << lg, 3 << lg, crng); t1 = time.perf_counter()
+    ccs = C.R1cs("chain", size=(1 << lg) - 2, v0=3, v1=5)
+    cpk, cvk = C.index(csrs, ccs); t2 = time.perf_counter()
+    cproof = C.prove(cpk, ccs, C.Rng()); t3 = time.perf_counter()
+    out["cpu_arm"] = {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t2 - t1, "prove_s": t3 - t2,
+                      "cores": O_threads(), "kind": "port", "same_proof_bytes_as_gpu": cproof == proof_small}
+    out["prove_speedup_at_cpu_size"] = (t3 - t2) / small["prove_s"]
+    return out
+
+
+def O_threads() -> int:
+    from oracle import pyoracle as O
+    return O.num_threads()
+
+
 def run_reference(args):
     """--impl reference: the CPU path (oracle port of arkworks' VariableBaseMSM, all host threads)."""
     from oracle import pyoracle as O
@@ -155,6 +200,8 @@ def main():
     ap.add_argument("--impl", default="swb200", choices=["swb200", "reference"])
     ap.add_argument("--log-n", type=int, default=int(os.environ.get("SWB_BENCH_LOG_N", "26")))
     ap.add_argument("--cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_CPU_LOG_N", "20")))
+    ap.add_argument("--marlin-log-n", type=int, default=int(os.environ.get("SWB_BENCH_MARLIN_LOG_N", "20")))
+    ap.add_argument("--marlin-cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_MARLIN_CPU_LOG_N", "16")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -355,6 +402,11 @@ def main():
             "int_frac": (nn / 2) * log_ntt * 128 / ms * 1e3 / imad_wide, "passes": be.last_stages()}
         extra["setup_bases_s"] = t_bases
         extra["stages_ms_avg"] = {k: v / args.steps for k, v in stage_sum.items()}
+        if world == 1:
+            try:
+                extra["marlin"] = marlin_extra(be, args)
+            except Exception as e:     # the headline must not die with the side measurement
+                extra["marlin"] = {"error": repr(e)}
 
     line = {
         "metric": "msm_g1_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,

@@ -11,6 +11,7 @@
 #include <omp.h>
 
 #include "marlin/c_api_impl.hpp"
+#include "marlin/vec_host.hpp"
 #include "swb_oracle.h"
 
 using namespace swb;
@@ -22,8 +23,11 @@ struct CpuBases {
     std::vector<g1_affine_t> pts;
 };
 
-struct CpuEngine {
-    void ntt(Fr* v, uint32_t log_n, bool inverse, bool coset) { orc_ntt(reinterpret_cast<fr_t*>(v), log_n, inverse, coset, 0); }
+struct CpuEngine : HostVecOps {
+    void vntt(Vec& v, uint32_t log_n, bool inverse, bool coset) {
+        if (v.size() != ((size_t)1 << log_n)) throw MarlinError("vntt: size mismatch");
+        orc_ntt(reinterpret_cast<fr_t*>(v.data()), log_n, inverse, coset, 0);
+    }
     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n) {
         auto* b = new CpuBases();
         b->pts.resize(n);
@@ -51,7 +55,8 @@ struct CpuEngine {
         }
     }
     void free_bases(void* h) { delete static_cast<CpuBases*>(h); }
-    G1Point msm(void* h, size_t offset, const Fr* scalars_mont, size_t n) {
+    G1Point msm(void* h, size_t offset, const Vec& scalars, size_t n) {
+        const Fr* scalars_mont = scalars.data();
         auto* b = static_cast<CpuBases*>(h);
         std::vector<big256_t> sc(n);
 #pragma omp parallel for schedule(static)

@@ -111,6 +111,7 @@ struct MarlinApi {
                      std::string* err) {
         try {
             Proof pr = marlin::prove(eng, pk->pk, cs->cs, rng->rng);
+            host_profile().report("prove");
             std::vector<uint8_t> b = pr.serialize();
             *bytes = (uint8_t*)malloc(b.size());
             memcpy(*bytes, b.data(), b.size());

@@ -9,15 +9,19 @@
 // ones), soundness smoke tests (tampered proofs / inputs rejected), and that the GPU engine and the
 // CPU engine produce byte-identical proofs.
 //
-// Template parameter Engine supplies the heavy operators (NTT, MSM, fixed-base powers):
+// Template parameter Engine supplies the operators and owns the polynomial storage: Engine::Vec is
+// a vector of Fr living where the engine computes (HBM for the CUDA engine of libswb200, RAM for
+// the CPU arm), so round polynomials stay resident between NTTs, element-wise passes and MSMs:
 //   struct Engine {
-//     void  ntt(Fr* v, uint32_t log_n, bool inverse, bool coset);             // host vector, in place
-//     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n);    // resident beta^i * g
+//     using Vec = ...;   vzeros vfrom vhost vclone vresize vlen vget vset vmul vadd vsub vadd_scaled
+//                        vscale vlin vadd_offset veval vdiv_vanishing vdiv_linear vbatch_inverse
+//                        vshift_down vdomain            (semantics: marlin/vec_host.hpp)
+//     void  vntt(Vec& v, uint32_t log_n, bool inverse, bool coset);            // size 2^log_n, in place
+//     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n);     // resident beta^i * g
 //     void  export_bases(void* h, size_t offset, size_t n, G1Point* out);
 //     void  free_bases(void* h);
-//     G1Point msm(void* h, size_t offset, const Fr* scalars_mont, size_t n);  // sum s_i * base[offset+i]
+//     G1Point msm(void* h, size_t offset, const Vec& scalars_mont, size_t n);  // sum s_i * base[offset+i]
 //   };
-// libswb200 instantiates it with the CUDA kernels; the oracle build with the C restatement.
 //
 // Verification: the KZG opening equations are checked in G1 with the setup trapdoor beta
 // (C - v*g - v'*gamma_g == (beta - z) * W) instead of the pairing product; the algebra, transcript
@@ -80,9 +84,10 @@ struct Randomness {
     Poly blind;              // hiding polynomial (empty = not hiding)
     Poly shifted_blind;
 };
+template <class Engine>
 struct LabeledPoly {
     std::string label;
-    Poly poly;
+    typename Engine::Vec poly;
     bool has_bound = false;
     size_t bound = 0;
     bool hiding = false;
@@ -96,17 +101,18 @@ struct CommitterKey {
 
 inline Poly rand_poly(size_t degree, ChaChaRng& rng) {   // DensePolynomial::rand: degree + 1 coefficients
     Poly p(degree + 1);
-    for (auto& c : p) c = rand_fr(rng);
+    if (degree < 64) for (auto& c : p) c = rand_fr(rng);
+    else rand_fr_bulk(rng, p.data(), p.size());
     return p;
 }
 
 template <class Engine>
-G1Point kzg_msm(const CommitterKey<Engine>& ck, size_t offset, const Poly& p) {
-    size_t n = p.size();
-    while (n > 0 && p[n - 1].is_zero()) n--;
+G1Point kzg_msm(const CommitterKey<Engine>& ck, size_t offset, const typename Engine::Vec& p) {
+    const size_t n = ck.srs->eng->vlen(p);
     if (n == 0) return G1Point::identity();
     if (offset + n > ck.srs->max_degree + 1) throw MarlinError("polynomial degree exceeds the SRS");
-    return ck.srs->eng->msm(ck.srs->powers_of_g, offset, p.data(), n);
+    ScopedPhase ph("msm");
+    return ck.srs->eng->msm(ck.srs->powers_of_g, offset, p, n);
 }
 inline G1Point gamma_msm(const std::vector<G1Point>& gamma, const Poly& blind) {
     G1Xyzz acc = G1Xyzz::identity();
@@ -120,12 +126,12 @@ inline G1Point gamma_msm(const std::vector<G1Point>& gamma, const Poly& blind) {
 
 // MarlinKZG10::commit: per polynomial [commitment][shifted commitment], blinders drawn in that order
 template <class Engine>
-void pc_commit(const CommitterKey<Engine>& ck, const std::vector<LabeledPoly>& polys, ChaChaRng* rng,
+void pc_commit(const CommitterKey<Engine>& ck, const std::vector<LabeledPoly<Engine>>& polys, ChaChaRng* rng,
                std::vector<Commitment>* comms, std::vector<Randomness>* rands) {
     for (const auto& lp : polys) {
         Commitment c;
         Randomness r;
-        if (poly_degree(lp.poly) > ck.supported_degree) throw MarlinError("polynomial " + lp.label + " too large for the committer key");
+        if (ck.srs->eng->vlen(lp.poly) > ck.supported_degree + 1) throw MarlinError("polynomial " + lp.label + " too large for the committer key");
         c.comm = kzg_msm(ck, 0, lp.poly);
         if (lp.hiding) {
             r.blind = rand_poly(2, *rng);     // hiding_bound + 1 = degree 2
@@ -153,25 +159,28 @@ struct PcProof {
 // MarlinKZG10::open at one point for a list of polynomials (opening challenge powers xi^j, one per
 // polynomial and one more for a shifted part)
 template <class Engine>
-PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledPoly*>& polys,
+PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledPoly<Engine>*>& polys,
                 const std::vector<const Randomness*>& rands, const Fr& point, const Fr& xi) {
-    Poly p, r, shifted_w, shifted_r_witness;
-    bool hiding = false, any_shifted = false;
+    using Vec = typename Engine::Vec;
+    Engine& eng = *ck.srs->eng;
+    Vec p = eng.vzeros(0);
+    Poly r, shifted_r_witness;
+    bool hiding = false;
     Fr shifted_r_value = Fr::zero();
     Fr chal = Fr::one();
-    size_t max_bound_offset = 0;
-    (void)max_bound_offset;
     // shifted witnesses are committed against different offsets of the powers, so they are
     // accumulated per offset
-    std::map<size_t, Poly> shifted_by_offset;
+    std::map<size_t, Vec> shifted_by_offset;
     for (size_t j = 0; j < polys.size(); j++) {
-        poly_add_scaled(p, chal, polys[j]->poly);
+        eng.vadd_scaled(p, chal, polys[j]->poly);
         if (!rands[j]->blind.empty()) { poly_add_scaled(r, chal, rands[j]->blind); hiding = true; }
         chal = chal * xi;
         if (polys[j]->has_bound) {
-            any_shifted = true;
-            Poly wj = poly_divide_by_linear(polys[j]->poly, point);
-            poly_add_scaled(shifted_by_offset[ck.srs->max_degree - polys[j]->bound], chal, wj);
+            Vec wj = eng.vdiv_linear(polys[j]->poly, point);
+            const size_t off = ck.srs->max_degree - polys[j]->bound;
+            auto it = shifted_by_offset.find(off);
+            if (it == shifted_by_offset.end()) it = shifted_by_offset.emplace(off, eng.vzeros(0)).first;
+            eng.vadd_scaled(it->second, chal, wj);
             if (!rands[j]->shifted_blind.empty()) {
                 hiding = true;
                 Poly rw = poly_divide_by_linear(rands[j]->shifted_blind, point);
@@ -182,7 +191,7 @@ PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledP
         }
     }
     PcProof pr;
-    Poly witness = poly_divide_by_linear(p, point);
+    Vec witness = eng.vdiv_linear(p, point);
     G1Xyzz w = to_xyzz(kzg_msm(ck, 0, witness));
     if (hiding) {
         Poly rwit = poly_divide_by_linear(r, point);
@@ -191,16 +200,14 @@ PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledP
         pr.has_random_v = true;
         pr.random_v = poly_eval(r, point);
     }
-    if (any_shifted) {
-        for (auto& kv : shifted_by_offset) {
-            G1Point t = kzg_msm(ck, kv.first, kv.second);
-            if (!t.infinity) w.add_affine(t.x, t.y);
-        }
-        if (!shifted_r_witness.empty()) {
-            G1Point t = gamma_msm(ck.srs->powers_of_gamma_g, shifted_r_witness);
-            if (!t.infinity) w.add_affine(t.x, t.y);
-            pr.random_v = pr.random_v + shifted_r_value;
-        }
+    for (auto& kv : shifted_by_offset) {
+        G1Point t = kzg_msm(ck, kv.first, kv.second);
+        if (!t.infinity) w.add_affine(t.x, t.y);
+    }
+    if (!shifted_r_witness.empty()) {
+        G1Point t = gamma_msm(ck.srs->powers_of_gamma_g, shifted_r_witness);
+        if (!t.infinity) w.add_affine(t.x, t.y);
+        pr.random_v = pr.random_v + shifted_r_value;
     }
     pr.w = to_affine(w);
     return pr;
@@ -220,8 +227,13 @@ struct ProvingKey {
     std::vector<SparseRow> a, b, c;                 // padded, squared matrices
     // joint arithmetisation: entry k of K is (constraint r_k, variable c_k)
     std::vector<uint32_t> ent_row, ent_col;         // r_k, position of c_k in H (reindexed)
-    std::vector<LabeledPoly> index_polys;           // row, col, a_val, b_val, c_val, row_col
-    std::vector<Fr> row_evals, col_evals, val_a_evals, val_b_evals, val_c_evals;   // on K
+    std::vector<LabeledPoly<Engine>> index_polys;   // row, col, a_val, b_val, c_val, row_col (resident)
+    typename Engine::Vec row_evals, col_evals, val_a_evals, val_b_evals, val_c_evals;   // on K (resident)
+    // matrices regrouped by H position of the column (for t = sum_M eta_M M^T r_alpha): entries of
+    // position p are t_ent[t_start[p] .. t_start[p+1]): (constraint row, which matrix, coefficient)
+    std::vector<uint32_t> t_start, t_row;
+    std::vector<uint8_t> t_mat;
+    std::vector<Fr> t_coef;
     std::vector<Commitment> index_comms;
     CommitterKey<Engine> ck;
 };
@@ -322,16 +334,36 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
         vala[k] = va[k] * scale; valb[k] = vb[k] * scale; valc[k] = vc[k] * scale;
     }
     for (size_t k = 0; k < K.n; k++) rowcol[k] = row[k] * col[k];
-    pk->row_evals = row; pk->col_evals = col;
-    pk->val_a_evals = vala; pk->val_b_evals = valb; pk->val_c_evals = valc;
-    auto interp = [&](std::vector<Fr> ev) { eng.ntt(ev.data(), K.log_n, true, false); return ev; };
+    pk->row_evals = eng.vfrom(row); pk->col_evals = eng.vfrom(col);
+    pk->val_a_evals = eng.vfrom(vala); pk->val_b_evals = eng.vfrom(valb); pk->val_c_evals = eng.vfrom(valc);
+    {
+        std::vector<uint32_t> pos_of(nvar), cnt(H.n + 1, 0);
+        for (size_t v = 0; v < nvar; v++) pos_of[v] = (uint32_t)H.reindex_by_subdomain(pk->dom_x, v);
+        const std::vector<SparseRow>* ms[3] = {&cs.a, &cs.b, &cs.c};
+        for (int m = 0; m < 3; m++)
+            for (auto& row : *ms[m])
+                for (auto& e : row.e) cnt[pos_of[e.second] + 1]++;
+        for (size_t i = 0; i < H.n; i++) cnt[i + 1] += cnt[i];
+        pk->t_start = cnt;
+        const size_t tot = cnt[H.n];
+        pk->t_row.resize(tot); pk->t_mat.resize(tot); pk->t_coef.resize(tot);
+        std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+        for (int m = 0; m < 3; m++)
+            for (size_t r = 0; r < ms[m]->size(); r++)
+                for (auto& e : (*ms[m])[r].e) {
+                    const uint32_t at = cur[pos_of[e.second]]++;
+                    pk->t_row[at] = (uint32_t)r; pk->t_mat[at] = (uint8_t)m; pk->t_coef[at] = e.first;
+                }
+    }
     const char* names[6] = {"row", "col", "a_val", "b_val", "c_val", "row_col"};
-    std::vector<Fr>* evs[6] = {&row, &col, &vala, &valb, &valc, &rowcol};
+    typename Engine::Vec rowcol_v = eng.vfrom(rowcol);
+    const typename Engine::Vec* evs[6] = {&pk->row_evals, &pk->col_evals, &pk->val_a_evals, &pk->val_b_evals, &pk->val_c_evals, &rowcol_v};
     pk->index_polys.clear();
     for (int i = 0; i < 6; i++) {
-        LabeledPoly lp;
+        LabeledPoly<Engine> lp;
         lp.label = names[i];
-        lp.poly = interp(*evs[i]);
+        lp.poly = eng.vclone(*evs[i]);
+        eng.vntt(lp.poly, K.log_n, true, false);
         pk->index_polys.push_back(std::move(lp));
     }
     pk->ck.srs = &srs;
@@ -482,20 +514,27 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     cs.make_square();
     if (cs.num_variables() != pk.info.num_variables || cs.num_constraints() != pk.info.num_constraints)
         throw MarlinError("prove: constraint system does not match the proving key");
+    using Vec = typename Engine::Vec;
     const Domain &H = pk.dom_h, &K = pk.dom_k, &X = pk.dom_x;
     const size_t nh = H.n, nx = X.n, ratio = nh / nx;
-    auto ifft = [&](std::vector<Fr> ev, const Domain& d) { ev.resize(d.n, Fr::zero()); eng.ntt(ev.data(), d.log_n, true, false); return ev; };
-    auto fft = [&](Poly p, const Domain& d) { p.resize(d.n, Fr::zero()); eng.ntt(p.data(), d.log_n, false, false); return p; };
-    auto poly_mul = [&](const Poly& a, const Poly& b) {
-        const size_t da = poly_degree(a), db = poly_degree(b);
-        Domain d(da + db + 1);
-        Poly ea = fft(a, d), eb = fft(b, d);
-#pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < d.n; i++) ea[i] = ea[i] * eb[i];
-        eng.ntt(ea.data(), d.log_n, true, false);
+    auto ntt = [&](Vec& v, const Domain& d, bool inverse) {
+        eng.vresize(v, d.n);
+        ScopedPhase ph("ntt");
+        eng.vntt(v, d.log_n, inverse, false);
+    };
+    auto poly_mul = [&](const Vec& a, const Vec& b) {
+        const size_t la = eng.vlen(a), lb = eng.vlen(b);
+        Domain d(la + lb - 1);
+        Vec ea = eng.vclone(a), eb = eng.vclone(b);
+        ntt(ea, d, false);
+        ntt(eb, d, false);
+        eng.vmul(ea, eb);
+        ntt(ea, d, true);
         return ea;
     };
-    // ---- init: z_A = A z, z_B = B z ------------------------------------------------------------
+    ScopedPhase ph_total("total");
+    std::unique_ptr<ScopedPhase> ph(new ScopedPhase("r0_init"));
+    // ---- init: z_A = A z, z_B = B z (sparse, host) ------------------------------------------------
     auto matvec = [&](const std::vector<SparseRow>& m) {
         std::vector<Fr> out(nh, Fr::zero());
 #pragma omp parallel for schedule(static)
@@ -509,8 +548,10 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     std::vector<Fr> za_ev = matvec(pk.a), zb_ev = matvec(pk.b);
     {
         std::vector<Fr> zc_ev = matvec(pk.c);
-        for (size_t i = 0; i < nh; i++)
-            if (!(za_ev[i] * zb_ev[i] == zc_ev[i])) throw MarlinError("prove: constraint system is not satisfied");
+        bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+        for (size_t i = 0; i < nh; i++) bad = bad || !(za_ev[i] * zb_ev[i] == zc_ev[i]);
+        if (bad) throw MarlinError("prove: constraint system is not satisfied");
     }
     std::vector<Fr> public_input(cs.instance.begin() + 1, cs.instance.end());   // padded, without the one
     FiatShamirRng fs;
@@ -523,47 +564,66 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
         fs.initialize(init);
     }
     // ---- round 1 ---------------------------------------------------------------------------------
-    Poly x_hat = ifft(cs.instance, X);
-    const std::vector<Fr> h_el = H.elements();
-    std::vector<Fr> w_ev(nh);
+    ph.reset(); ph.reset(new ScopedPhase("r1_polys"));
+    Vec x_hat = eng.vfrom(cs.instance);
+    ntt(x_hat, X, true);
+    Vec w_poly;
+    const Fr rho_w = rand_fr(zk_rng);
     {
-        std::vector<Fr> xh_on_h = fft(x_hat, H);
+        // w on H: 0 on the X-subdomain, witness - x^ elsewhere
+        std::vector<Fr> wit_on_h(nh, Fr::zero()), mask01(nh, Fr::one());
 #pragma omp parallel for schedule(static)
         for (size_t k = 0; k < nh; k++) {
-            if (k % ratio == 0) { w_ev[k] = Fr::zero(); continue; }
+            if (k % ratio == 0) { mask01[k] = Fr::zero(); continue; }
             const size_t wi = k - k / ratio - 1;
-            const Fr wv = wi < cs.witness.size() ? cs.witness[wi] : Fr::zero();
-            w_ev[k] = wv - xh_on_h[k];
+            if (wi < cs.witness.size()) wit_on_h[k] = cs.witness[wi];
         }
+        Vec xh_on_h = eng.vclone(x_hat);
+        ntt(xh_on_h, H, false);
+        Vec w_ev = eng.vfrom(wit_on_h);
+        eng.vsub(w_ev, xh_on_h);
+        Vec m01 = eng.vfrom(mask01);
+        eng.vmul(w_ev, m01);
+        ntt(w_ev, H, true);
+        // + rho_w * (X^nh - 1), then / v_X
+        eng.vresize(w_ev, nh + 1);
+        eng.vset(w_ev, 0, eng.vget(w_ev, 0) - rho_w);
+        eng.vset(w_ev, nh, rho_w);
+        Vec rem;
+        eng.vdiv_vanishing(w_ev, nx, &w_poly, &rem);
     }
-    auto add_vanishing = [&](Poly p, const Fr& rho) {      // p + rho * (X^nh - 1)
-        p.resize(nh + 1, Fr::zero());
-        p[0] = p[0] - rho;
-        p[nh] = p[nh] + rho;
+    auto blinded_interp = [&](const std::vector<Fr>& ev, const Fr& rho) {
+        Vec p = eng.vfrom(ev);
+        ntt(p, H, true);
+        eng.vresize(p, nh + 1);
+        eng.vset(p, 0, eng.vget(p, 0) - rho);
+        eng.vset(p, nh, rho);
         return p;
     };
-    const Fr rho_w = rand_fr(zk_rng);
-    Poly w_poly;
-    {
-        Poly num = add_vanishing(ifft(w_ev, H), rho_w), rem;
-        poly_divide_by_vanishing(num, nx, &w_poly, &rem);
-    }
     const Fr rho_a = rand_fr(zk_rng);
-    Poly za_poly = add_vanishing(ifft(za_ev, H), rho_a);
+    Vec za_poly = blinded_interp(za_ev, rho_a);
     const Fr rho_b = rand_fr(zk_rng);
-    Poly zb_poly = add_vanishing(ifft(zb_ev, H), rho_b);
-    Poly mask = rand_poly(3 * nh - 1, zk_rng);               // degree 3|H| + 2 zk - 3
+    Vec zb_poly = blinded_interp(zb_ev, rho_b);
+    Vec mask;
     {
+        Poly mh = rand_poly(3 * nh - 1, zk_rng);               // degree 3|H| + 2 zk - 3
         Fr r0 = Fr::zero();
-        for (size_t i = 0; i < mask.size(); i += nh) r0 = r0 + mask[i];
-        mask[0] = mask[0] - r0;                              // sum over H becomes zero
+        for (size_t i = 0; i < mh.size(); i += nh) r0 = r0 + mh[i];
+        mh[0] = mh[0] - r0;                                    // sum over H becomes zero
+        mask = eng.vfrom(mh);
     }
-    std::vector<LabeledPoly> first = {{"w", w_poly, false, 0, true}, {"z_a", za_poly, false, 0, true},
-                                      {"z_b", zb_poly, false, 0, true}, {"mask_poly", mask, false, 0, false}};
+    std::vector<LabeledPoly<Engine>> first(4);
+    first[0].label = "w"; first[0].poly = std::move(w_poly); first[0].hiding = true;
+    first[1].label = "z_a"; first[1].poly = std::move(za_poly); first[1].hiding = true;
+    first[2].label = "z_b"; first[2].poly = std::move(zb_poly); first[2].hiding = true;
+    first[3].label = "mask_poly"; first[3].poly = std::move(mask);
+    const Vec &w_p = first[0].poly, &za_p = first[1].poly, &zb_p = first[2].poly, &mask_p = first[3].poly;
     Proof proof;
     proof.commitments.resize(3);
     std::vector<Randomness> first_r, second_r, third_r;
+    ph.reset(); ph.reset(new ScopedPhase("r1_commit"));
     pc_commit(pk.ck, first, &zk_rng, &proof.commitments[0], &first_r);
+    ph.reset(); ph.reset(new ScopedPhase("r2_polys"));
     fs.absorb(round_bytes(proof.commitments[0]));
     Challenges ch;
     ch.alpha = sample_outside(H, fs.rng());
@@ -572,94 +632,105 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     ch.eta_c = rand_fr(fs.rng());
     // ---- round 2 ---------------------------------------------------------------------------------
     const Fr vh_alpha = H.vanishing_at(ch.alpha);
-    std::vector<Fr> r_alpha_ev(nh);
+    Vec r_alpha = eng.vdomain(H.log_n);                      // r(alpha, h) = v_H(alpha) / (alpha - h)
+    eng.vlin(r_alpha, ch.alpha, Fr::one().neg());
+    eng.vbatch_inverse(r_alpha);
+    eng.vscale(r_alpha, vh_alpha);
+    // t on H: t(H[pos(c)]) = sum_M eta_M sum_r M[r][c] r_alpha(H[r])   (sparse transpose product, host)
+    Vec t_poly;
     {
-        std::vector<Fr> den(nh);
+        const std::vector<Fr> r_alpha_ev = eng.vhost(r_alpha);
+        std::vector<Fr> t_ev(nh, Fr::zero());
+        const Fr etas[3] = {ch.eta_a, ch.eta_b, ch.eta_c};
 #pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < nh; i++) den[i] = ch.alpha - h_el[i];
-        batch_inverse(den);
-#pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < nh; i++) r_alpha_ev[i] = vh_alpha * den[i];
+        for (size_t p = 0; p < nh; p++) {
+            Fr acc = Fr::zero();
+            for (uint32_t k = pk.t_start[p]; k < pk.t_start[p + 1]; k++)
+                acc = acc + etas[pk.t_mat[k]] * pk.t_coef[k] * r_alpha_ev[pk.t_row[k]];
+            t_ev[p] = acc;
+        }
+        t_poly = eng.vfrom(t_ev);
     }
-    Poly r_alpha = ifft(r_alpha_ev, H);
-    // t on H: t(H[pos(c)]) = sum_M eta_M sum_{r} M[r][c] r_alpha(H[r])
-    std::vector<Fr> t_ev(nh, Fr::zero());
+    ntt(t_poly, H, true);
+    ntt(r_alpha, H, true);                                   // now the polynomial r(alpha, X)
+    Vec g1_poly, h1_poly;
     {
-        auto scatter = [&](const std::vector<SparseRow>& m, const Fr& eta) {
-            for (size_t r = 0; r < m.size(); r++) {
-                const Fr f = eta * r_alpha_ev[r];
-                for (auto& e : m[r].e) {
-                    const size_t pos = H.reindex_by_subdomain(X, e.second);
-                    t_ev[pos] = t_ev[pos] + f * e.first;
-                }
-            }
-        };
-        scatter(pk.a, ch.eta_a); scatter(pk.b, ch.eta_b); scatter(pk.c, ch.eta_c);
+        Vec summed = poly_mul(za_p, zb_p);                   // z_c = z_a z_b
+        eng.vscale(summed, ch.eta_c);
+        eng.vadd_scaled(summed, ch.eta_a, za_p);
+        eng.vadd_scaled(summed, ch.eta_b, zb_p);
+        Vec z_poly = eng.vclone(x_hat);                      // z = w v_X + x^
+        eng.vadd_offset(z_poly, nx, w_p, false);
+        eng.vadd_offset(z_poly, 0, w_p, true);
+        Vec q1 = poly_mul(r_alpha, summed);
+        Vec tz = poly_mul(t_poly, z_poly);
+        eng.vsub(q1, tz);
+        eng.vadd(q1, mask_p);
+        Vec rem;
+        eng.vdiv_vanishing(q1, nh, &h1_poly, &rem);
+        if (!eng.vget(rem, 0).is_zero()) throw MarlinError("prove: outer sumcheck does not sum to zero");
+        g1_poly = eng.vshift_down(rem, 1);                   // rem = X g_1
     }
-    Poly t_poly = ifft(t_ev, H);
-    Poly g1_poly, h1_poly;
-    {
-        Poly summed = poly_mul(za_poly, zb_poly);            // z_c = z_a z_b
-        poly_scale(summed, ch.eta_c);
-        poly_add_scaled(summed, ch.eta_a, za_poly);
-        poly_add_scaled(summed, ch.eta_b, zb_poly);
-        Poly z_poly(w_poly.size() + nx, Fr::zero());         // z = w v_X + x^
-        for (size_t i = 0; i < w_poly.size(); i++) { z_poly[i + nx] = z_poly[i + nx] + w_poly[i]; z_poly[i] = z_poly[i] - w_poly[i]; }
-        poly_add(z_poly, x_hat);
-        Poly q1 = poly_mul(r_alpha, summed);
-        Poly tz = poly_mul(t_poly, z_poly);
-        poly_sub(q1, tz);
-        poly_add(q1, mask);
-        Poly rem;
-        poly_divide_by_vanishing(q1, nh, &h1_poly, &rem);
-        if (!rem[0].is_zero()) throw MarlinError("prove: outer sumcheck does not sum to zero");
-        g1_poly.assign(rem.begin() + 1, rem.end());          // rem = X g_1
-    }
-    std::vector<LabeledPoly> second = {{"t", t_poly, false, 0, false}, {"g_1", g1_poly, true, nh - 2, true},
-                                       {"h_1", h1_poly, false, 0, true}};
+    std::vector<LabeledPoly<Engine>> second(3);
+    second[0].label = "t"; second[0].poly = std::move(t_poly);
+    second[1].label = "g_1"; second[1].poly = std::move(g1_poly); second[1].has_bound = true; second[1].bound = nh - 2; second[1].hiding = true;
+    second[2].label = "h_1"; second[2].poly = std::move(h1_poly); second[2].hiding = true;
+    ph.reset(); ph.reset(new ScopedPhase("r2_commit"));
     pc_commit(pk.ck, second, &zk_rng, &proof.commitments[1], &second_r);
+    ph.reset(); ph.reset(new ScopedPhase("r3_polys"));
     fs.absorb(round_bytes(proof.commitments[1]));
     ch.beta = sample_outside(H, fs.rng());
     // ---- round 3 ---------------------------------------------------------------------------------
     const Fr vh_beta = H.vanishing_at(ch.beta), vv = vh_alpha * vh_beta;
-    std::vector<Fr> f_ev(K.n), den(K.n);
-#pragma omp parallel for schedule(static)
-    for (size_t k = 0; k < K.n; k++) den[k] = (ch.beta - pk.row_evals[k]) * (ch.alpha - pk.col_evals[k]);
-    batch_inverse(den);
-#pragma omp parallel for schedule(static)
-    for (size_t k = 0; k < K.n; k++)
-        f_ev[k] = vv * (ch.eta_a * pk.val_a_evals[k] + ch.eta_b * pk.val_b_evals[k] + ch.eta_c * pk.val_c_evals[k]) * den[k];
-    Poly f_poly = ifft(f_ev, K);
-    Poly g2_poly(f_poly.begin() + 1, f_poly.end());
-    Poly h2_poly;
+    Vec f_poly;
     {
-        const Poly &row = pk.index_polys[0].poly, &col = pk.index_polys[1].poly, &rc = pk.index_polys[5].poly;
-        Poly a_poly(K.n, Fr::zero()), b_poly(K.n, Fr::zero());
-        poly_add_scaled(a_poly, vv * ch.eta_a, pk.index_polys[2].poly);
-        poly_add_scaled(a_poly, vv * ch.eta_b, pk.index_polys[3].poly);
-        poly_add_scaled(a_poly, vv * ch.eta_c, pk.index_polys[4].poly);
-        poly_add(b_poly, rc);
-        poly_add_scaled(b_poly, ch.alpha.neg(), row);
-        poly_add_scaled(b_poly, ch.beta.neg(), col);
-        b_poly[0] = b_poly[0] + ch.alpha * ch.beta;
-        Poly bf = poly_mul(b_poly, f_poly);
-        poly_sub(a_poly, bf);
-        Poly rem;
-        poly_divide_by_vanishing(a_poly, K.n, &h2_poly, &rem);
-        for (auto& c : rem)
-            if (!c.is_zero()) throw MarlinError("prove: inner sumcheck identity does not hold on K");
+        Vec den = eng.vclone(pk.row_evals);                  // (beta - row)(alpha - col)
+        eng.vlin(den, ch.beta, Fr::one().neg());
+        Vec d2 = eng.vclone(pk.col_evals);
+        eng.vlin(d2, ch.alpha, Fr::one().neg());
+        eng.vmul(den, d2);
+        eng.vbatch_inverse(den);
+        Vec num = eng.vclone(pk.val_a_evals);
+        eng.vscale(num, vv * ch.eta_a);
+        eng.vadd_scaled(num, vv * ch.eta_b, pk.val_b_evals);
+        eng.vadd_scaled(num, vv * ch.eta_c, pk.val_c_evals);
+        eng.vmul(num, den);
+        f_poly = std::move(num);
     }
-    std::vector<LabeledPoly> third = {{"g_2", g2_poly, true, K.n - 2, false}, {"h_2", h2_poly, false, 0, false}};
+    ntt(f_poly, K, true);
+    Vec g2_poly = eng.vshift_down(f_poly, 1);
+    Vec h2_poly;
+    {
+        const Vec &row = pk.index_polys[0].poly, &col = pk.index_polys[1].poly, &rc = pk.index_polys[5].poly;
+        Vec a_poly = eng.vclone(pk.index_polys[2].poly);
+        eng.vscale(a_poly, vv * ch.eta_a);
+        eng.vadd_scaled(a_poly, vv * ch.eta_b, pk.index_polys[3].poly);
+        eng.vadd_scaled(a_poly, vv * ch.eta_c, pk.index_polys[4].poly);
+        Vec b_poly = eng.vclone(rc);
+        eng.vadd_scaled(b_poly, ch.alpha.neg(), row);
+        eng.vadd_scaled(b_poly, ch.beta.neg(), col);
+        eng.vset(b_poly, 0, eng.vget(b_poly, 0) + ch.alpha * ch.beta);
+        Vec bf = poly_mul(b_poly, f_poly);
+        eng.vsub(a_poly, bf);
+        Vec rem;
+        eng.vdiv_vanishing(a_poly, K.n, &h2_poly, &rem);
+        if (eng.vlen(rem) != 0) throw MarlinError("prove: inner sumcheck identity does not hold on K");
+    }
+    std::vector<LabeledPoly<Engine>> third(2);
+    third[0].label = "g_2"; third[0].poly = std::move(g2_poly); third[0].has_bound = true; third[0].bound = K.n - 2;
+    third[1].label = "h_2"; third[1].poly = std::move(h2_poly);
+    ph.reset(); ph.reset(new ScopedPhase("r3_commit"));
     pc_commit(pk.ck, third, &zk_rng, &proof.commitments[2], &third_r);
+    ph.reset(); ph.reset(new ScopedPhase("r4_evals_lcs"));
     fs.absorb(round_bytes(proof.commitments[2]));
     ch.gamma = rand_fr(fs.rng());
     // ---- evaluations, linear combinations, openings -----------------------------------------------
     LcInputs in;
-    in.g1_beta = poly_eval(g1_poly, ch.beta);
-    in.g2_gamma = poly_eval(g2_poly, ch.gamma);
-    in.t_beta = poly_eval(t_poly, ch.beta);
-    in.zb_beta = poly_eval(zb_poly, ch.beta);
-    in.x_hat_beta = poly_eval(x_hat, ch.beta);
+    in.g1_beta = eng.veval(second[1].poly, ch.beta);
+    in.g2_gamma = eng.veval(third[0].poly, ch.gamma);
+    in.t_beta = eng.veval(second[0].poly, ch.beta);
+    in.zb_beta = eng.veval(zb_p, ch.beta);
+    in.x_hat_beta = eng.veval(x_hat, ch.beta);
     in.v_x_beta = X.vanishing_at(ch.beta);
     proof.evaluations = {in.g1_beta, in.g2_gamma, in.t_beta, in.zb_beta};
     {
@@ -672,35 +743,38 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     ch.xi = fr_from_u128(u);
     LinComb outer, inner;
     build_lcs(H, K, ch, in, &outer, &inner);
-    std::map<std::string, std::pair<const LabeledPoly*, const Randomness*>> by_label;
+    std::map<std::string, std::pair<const LabeledPoly<Engine>*, const Randomness*>> by_label;
     for (size_t i = 0; i < first.size(); i++) by_label[first[i].label] = {&first[i], &first_r[i]};
     for (size_t i = 0; i < second.size(); i++) by_label[second[i].label] = {&second[i], &second_r[i]};
     for (size_t i = 0; i < third.size(); i++) by_label[third[i].label] = {&third[i], &third_r[i]};
     static const Randomness no_rand;
     for (auto& ip : pk.index_polys) by_label[ip.label] = {&ip, &no_rand};
-    auto make_lc = [&](const LinComb& lc, LabeledPoly* lp, Randomness* lr) {
+    auto make_lc = [&](const LinComb& lc, LabeledPoly<Engine>* lp, Randomness* lr) {
         lp->label = lc.label;
+        lp->poly = eng.vzeros(0);
         for (auto& t : lc.terms) {
             auto& src = by_label.at(t.second);
-            poly_add_scaled(lp->poly, t.first, src.first->poly);
+            eng.vadd_scaled(lp->poly, t.first, src.first->poly);
             if (!src.second->blind.empty()) poly_add_scaled(lr->blind, t.first, src.second->blind);
         }
     };
-    LabeledPoly outer_p, inner_p;
+    LabeledPoly<Engine> outer_p, inner_p;
     Randomness outer_r, inner_r;
     make_lc(outer, &outer_p, &outer_r);
     make_lc(inner, &inner_p, &inner_r);
-    if (!(poly_eval(outer_p.poly, ch.beta) + outer.constant).is_zero())
+    if (!(eng.veval(outer_p.poly, ch.beta) + outer.constant).is_zero())
         throw MarlinError("prove: outer_sumcheck linear combination does not vanish at beta");
-    if (!(poly_eval(inner_p.poly, ch.gamma) + inner.constant).is_zero())
+    if (!(eng.veval(inner_p.poly, ch.gamma) + inner.constant).is_zero())
         throw MarlinError("prove: inner_sumcheck linear combination does not vanish at gamma");
     // query set, ordered by label within each point: beta {g_1, outer_sumcheck, t, z_b}; gamma {g_2, inner_sumcheck}
-    std::vector<const LabeledPoly*> at_beta = {by_label["g_1"].first, &outer_p, by_label["t"].first, by_label["z_b"].first};
+    std::vector<const LabeledPoly<Engine>*> at_beta = {by_label["g_1"].first, &outer_p, by_label["t"].first, by_label["z_b"].first};
     std::vector<const Randomness*> at_beta_r = {by_label["g_1"].second, &outer_r, by_label["t"].second, by_label["z_b"].second};
-    std::vector<const LabeledPoly*> at_gamma = {by_label["g_2"].first, &inner_p};
+    std::vector<const LabeledPoly<Engine>*> at_gamma = {by_label["g_2"].first, &inner_p};
     std::vector<const Randomness*> at_gamma_r = {by_label["g_2"].second, &inner_r};
+    ph.reset(); ph.reset(new ScopedPhase("r5_open"));
     proof.pc_proofs.push_back(pc_open(pk.ck, at_beta, at_beta_r, ch.beta, ch.xi));
     proof.pc_proofs.push_back(pc_open(pk.ck, at_gamma, at_gamma_r, ch.gamma, ch.xi));
+    ph.reset();
     return proof;
 }
 

@@ -10,8 +10,38 @@
 
 #include "../fp.cuh"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+
 namespace swb {
 namespace marlin {
+
+// SWB_TRACE=1: wall-clock breakdown of the host protocol code by phase (stderr)
+struct HostProfile {
+    std::map<std::string, double> acc;
+    bool on = false;
+    HostProfile() { const char* e = getenv("SWB_TRACE"); on = e && atoi(e) > 0; }
+    void report(const char* what) {
+        if (!on) return;
+        fprintf(stderr, "[swb trace] %s host phases:", what);
+        for (auto& kv : acc) fprintf(stderr, " %s=%.1fms", kv.first.c_str(), kv.second * 1e3);
+        fprintf(stderr, "\n");
+        acc.clear();
+    }
+};
+inline HostProfile& host_profile() { static HostProfile p; return p; }
+struct ScopedPhase {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    explicit ScopedPhase(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    ~ScopedPhase() {
+        if (!host_profile().on) return;
+        host_profile().acc[name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 using Poly = std::vector<Fr>;   // coefficients, low degree first; may carry leading zeros
 

@@ -28,25 +28,18 @@ public:
             key_[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) |
                       ((uint32_t)seed[4 * i + 3] << 24);
     }
+    // BlockRng buffers 64 words (4 ChaCha blocks) and next_u64 takes two consecutive words, also
+    // across a refill (index == 63: low word, refill, high word) -- so the output is one linear
+    // word stream and the generator state is just a position in it.
     uint32_t next_u32() {
-        if (index_ >= 64) refill();
-        return buf_[index_++];
+        const uint64_t g = pos_ >> 6;
+        if (g != group_) load_group(g);
+        return buf_[pos_++ & 63];
     }
     uint64_t next_u64() {
-        if (index_ < 63) {
-            uint64_t lo = buf_[index_], hi = buf_[index_ + 1];
-            index_ += 2;
-            return (hi << 32) | lo;
-        }
-        if (index_ >= 64) {
-            refill();
-            index_ = 2;
-            return ((uint64_t)buf_[1] << 32) | buf_[0];
-        }
-        uint64_t lo = buf_[63];
-        refill();
-        index_ = 1;
-        return ((uint64_t)buf_[0] << 32) | lo;
+        const uint64_t lo = next_u32();
+        const uint64_t hi = next_u32();
+        return (hi << 32) | lo;
     }
     bool next_bool() { return (int32_t)next_u32() < 0; }            // rand 0.8 Standard for bool
     // rand 0.8 `Standard` for u128: low word first
@@ -54,6 +47,18 @@ public:
         out[0] = next_u64();
         out[1] = next_u64();
     }
+    // words [pos, pos + count) of the stream without consuming them (ChaCha is counter based, so
+    // blocks are generated in parallel); seek() then moves the position
+    void peek_words(uint32_t* out, size_t count) const {
+        const uint64_t first_blk = pos_ >> 4, last_blk = (pos_ + count + 15) >> 4;
+        const size_t nblk = (size_t)(last_blk - first_blk);
+        std::vector<uint32_t> tmp(nblk * 16);
+#pragma omp parallel for schedule(static)
+        for (size_t b = 0; b < nblk; b++) block(first_blk + b, tmp.data() + 16 * b);
+        memcpy(out, tmp.data() + (pos_ & 15), count * sizeof(uint32_t));
+    }
+    uint64_t position() const { return pos_; }
+    void seek(uint64_t pos) { pos_ = pos; }
 
 private:
     static inline uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
@@ -78,16 +83,15 @@ private:
         }
         for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
     }
-    void refill() {
-        for (int i = 0; i < 4; i++) block(counter_ + i, buf_ + 16 * i);
-        counter_ += 4;
-        index_ = 0;
+    void load_group(uint64_t g) {
+        for (int i = 0; i < 4; i++) block(4 * g + i, buf_ + 16 * i);
+        group_ = g;
     }
     uint32_t key_[8];
     int rounds_;
-    uint64_t counter_ = 0;
+    uint64_t pos_ = 0;                 // next word of the linear stream
+    uint64_t group_ = ~0ull;           // which 64-word group buf_ holds
     uint32_t buf_[64];
-    int index_ = 64;
 };
 
 inline ChaChaRng test_rng() {
@@ -118,6 +122,32 @@ inline Fp<P> rand_fp(ChaChaRng& rng) {
     }
 }
 inline Fr rand_fr(ChaChaRng& rng) { return rand_fp<FrParams, 3>(rng); }
+// n consecutive Fr::rand draws (DensePolynomial::rand): identical stream consumption, but the
+// ChaCha blocks are produced in parallel and only the accept/reject walk is sequential
+inline void rand_fr_bulk(ChaChaRng& rng, Fr* out, size_t n) {
+    size_t done = 0;
+    std::vector<uint32_t> words;
+    while (done < n) {
+        size_t want = n - done;
+        if (want > (1u << 17)) want = 1u << 17;             // batches that stay in cache
+        const size_t cand = want + want + 64;               // acceptance is ~0.58
+        words.resize(cand * 8);
+        rng.peek_words(words.data(), words.size());
+        size_t used = 0;
+        for (size_t k = 0; k < cand && done < n; k++) {
+            const uint32_t* w = &words[8 * k];
+            used = k + 1;
+            Fr r;
+            for (int i = 0; i < 8; i++) r.l[i] = w[i];
+            r.l[7] &= 0xFFFFFFFFu >> 3;
+            bool lt = false;
+            for (int i = 7; i >= 0; i--)
+                if (r.l[i] != FrParams::mod(i)) { lt = r.l[i] < FrParams::mod(i); break; }
+            if (lt) out[done++] = r;
+        }
+        rng.seek(rng.position() + 8 * used);
+    }
+}
 inline Fq rand_fq(ChaChaRng& rng) { return rand_fp<FqParams, 7>(rng); }
 
 // ---- BLAKE2s-256 (RFC 7693), unkeyed ------------------------------------------------------------

@@ -1,0 +1,52 @@
+// Host implementation of the Engine vector interface used by the protocol templates
+// (marlin.hpp): Vec = std::vector<Fr> in RAM, every operation a parallel loop.  The CPU arm
+// (oracle build) derives its engine from this; the CUDA engine (marlin_abi.cu) implements the same
+// interface on device memory so that polynomials stay in HBM between NTTs and MSMs.
+#pragma once
+#include "poly.hpp"
+
+namespace swb {
+namespace marlin {
+
+struct HostVecOps {
+    using Vec = std::vector<Fr>;
+    Vec vzeros(size_t n) { return Vec(n, Fr::zero()); }
+    Vec vfrom(const std::vector<Fr>& h) { return h; }
+    std::vector<Fr> vhost(const Vec& v) { return v; }
+    Vec vclone(const Vec& v) { return v; }
+    void vresize(Vec& v, size_t n) { v.resize(n, Fr::zero()); }
+    size_t vlen(const Vec& v) {
+        size_t n = v.size();
+        while (n > 0 && v[n - 1].is_zero()) n--;
+        return n;
+    }
+    Fr vget(const Vec& v, size_t i) { return v[i]; }
+    void vset(Vec& v, size_t i, const Fr& x) { v[i] = x; }
+    void vmul(Vec& a, const Vec& b) {
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < a.size(); i++) a[i] = a[i] * b[i];
+    }
+    void vadd(Vec& a, const Vec& b) { poly_add(a, b); }
+    void vsub(Vec& a, const Vec& b) { poly_sub(a, b); }
+    void vadd_scaled(Vec& a, const Fr& c, const Vec& b) { poly_add_scaled(a, c, b); }
+    void vscale(Vec& a, const Fr& c) { poly_scale(a, c); }
+    void vlin(Vec& a, const Fr& c0, const Fr& c1) {
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < a.size(); i++) a[i] = c0 + c1 * a[i];
+    }
+    // a[off + i] += sign * b[i]
+    void vadd_offset(Vec& a, size_t off, const Vec& b, bool negate) {
+        if (a.size() < off + b.size()) a.resize(off + b.size(), Fr::zero());
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < b.size(); i++) a[off + i] = negate ? a[off + i] - b[i] : a[off + i] + b[i];
+    }
+    Fr veval(const Vec& p, const Fr& x) { return poly_eval(p, x); }
+    void vdiv_vanishing(const Vec& p, size_t n, Vec* q, Vec* r) { poly_divide_by_vanishing(p, n, q, r); }
+    Vec vdiv_linear(const Vec& p, const Fr& z) { return poly_divide_by_linear(p, z); }
+    void vbatch_inverse(Vec& v) { batch_inverse(v); }
+    Vec vshift_down(const Vec& p, size_t k) { return k < p.size() ? Vec(p.begin() + k, p.end()) : Vec(); }
+    Vec vdomain(uint32_t log_n) { return Domain((size_t)1 << log_n).elements(); }
+};
+
+}  // namespace marlin
+}  // namespace swb

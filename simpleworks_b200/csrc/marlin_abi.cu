@@ -4,18 +4,214 @@
 // engine in libswb200.
 #include "ctx.hpp"
 #include "marlin/c_api_impl.hpp"
+#include "polyops.hpp"
 
 using namespace swb;
 using namespace swb::marlin;
 
 namespace {
 
-struct GpuEngine {
-    swb_ctx* c;
-    void fail(const char* what) { throw MarlinError(std::string(what) + ": " + swb_last_error(c)); }
-    void ntt(Fr* v, uint32_t log_n, bool inverse, bool coset) {
-        if (swb_ntt_fr(c, reinterpret_cast<swb_fr*>(v), log_n, inverse, coset) != SWB_OK) fail("ntt");
+// Fr vector in HBM, owned; stream-ordered allocation from the device's default pool
+struct DVec {
+    swb_ctx* c = nullptr;
+    Fr* p = nullptr;
+    size_t n = 0, cap = 0;
+    DVec() {}
+    DVec(const DVec&) = delete;
+    DVec& operator=(const DVec&) = delete;
+    DVec(DVec&& o) noexcept : c(o.c), p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    DVec& operator=(DVec&& o) noexcept {
+        if (this != &o) {
+            release();
+            c = o.c; p = o.p; n = o.n; cap = o.cap;
+            o.p = nullptr; o.n = o.cap = 0;
+        }
+        return *this;
     }
+    ~DVec() { release(); }
+    void release() {
+        if (p && c) cudaFreeAsync(p, c->stream);
+        p = nullptr;
+        n = cap = 0;
+    }
+    size_t size() const { return n; }
+};
+
+struct GpuEngine;
+// SWB_TRACE=2: every engine operation is bracketed by stream synchronisations and accounted under
+// "op:<name>" in the host profile (serialises the stream; for attribution only)
+struct OpTimer {
+    swb_ctx* c;
+    const char* name;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    OpTimer(swb_ctx* ctx, const char* n) : c(ctx), name(n), on(ctx->trace >= 2) {
+        if (on) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
+    }
+    ~OpTimer() {
+        if (!on) return;
+        cudaStreamSynchronize(c->stream);
+        host_profile().acc[std::string("op:") + name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+
+struct GpuEngine {
+    using Vec = DVec;
+    swb_ctx* c;
+    explicit GpuEngine(swb_ctx* ctx) : c(ctx) {
+        cudaSetDevice(c->device);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            uint64_t keep = ~0ull;           // keep freed blocks cached: the rounds re-allocate the same sizes
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    [[noreturn]] void fail(const char* what) { throw MarlinError(std::string(what) + ": " + swb_last_error(c)); }
+    void ck(int rc, const char* what) { if (rc != SWB_OK) fail(what); }
+    void cu(cudaError_t e, const char* what) {
+        if (e != cudaSuccess) throw MarlinError(std::string(what) + ": " + cudaGetErrorString(e));
+    }
+    // ---- storage ----------------------------------------------------------------------------
+    Vec alloc(size_t n) {
+        Vec v;
+        v.c = c;
+        v.n = v.cap = n;
+        if (n) cu(cudaMallocAsync((void**)&v.p, n * sizeof(Fr), c->stream), "cudaMallocAsync");
+        return v;
+    }
+    Vec vzeros(size_t n) {
+        OpTimer ot_(c, "vzeros");
+        Vec v = alloc(n);
+        if (n) cu(cudaMemsetAsync(v.p, 0, n * sizeof(Fr), c->stream), "memset");
+        return v;
+    }
+    Vec vfrom(const std::vector<Fr>& h) {
+        OpTimer ot_(c, "vfrom");
+        Vec v = alloc(h.size());
+        if (!h.empty()) {
+            cu(cudaMemcpyAsync(v.p, h.data(), h.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream), "H2D");
+            cu(cudaStreamSynchronize(c->stream), "sync");     // h may be a temporary
+        }
+        return v;
+    }
+    std::vector<Fr> vhost(const Vec& v) {
+        OpTimer ot_(c, "vhost");
+        std::vector<Fr> h(v.n);
+        if (v.n) {
+            cu(cudaMemcpyAsync(h.data(), v.p, v.n * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream), "D2H");
+            cu(cudaStreamSynchronize(c->stream), "sync");
+        }
+        return h;
+    }
+    Vec vclone(const Vec& v) {
+        OpTimer ot_(c, "vclone");
+        Vec r = alloc(v.n);
+        if (v.n) cu(cudaMemcpyAsync(r.p, v.p, v.n * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream), "D2D");
+        return r;
+    }
+    void vresize(Vec& v, size_t n) {
+        OpTimer ot_(c, "vresize");
+        if (!v.c) v.c = c;
+        if (n <= v.cap) {
+            if (n > v.n) cu(cudaMemsetAsync(v.p + v.n, 0, (n - v.n) * sizeof(Fr), c->stream), "memset");
+            v.n = n;
+            return;
+        }
+        Vec r = alloc(n);
+        if (v.n) cu(cudaMemcpyAsync(r.p, v.p, v.n * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream), "D2D");
+        cu(cudaMemsetAsync(r.p + v.n, 0, (n - v.n) * sizeof(Fr), c->stream), "memset");
+        v = std::move(r);
+    }
+    size_t vlen(const Vec& v) {
+        OpTimer ot_(c, "vlen");
+        size_t len = 0;
+        ck(poly_len_dev(c, v.p, v.n, &len), "poly_len");
+        return len;
+    }
+    Fr vget(const Vec& v, size_t i) {
+        OpTimer ot_(c, "vget");
+        if (i >= v.n) throw MarlinError("vget: index out of range");
+        Fr x;
+        cu(cudaMemcpyAsync(&x, v.p + i, sizeof(Fr), cudaMemcpyDeviceToHost, c->stream), "D2H");
+        cu(cudaStreamSynchronize(c->stream), "sync");
+        return x;
+    }
+    void vset(Vec& v, size_t i, const Fr& x) {
+        OpTimer ot_(c, "vset");
+        if (i >= v.n) throw MarlinError("vset: index out of range");
+        cu(cudaMemcpyAsync(v.p + i, &x, sizeof(Fr), cudaMemcpyHostToDevice, c->stream), "H2D");
+        cu(cudaStreamSynchronize(c->stream), "sync");
+    }
+    // ---- element-wise ---------------------------------------------------------------------------
+    void vmul(Vec& a, const Vec& b) {
+        OpTimer ot_(c, "vmul");
+        if (a.n != b.n) throw MarlinError("vmul: size mismatch");
+        ck(poly_mul_ew(c, a.p, b.p, a.n), "vmul");
+    }
+    void vadd(Vec& a, const Vec& b) {
+        OpTimer ot_(c, "vadd");
+        if (a.n < b.n) vresize(a, b.n);
+        ck(poly_add_ew(c, a.p, b.p, b.n), "vadd");
+    }
+    void vsub(Vec& a, const Vec& b) {
+        OpTimer ot_(c, "vsub");
+        if (a.n < b.n) vresize(a, b.n);
+        ck(poly_sub_ew(c, a.p, b.p, b.n), "vsub");
+    }
+    void vadd_scaled(Vec& a, const Fr& s, const Vec& b) {
+        OpTimer ot_(c, "vadd_scaled");
+        if (a.n < b.n) vresize(a, b.n);
+        ck(poly_add_scaled_ew(c, a.p, s, b.p, b.n), "vadd_scaled");
+    }
+    void vscale(Vec& a, const Fr& s) {
+        OpTimer ot_(c, "vscale"); ck(poly_scale_ew(c, a.p, s, a.n), "vscale"); }
+    void vlin(Vec& a, const Fr& c0, const Fr& c1) {
+        OpTimer ot_(c, "vlin"); ck(poly_lin_ew(c, a.p, c0, c1, a.n), "vlin"); }
+    void vadd_offset(Vec& a, size_t off, const Vec& b, bool negate) {
+        OpTimer ot_(c, "vadd_offset");
+        if (a.n < off + b.n) vresize(a, off + b.n);
+        ck(negate ? poly_sub_ew(c, a.p + off, b.p, b.n) : poly_add_ew(c, a.p + off, b.p, b.n), "vadd_offset");
+    }
+    // ---- polynomial -------------------------------------------------------------------------------
+    Fr veval(const Vec& p, const Fr& x) {
+        OpTimer ot_(c, "veval");
+        Fr out;
+        ck(poly_eval_dev(c, p.p, p.n, x, &out), "veval");
+        return out;
+    }
+    void vdiv_vanishing(const Vec& p, size_t n, Vec* q, Vec* r) {
+        OpTimer ot_(c, "vdiv_vanishing");
+        *q = alloc(p.n > n ? p.n - n : 0);
+        *r = alloc(n);
+        ck(poly_div_vanishing_dev(c, q->p, r->p, p.p, p.n, n), "vdiv_vanishing");
+    }
+    Vec vdiv_linear(const Vec& p, const Fr& z) {
+        OpTimer ot_(c, "vdiv_linear");
+        Vec q = alloc(p.n > 1 ? p.n - 1 : 0);
+        ck(poly_div_linear_dev(c, q.p, p.p, p.n, z), "vdiv_linear");
+        return q;
+    }
+    void vbatch_inverse(Vec& v) {
+        OpTimer ot_(c, "vbatch_inverse"); ck(swb_fr_batch_inverse_dev(c, reinterpret_cast<swb_fr*>(v.p), v.n), "vbatch_inverse"); }
+    Vec vshift_down(const Vec& p, size_t k) {
+        OpTimer ot_(c, "vshift_down");
+        if (k >= p.n) return alloc(0);
+        Vec r = alloc(p.n - k);
+        cu(cudaMemcpyAsync(r.p, p.p + k, (p.n - k) * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream), "D2D");
+        return r;
+    }
+    Vec vdomain(uint32_t log_n) {
+        OpTimer ot_(c, "vdomain");
+        Vec r = alloc((size_t)1 << log_n);
+        ck(poly_powers_dev(c, r.p, r.n, Domain((size_t)1 << log_n).gen), "vdomain");
+        return r;
+    }
+    void vntt(Vec& v, uint32_t log_n, bool inverse, bool coset) {
+        OpTimer ot_(c, "vntt");
+        if (v.n != ((size_t)1 << log_n)) throw MarlinError("vntt: size mismatch");
+        ck(swb_ntt_fr_dev(c, reinterpret_cast<swb_fr*>(v.p), log_n, inverse, coset), "ntt");
+    }
+    // ---- bases / MSM --------------------------------------------------------------------------------
     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n) {
         swb_g1_jacobian gj;
         memset(&gj, 0, sizeof gj);
@@ -29,12 +225,12 @@ struct GpuEngine {
         swb_fr b;
         memcpy(b.l, beta.l, 32);
         swb_bases* out = nullptr;
-        if (swb_bases_from_powers(c, &gj, &b, n, &out) != SWB_OK) fail("bases_from_powers");
+        ck(swb_bases_from_powers(c, &gj, &b, n, &out), "bases_from_powers");
         return out;
     }
     void export_bases(void* h, size_t offset, size_t n, G1Point* out) {
         std::vector<swb_g1_affine> tmp(n);
-        if (swb_bases_export(c, static_cast<swb_bases*>(h), offset, n, tmp.data()) != SWB_OK) fail("bases_export");
+        ck(swb_bases_export(c, static_cast<swb_bases*>(h), offset, n, tmp.data()), "bases_export");
         for (size_t i = 0; i < n; i++) {
             out[i].infinity = tmp[i].infinity != 0;
             memcpy(out[i].x.l, tmp[i].x.l, 48);
@@ -42,10 +238,10 @@ struct GpuEngine {
         }
     }
     void free_bases(void* h) { swb_bases_free(static_cast<swb_bases*>(h)); }
-    G1Point msm(void* h, size_t offset, const Fr* scalars_mont, size_t n) {
+    G1Point msm(void* h, size_t offset, const Vec& scalars, size_t n) {
+        OpTimer ot_(c, "msm");
         swb_g1_jacobian out;
-        if (swb_msm_g1_fr(c, static_cast<swb_bases*>(h), offset, reinterpret_cast<const swb_fr*>(scalars_mont), n, &out) != SWB_OK)
-            fail("msm");
+        ck(swb_msm_g1_fr_dev(c, static_cast<swb_bases*>(h), offset, reinterpret_cast<const swb_fr*>(scalars.p), n, &out), "msm");
         G1Point p = G1Point::identity();
         Fq z;
         memcpy(z.l, out.z.l, 48);
@@ -101,7 +297,7 @@ void swb_r1cs_free(swb_r1cs* cs) {
 
 int swb_marlin_universal_setup(swb_ctx* c, size_t nc, size_t nv, size_t nnz, swb_rng* rng, swb_srs** out) {
     if (!c || !rng || !out) return SWB_EARG;
-    auto* s = new swb_srs{GpuEngine{c}, nullptr};
+    auto* s = new swb_srs{GpuEngine(c), nullptr};
     std::string err;
     int rc = Api::setup(s->eng, nc, nv, nnz, &rng->h, &s->h, &err);
     if (rc) {
@@ -122,7 +318,7 @@ int swb_marlin_index(swb_ctx* c, const swb_srs* srs, const swb_r1cs* cs, swb_pk*
     std::string err;
     auto* p = new swb_pk{nullptr};
     auto* v = new swb_vk{nullptr};
-    GpuEngine eng{c};
+    GpuEngine eng(c);
     int rc = Api::index(eng, srs->h, cs->h, &p->h, &v->h, &err);
     if (rc) {
         delete p;
@@ -146,7 +342,7 @@ void swb_vk_free(swb_vk* v) {
 int swb_marlin_prove(swb_ctx* c, const swb_pk* pk, const swb_r1cs* cs, swb_rng* rng, uint8_t** proof, size_t* len) {
     if (!c || !pk || !cs || !rng || !proof || !len) return SWB_EARG;
     std::string err;
-    GpuEngine eng{c};
+    GpuEngine eng(c);
     int rc = Api::prove(eng, pk->h, cs->h, &rng->h, proof, len, &err);
     if (rc) return swb::set_err(c, SWB_EINTERNAL, "prove: %s", err.c_str());
     return SWB_OK;
