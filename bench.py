@@ -122,7 +122,7 @@ def marlin_extra(be, args) -> dict:
     from simpleworks_b200 import _gen
     from simpleworks_b200.binding import ConstraintSystem, Marlin, Rng
     m = Marlin(be)
-    out = {"circuit": "mul-chain x_i*x_{i+1}=x_{i+2}, 1 public input", "verifier": "G1-side trapdoor check (no pairing)"}
+    out = {"circuit": "mul-chain x_i*x_{i+1}=x_{i+2}, 1 public input", "verifier": "pairing check on the host (BLS12-377 ate pairing)"}
 
     def gpu_run(lg, proofs):
         n = (1 << lg) - 2

@@ -150,9 +150,9 @@ int  swb_ntt_fr_batch_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, size_t ba
  * verify exclude the leading one, as in simple_merkle_tree.rs:133-143.
  * An unsatisfied instance makes swb_marlin_prove fail (the reference panics through a
  * debug_assert, examples/schnorr-signature/main.rs:214-217).
- * NOTE: verification checks the KZG opening equations in G1 with the setup trapdoor instead of the
- * pairing product (the pairing tower is not implemented); keys from this library are a test
- * harness, not deployable verifier keys. */
+ * Verification evaluates the KZG pairing-product check on the host (Fq2/Fq6/Fq12 tower, ate
+ * pairing); the verifying key holds g, gamma_g, h, beta_h and the degree-bound shift powers, never
+ * the trapdoor. */
 typedef struct swb_rng swb_rng;
 typedef struct swb_r1cs swb_r1cs;
 typedef struct swb_srs swb_srs;
@@ -182,8 +182,11 @@ int  swb_marlin_index(swb_ctx*, const swb_srs*, const swb_r1cs*, swb_pk** pk, sw
 void swb_pk_free(swb_pk*);
 void swb_vk_free(swb_vk*);
 int  swb_marlin_prove(swb_ctx*, const swb_pk*, const swb_r1cs* cs_with_assignment, swb_rng*, uint8_t** proof, size_t* len);
+/* rng supplies the scalar that folds the two opening equations into one pairing product (the
+ * reference passes its StdRng, mod.rs:79-86); NULL uses a fresh test_rng().  ctx may be NULL:
+ * verification is host arithmetic (BLS12-377 pairing), no GPU involved. */
 int  swb_marlin_verify(swb_ctx*, const swb_vk*, const swb_fr* public_inputs, size_t n, const uint8_t* proof, size_t len,
-                       int* ok);
+                       swb_rng*, int* ok);
 void swb_bytes_free(uint8_t*);
 
 #ifdef __cplusplus

@@ -130,21 +130,56 @@ size_t orc_srs_max_degree(void* srs) { return static_cast<SrsHandle<CpuEngine>*>
 void orc_srs_free(void* srs) { delete static_cast<SrsHandle<CpuEngine>*>(srs); }
 int orc_marlin_index(void* srs, void* cs, void** pk, void** vk) {
     PkHandle<CpuEngine>* p = nullptr;
-    VkHandle<CpuEngine>* v = nullptr;
+    VkHandle* v = nullptr;
     int rc = Api::index(g_engine, static_cast<SrsHandle<CpuEngine>*>(srs), static_cast<R1csHandle*>(cs), &p, &v, &g_err);
     *pk = p;
     *vk = v;
     return rc;
 }
 void orc_pk_free(void* pk) { delete static_cast<PkHandle<CpuEngine>*>(pk); }
-void orc_vk_free(void* vk) { delete static_cast<VkHandle<CpuEngine>*>(vk); }
+void orc_vk_free(void* vk) { delete static_cast<VkHandle*>(vk); }
 int orc_marlin_prove(void* pk, void* cs, void* rng, uint8_t** bytes, size_t* len) {
     return Api::prove(g_engine, static_cast<PkHandle<CpuEngine>*>(pk), static_cast<R1csHandle*>(cs), static_cast<RngHandle*>(rng),
                       bytes, len, &g_err);
 }
-int orc_marlin_verify(void* vk, const uint64_t* pi, size_t n, const uint8_t* proof, size_t len, int* ok) {
-    return Api::verify(static_cast<VkHandle<CpuEngine>*>(vk), pi, n, proof, len, ok, &g_err);
+int orc_marlin_verify(void* vk, const uint64_t* pi, size_t n, const uint8_t* proof, size_t len, void* rng, int* ok) {
+    return Api::verify(static_cast<VkHandle*>(vk), pi, n, proof, len, static_cast<RngHandle*>(rng), ok, &g_err);
 }
 void orc_bytes_free(uint8_t* p) { free(p); }
+
+/* self-test of the pairing tower used by the verifier: field inverses, tower relations, a G2 point
+ * of order r from the derived cofactor, bilinearity, non-degeneracy, the product check; returns a
+ * bit mask of failed checks */
+int orc_pairing_selftest() {
+    ChaChaRng rng = test_rng();
+    int bad = 0;
+    Fq2 a2 = {rand_fq(rng), rand_fq(rng)};
+    if (!(a2 * a2.inverse() == Fq2::one())) bad |= 1;
+    Fq6 a6 = {{rand_fq(rng), rand_fq(rng)}, {rand_fq(rng), rand_fq(rng)}, {rand_fq(rng), rand_fq(rng)}};
+    if (!(a6 * a6.inverse() == Fq6::one())) bad |= 2;
+    Fq12 a12 = {a6, a6 * a6};
+    if (!(a12 * a12.inverse() == Fq12::one())) bad |= 4;
+    Fq6 v = Fq6::zero();
+    v.c1 = Fq2::one();
+    Fq6 uu = Fq6::zero();
+    uu.c0 = {Fq::zero(), Fq::one()};
+    if (!(v * v * v == uu)) bad |= 8;
+    Fq2 sq = a2.sqr(), r;
+    if (!fq2_sqrt(sq, &r) || !(r.sqr() == sq)) bad |= 16;
+    G2Point h = g2_rand(rng);
+    uint32_t rw[8];
+    for (int i = 0; i < 8; i++) rw[i] = FrParams::mod(i);
+    if (!g2_on_curve(h) || h.infinity || !g2_mul_words(h, rw, 8).infinity) bad |= 32;
+    G1Point g = g1_generator();
+    Fr a = rand_fr(rng), b = rand_fr(rng);
+    Fq12 e = pairing(g, h);
+    if (e == Fq12::one()) bad |= 64;
+    Fr ab = (a * b).to_canonical();
+    if (!(pairing(g1_mul_fr(g, a), g2_mul_fr(h, b)) == e.pow_words(ab.l, 8))) bad |= 128;
+    if (!(e.pow_words(rw, 8) == Fq12::one())) bad |= 256;
+    if (!pairing_product_is_one({{g1_mul_fr(g, a), h}, {g1_neg(g), g2_mul_fr(h, a)}})) bad |= 512;
+    if (pairing_product_is_one({{g1_mul_fr(g, a), h}, {g1_neg(g), g2_mul_fr(h, b)}})) bad |= 1024;
+    return bad;
+}
 
 }  // extern "C"

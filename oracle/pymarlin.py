@@ -43,7 +43,7 @@ def lib():
         L.orc_pk_free.argtypes = [vp]
         L.orc_vk_free.argtypes = [vp]
         L.orc_marlin_prove.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]
-        L.orc_marlin_verify.argtypes = [vp, vp, sz, ctypes.c_char_p, sz, ctypes.POINTER(i32)]
+        L.orc_marlin_verify.argtypes = [vp, vp, sz, ctypes.c_char_p, sz, vp, ctypes.POINTER(i32)]
         L.orc_bytes_free.argtypes = [ctypes.POINTER(ctypes.c_uint8)]
         _LIB = L
     return _LIB
@@ -113,8 +113,9 @@ def prove(pk, cs: R1cs, rng: Rng) -> bytes:
     return out
 
 
-def verify(vk, public_inputs_mont: np.ndarray, proof: bytes) -> bool:
+def verify(vk, public_inputs_mont: np.ndarray, proof: bytes, rng: Rng | None = None) -> bool:
     ok = ctypes.c_int()
     pi = np.ascontiguousarray(public_inputs_mont, dtype=np.uint64).reshape(-1, 4)
-    _chk(lib().orc_marlin_verify(vk, pi.ctypes.data_as(ctypes.c_void_p), pi.shape[0], proof, len(proof), ctypes.byref(ok)))
+    _chk(lib().orc_marlin_verify(vk, pi.ctypes.data_as(ctypes.c_void_p), pi.shape[0], proof, len(proof),
+                                 rng.h if rng else None, ctypes.byref(ok)))
     return bool(ok.value)

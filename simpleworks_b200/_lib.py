@@ -94,7 +94,7 @@ def load() -> ctypes.CDLL:
         "swb_pk_free": (None, [vp]),
         "swb_vk_free": (None, [vp]),
         "swb_marlin_prove": (i32, [vp, vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
-        "swb_marlin_verify": (i32, [vp, vp, vp, sz, ctypes.c_char_p, sz, ctypes.POINTER(i32)]),
+        "swb_marlin_verify": (i32, [vp, vp, vp, sz, ctypes.c_char_p, sz, vp, ctypes.POINTER(i32)]),
         "swb_bytes_free": (None, [ctypes.POINTER(ctypes.c_uint8)]),
         "swb_msm_set_window_bits": (i32, [vp, i32]),
         "swb_g1_sum_jacobian": (i32, [vp, vp, sz, vp]),

@@ -357,8 +357,10 @@ class Marlin:
         self._lib.swb_bytes_free(p)
         return out
 
-    def verify_proof(self, vk, public_inputs: np.ndarray, proof: bytes) -> bool:
+    def verify_proof(self, vk, public_inputs: np.ndarray, proof: bytes, rng: "Rng | None" = None) -> bool:
+        """verify_proof(deserialize_proof(bytes)): pairing check on the host"""
         ok = ctypes.c_int()
         pi = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
-        self.be._check(self._lib.swb_marlin_verify(self.be._h, vk, pi.ctypes.data, pi.shape[0], proof, len(proof), ctypes.byref(ok)))
+        self.be._check(self._lib.swb_marlin_verify(self.be._h, vk, pi.ctypes.data, pi.shape[0], proof, len(proof),
+                                                   rng._h if rng else None, ctypes.byref(ok)))
         return bool(ok.value)

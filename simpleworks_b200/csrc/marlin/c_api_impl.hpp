@@ -25,9 +25,8 @@ template <class Engine>
 struct PkHandle {
     ProvingKey<Engine> pk;
 };
-template <class Engine>
 struct VkHandle {
-    VerifyingKey<Engine> vk;
+    VerifyingKey vk;
 };
 
 inline Fr fr_from_abi(const uint64_t l[4]) {
@@ -93,11 +92,11 @@ struct MarlinApi {
             return 4;
         }
     }
-    static int index(Engine& eng, const SrsHandle<Engine>* srs, const R1csHandle* cs, PkHandle<Engine>** pk, VkHandle<Engine>** vk,
+    static int index(Engine& eng, const SrsHandle<Engine>* srs, const R1csHandle* cs, PkHandle<Engine>** pk, VkHandle** vk,
                      std::string* err) {
         try {
             auto* p = new PkHandle<Engine>();
-            auto* v = new VkHandle<Engine>();
+            auto* v = new VkHandle();
             marlin::index(eng, *srs->srs, cs->cs, &p->pk, &v->vk);
             *pk = p;
             *vk = v;
@@ -122,15 +121,17 @@ struct MarlinApi {
             return 4;
         }
     }
-    static int verify(const VkHandle<Engine>* vk, const uint64_t* public_inputs, size_t n, const uint8_t* proof, size_t len, int* ok,
-                      std::string* err) {
+    // rng may be null: a fresh test_rng() then supplies the batching scalar (any value is sound to test with)
+    static int verify(const VkHandle* vk, const uint64_t* public_inputs, size_t n, const uint8_t* proof, size_t len, RngHandle* rng,
+                      int* ok, std::string* err) {
         try {
             Proof pr;
             *ok = 0;
             if (!Proof::deserialize(proof, len, &pr)) return 0;      // malformed proof: rejected, not an error
             std::vector<Fr> pi(n);
             for (size_t i = 0; i < n; i++) pi[i] = fr_from_abi(public_inputs + 4 * i);
-            *ok = marlin::verify(vk->vk, pi, pr) ? 1 : 0;
+            ChaChaRng local = test_rng();
+            *ok = marlin::verify(vk->vk, pi, pr, rng ? rng->rng : local) ? 1 : 0;
             return 0;
         } catch (const std::exception& e) {
             *err = e.what();

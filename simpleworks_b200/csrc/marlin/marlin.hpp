@@ -23,10 +23,9 @@
 //     G1Point msm(void* h, size_t offset, const Vec& scalars_mont, size_t n);  // sum s_i * base[offset+i]
 //   };
 //
-// Verification: the KZG opening equations are checked in G1 with the setup trapdoor beta
-// (C - v*g - v'*gamma_g == (beta - z) * W) instead of the pairing product; the algebra, transcript
-// and linear combinations are those of the pairing verifier.  A verifying key therefore carries the
-// trapdoor and is only meaningful as a test harness (the pairing tower is SURVEY 8f-3).
+// Verification is the pairing check of kzg10::batch_check on the host (marlin/pairing.hpp): the two
+// opening equations are folded with a verifier-side random scalar into one pairing-product test
+// e(sum r_i (C_i - v_i g - v'_i gamma_g + z_i W_i), h) * e(-sum r_i W_i, beta h) == 1.
 #pragma once
 #include <array>
 #include <map>
@@ -35,6 +34,7 @@
 #include <string>
 
 #include "curve_host.hpp"
+#include "pairing.hpp"
 #include "poly.hpp"
 #include "r1cs.hpp"
 #include "rng.hpp"
@@ -69,7 +69,7 @@ struct UniversalSrs {
     void* powers_of_g = nullptr;              // resident beta^i * g, i <= max_degree
     std::vector<G1Point> powers_of_gamma_g;   // beta^i * gamma_g, i <= hiding_bound + 1 (the only ones trim keeps)
     G1Point g, gamma_g;
-    Fr beta;                                  // setup trapdoor, kept for the G1-side opening check
+    G2Point h, beta_h;                        // verifier side (the trapdoor beta itself is dropped after setup)
     ~UniversalSrs() {
         if (eng && powers_of_g) eng->free_bases(powers_of_g);
     }
@@ -237,11 +237,20 @@ struct ProvingKey {
     std::vector<Commitment> index_comms;
     CommitterKey<Engine> ck;
 };
-template <class Engine>
+// IndexVerifierKey: index info + index commitments + MarlinKZG10's VerifierKey (g, gamma_g, h, beta_h,
+// degree_bounds_and_shift_powers); self-contained, independent of the engine
 struct VerifyingKey {
     IndexInfo info;
     std::vector<Commitment> index_comms;
-    const UniversalSrs<Engine>* srs = nullptr;      // g, gamma_g, shift powers and (test harness) beta
+    G1Point g, gamma_g;
+    G2Point h, beta_h;
+    size_t max_degree = 0;
+    std::vector<std::pair<size_t, G1Point>> shift_powers;   // (bound, beta^(D - bound) g)
+    const G1Point* shift_power(size_t bound) const {
+        for (auto& sp : shift_powers)
+            if (sp.first == bound) return &sp.second;
+        return nullptr;
+    }
 };
 
 inline void put_commitment_bytes(std::vector<uint8_t>& out, const Commitment& c) {   // ToBytes, 195 B
@@ -263,24 +272,25 @@ std::unique_ptr<UniversalSrs<Engine>> universal_setup(Engine& eng, size_t num_co
     srs->eng = &eng;
     srs->max_degree = ahp_max_degree(num_constraints, num_variables, num_non_zero);
     // KZG10::setup draw order: beta, g, gamma_g, h (G2)
-    srs->beta = rand_fr(rng);
+    const Fr beta = rand_fr(rng);
     srs->g = g1_rand(rng);
     srs->gamma_g = g1_rand(rng);
-    g2_rand_consume(rng);
-    srs->powers_of_g = eng.bases_from_powers(srs->g, srs->beta, srs->max_degree + 1);
+    srs->h = g2_rand(rng);
+    srs->beta_h = g2_mul_fr(srs->h, beta);
+    srs->powers_of_g = eng.bases_from_powers(srs->g, beta, srs->max_degree + 1);
     // upstream also tabulates all max_degree + 2 powers of gamma_g; only the first
     // hiding_bound + 2 = 3 survive trim, so only those are materialised here
     srs->powers_of_gamma_g.resize(3);
     Fr bp = Fr::one();
     for (int i = 0; i < 3; i++) {
         srs->powers_of_gamma_g[i] = g1_mul_fr(srs->gamma_g, bp);
-        bp = bp * srs->beta;
+        bp = bp * beta;
     }
     return srs;
 }
 
 template <class Engine>
-void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Engine>* pk, VerifyingKey<Engine>* vk) {
+void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Engine>* pk, VerifyingKey* vk) {
     cs.pad_instance();
     cs.make_square();
     const size_t nvar = cs.num_variables();
@@ -373,7 +383,17 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     pc_commit(pk->ck, pk->index_polys, nullptr, &pk->index_comms, &unused);
     vk->info = pk->info;
     vk->index_comms = pk->index_comms;
-    vk->srs = &srs;
+    vk->g = srs.g;
+    vk->gamma_g = srs.gamma_g;
+    vk->h = srs.h;
+    vk->beta_h = srs.beta_h;
+    vk->max_degree = srs.max_degree;
+    vk->shift_powers.clear();
+    for (size_t bound : {H.n - 2, K.n - 2}) {            // get_degree_bounds: |H| - 2, |K| - 2
+        G1Point sp;
+        eng.export_bases(srs.powers_of_g, srs.max_degree - bound, 1, &sp);
+        vk->shift_powers.push_back({bound, sp});
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -781,12 +801,10 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
 // ------------------------------------------------------------------------------------------------
 // verify (Marlin::verify) -- public input WITHOUT the leading one, padded internally
 // ------------------------------------------------------------------------------------------------
-template <class Engine>
-bool verify(const VerifyingKey<Engine>& vk, const std::vector<Fr>& public_input_unpadded, const Proof& proof) {
+inline bool verify(const VerifyingKey& vk, const std::vector<Fr>& public_input_unpadded, const Proof& proof, ChaChaRng& rng) {
     if (proof.commitments.size() != 3 || proof.commitments[0].size() != 4 || proof.commitments[1].size() != 3 ||
         proof.commitments[2].size() != 2 || proof.evaluations.size() != 4 || proof.pc_proofs.size() != 2)
         return false;
-    const UniversalSrs<Engine>& srs = *vk.srs;
     Domain H(vk.info.num_constraints), K(vk.info.num_non_zero), X(public_input_unpadded.size() + 1);
     if (X.n != vk.info.num_instance) return false;
     std::vector<Fr> public_input = public_input_unpadded;
@@ -855,38 +873,48 @@ bool verify(const VerifyingKey<Engine>& vk, const std::vector<Fr>& public_input_
     };
     const Commitment outer_c = lc_comm(outer), inner_c = lc_comm(inner);
     struct Item { const Commitment* c; Fr value; bool bounded; size_t bound; };
-    auto check_point = [&](const std::vector<Item>& items, const Fr& z, const PcProof& pr) {
-        // accumulate_commitments_and_values + the KZG check with the pairing replaced by the trapdoor
+    // kzg10::batch_check: total_c = sum r_i (C_i - v_i g - v'_i gamma_g + z_i W_i), total_w = sum r_i W_i,
+    // r_0 = 1, r_i = u128::rand(rng); accept iff e(total_c, h) == e(total_w, beta_h)
+    G1Xyzz total_c = G1Xyzz::identity(), total_w = G1Xyzz::identity();
+    bool ok = true;
+    auto add_scaled_to = [&](G1Xyzz& acc, const G1Point& p, const Fr& s) {
+        G1Point t = g1_mul_fr(p, s);
+        if (!t.infinity) acc.add_affine(t.x, t.y);
+    };
+    auto accumulate_point = [&](const std::vector<Item>& items, const Fr& z, const PcProof& pr, const Fr& randomizer) {
+        // accumulate_commitments_and_values (per-polynomial opening challenge powers)
         G1Xyzz cc = G1Xyzz::identity();
         Fr cv = Fr::zero(), chal = Fr::one();
-        auto add_scaled = [&](const G1Point& p, const Fr& s) {
-            G1Point t = g1_mul_fr(p, s);
-            if (!t.infinity) cc.add_affine(t.x, t.y);
-        };
         for (auto& it : items) {
-            add_scaled(it.c->comm, chal);
+            add_scaled_to(cc, it.c->comm, chal);
             cv = cv + it.value * chal;
             chal = chal * ch.xi;
             if (it.bounded) {
-                // shifted_comm - value * beta^(D - bound) g, times the next challenge power
-                const Fr shift = fr_pow(srs.beta, srs.max_degree - it.bound);
-                add_scaled(it.c->shifted, chal);
-                add_scaled(srs.g, (it.value * shift * chal).neg());
+                // (shifted_comm - value * beta^(D - bound) g) * next challenge power
+                const G1Point* sp = vk.shift_power(it.bound);
+                if (!sp) { ok = false; return; }
+                add_scaled_to(cc, it.c->shifted, chal);
+                add_scaled_to(cc, *sp, (it.value * chal).neg());
                 chal = chal * ch.xi;
             }
         }
-        add_scaled(srs.g, cv.neg());
-        if (pr.has_random_v) add_scaled(srs.gamma_g, pr.random_v.neg());
-        G1Point lhs = to_affine(cc);
-        G1Point rhs = g1_mul_fr(pr.w, srs.beta - z);
-        return lhs == rhs;
+        add_scaled_to(cc, vk.g, cv.neg());
+        if (pr.has_random_v) add_scaled_to(cc, vk.gamma_g, pr.random_v.neg());
+        add_scaled_to(cc, pr.w, z);
+        add_scaled_to(total_c, to_affine(cc), randomizer);
+        add_scaled_to(total_w, pr.w, randomizer);
     };
     std::vector<Item> at_beta = {{comm["g_1"], in.g1_beta, true, H.n - 2},
                                  {&outer_c, outer.constant.neg(), false, 0},
                                  {comm["t"], in.t_beta, false, 0},
                                  {comm["z_b"], in.zb_beta, false, 0}};
     std::vector<Item> at_gamma = {{comm["g_2"], in.g2_gamma, true, K.n - 2}, {&inner_c, inner.constant.neg(), false, 0}};
-    return check_point(at_beta, ch.beta, proof.pc_proofs[0]) && check_point(at_gamma, ch.gamma, proof.pc_proofs[1]);
+    accumulate_point(at_beta, ch.beta, proof.pc_proofs[0], Fr::one());
+    uint64_t rw[2];
+    rng.next_u128(rw);
+    accumulate_point(at_gamma, ch.gamma, proof.pc_proofs[1], fr_from_u128(rw));
+    if (!ok) return false;
+    return pairing_product_is_one({{to_affine(total_c), vk.h}, {g1_neg(to_affine(total_w)), vk.beta_h}});
 }
 
 }  // namespace marlin

@@ -1,0 +1,255 @@
+// BLS12-377 pairing on the host, for the verifier only: what
+// MarlinKZG10::check / batch_check evaluates under Marlin::verify (reference src/marlin/mod.rs:79-86).
+// Restates the tower and group of ark-bls12-377 0.3 (fields/{fq2,fq6,fq12}.rs, curves/g2.rs):
+//   Fq2  = Fq[u]  / (u^2 + 5)
+//   Fq6  = Fq2[v] / (v^3 - u)
+//   Fq12 = Fq6[w] / (w^2 - v)
+//   G2   : y^2 = x^3 - u/5 over Fq2 (D-type sextic twist), cofactor derived in tools/gen_constants.py
+// The pairing is the ate pairing f_{x,Q}(P)^((q^12-1)/r), x = 0x8508c00000000001, computed the plain
+// way: Q is mapped to E(Fq12) through the untwisting map (x', y') -> (x' w^2, y' w^3) and the Miller
+// loop runs in affine coordinates over Fq12 with a generic final exponentiation.  That is slow
+// (tens of milliseconds) but has no curve-specific line formulas to get wrong; verification checks
+// pairing *equations*, for which any bilinear non-degenerate pairing gives the same verdict as
+// arkworks' optimised one.  Verify is milliseconds either way and stays off the GPU.
+#pragma once
+#include "curve_host.hpp"
+
+namespace swb {
+namespace marlin {
+
+inline Fq fq_small(uint32_t v) {
+    Fq r = Fq::zero();
+    Fq one = Fq::one();
+    for (int b = 31; b >= 0; b--) {
+        r = r.dbl();
+        if ((v >> b) & 1u) r = r + one;
+    }
+    return r;
+}
+
+struct Fq2 {
+    Fq c0, c1;
+    static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+    static Fq2 one() { return {Fq::one(), Fq::zero()}; }
+    bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    Fq2 operator+(const Fq2& o) const { return {c0 + o.c0, c1 + o.c1}; }
+    Fq2 operator-(const Fq2& o) const { return {c0 - o.c0, c1 - o.c1}; }
+    Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+    static Fq mul5(const Fq& a) { Fq t = a.dbl().dbl(); return t + a; }
+    Fq2 operator*(const Fq2& o) const {                     // u^2 = -5
+        Fq a = c0 * o.c0, b = c1 * o.c1;
+        return {a - mul5(b), c0 * o.c1 + c1 * o.c0};
+    }
+    Fq2 sqr() const { return (*this) * (*this); }
+    Fq2 scale(const Fq& s) const { return {c0 * s, c1 * s}; }
+    Fq norm() const { return c0.sqr() + mul5(c1.sqr()); }
+    Fq2 inverse() const {
+        Fq ni = norm().inverse();
+        return {c0 * ni, (c1 * ni).neg()};
+    }
+    Fq2 mul_by_u() const { return {mul5(c1).neg(), c0}; }   // (c0 + c1 u) u = -5 c1 + c0 u
+};
+
+struct Fq6 {
+    Fq2 c0, c1, c2;
+    static Fq6 zero() { return {Fq2::zero(), Fq2::zero(), Fq2::zero()}; }
+    static Fq6 one() { return {Fq2::one(), Fq2::zero(), Fq2::zero()}; }
+    bool is_zero() const { return c0.is_zero() && c1.is_zero() && c2.is_zero(); }
+    bool operator==(const Fq6& o) const { return c0 == o.c0 && c1 == o.c1 && c2 == o.c2; }
+    Fq6 operator+(const Fq6& o) const { return {c0 + o.c0, c1 + o.c1, c2 + o.c2}; }
+    Fq6 operator-(const Fq6& o) const { return {c0 - o.c0, c1 - o.c1, c2 - o.c2}; }
+    Fq6 neg() const { return {c0.neg(), c1.neg(), c2.neg()}; }
+    Fq6 operator*(const Fq6& o) const {                     // v^3 = u
+        Fq2 t0 = c0 * o.c0, t1 = c1 * o.c1, t2 = c2 * o.c2;
+        Fq2 r0 = t0 + (c1 * o.c2 + c2 * o.c1).mul_by_u();
+        Fq2 r1 = c0 * o.c1 + c1 * o.c0 + t2.mul_by_u();
+        Fq2 r2 = c0 * o.c2 + t1 + c2 * o.c0;
+        return {r0, r1, r2};
+    }
+    Fq6 mul_by_v() const { return {c2.mul_by_u(), c0, c1}; }
+    Fq6 inverse() const {
+        Fq2 t0 = c0.sqr() - (c1 * c2).mul_by_u();
+        Fq2 t1 = c2.sqr().mul_by_u() - c0 * c1;
+        Fq2 t2 = c1.sqr() - c0 * c2;
+        Fq2 d = c0 * t0 + (c2 * t1 + c1 * t2).mul_by_u();
+        Fq2 di = d.inverse();
+        return {t0 * di, t1 * di, t2 * di};
+    }
+};
+
+struct Fq12 {
+    Fq6 c0, c1;
+    static Fq12 one() { return {Fq6::one(), Fq6::zero()}; }
+    static Fq12 zero() { return {Fq6::zero(), Fq6::zero()}; }
+    static Fq12 from_fq(const Fq& a) { Fq12 r = zero(); r.c0.c0.c0 = a; return r; }
+    bool operator==(const Fq12& o) const { return c0 == o.c0 && c1 == o.c1; }
+    bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    Fq12 operator+(const Fq12& o) const { return {c0 + o.c0, c1 + o.c1}; }
+    Fq12 operator-(const Fq12& o) const { return {c0 - o.c0, c1 - o.c1}; }
+    Fq12 operator*(const Fq12& o) const {                   // w^2 = v
+        Fq6 a = c0 * o.c0, b = c1 * o.c1;
+        return {a + b.mul_by_v(), c0 * o.c1 + c1 * o.c0};
+    }
+    Fq12 sqr() const { return (*this) * (*this); }
+    Fq12 inverse() const {
+        Fq6 d = (c0 * c0 - (c1 * c1).mul_by_v()).inverse();
+        return {c0 * d, (c1 * d).neg()};
+    }
+    Fq12 pow_words(const uint32_t* e, int nwords) const {
+        Fq12 acc = one();
+        bool started = false;
+        for (int i = nwords * 32 - 1; i >= 0; i--) {
+            if (started) acc = acc.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1u) { acc = acc * (*this); started = true; }
+        }
+        return acc;
+    }
+};
+
+// ---- G2: affine points on the twist over Fq2 -------------------------------------------------
+struct G2Point {
+    Fq2 x, y;
+    bool infinity = true;
+    static G2Point identity() { return {Fq2::zero(), Fq2::zero(), true}; }
+    bool operator==(const G2Point& o) const {
+        if (infinity || o.infinity) return infinity == o.infinity;
+        return x == o.x && y == o.y;
+    }
+};
+inline Fq2 g2_coeff_b() { return {Fq::zero(), fq_small(5).inverse().neg()}; }      // -u/5
+inline bool g2_on_curve(const G2Point& p) { return p.infinity || p.y.sqr() == p.x.sqr() * p.x + g2_coeff_b(); }
+inline G2Point g2_neg(const G2Point& p) { return {p.x, p.y.neg(), p.infinity}; }
+inline G2Point g2_add(const G2Point& a, const G2Point& b) {
+    if (a.infinity) return b;
+    if (b.infinity) return a;
+    Fq2 lam;
+    if (a.x == b.x) {
+        if (!(a.y == b.y) || a.y.is_zero()) return G2Point::identity();
+        Fq2 xx = a.x.sqr();
+        lam = (xx + xx + xx) * (a.y + a.y).inverse();
+    } else {
+        lam = (b.y - a.y) * (b.x - a.x).inverse();
+    }
+    Fq2 x3 = lam.sqr() - a.x - b.x;
+    return {x3, lam * (a.x - x3) - a.y, false};
+}
+inline G2Point g2_mul_words(const G2Point& p, const uint32_t* k, int nwords) {
+    G2Point acc = G2Point::identity();
+    for (int i = nwords * 32 - 1; i >= 0; i--) {
+        acc = g2_add(acc, acc);
+        if ((k[i >> 5] >> (i & 31)) & 1u) acc = g2_add(acc, p);
+    }
+    return acc;
+}
+inline G2Point g2_mul_fr(const G2Point& p, const Fr& k_mont) {
+    Fr c = k_mont.to_canonical();
+    return g2_mul_words(p, c.l, 8);
+}
+// square root in Fq2 (complex method over the norm); false for non-residues.  Every candidate is
+// verified by squaring, so a returned root is always correct.
+inline bool fq2_sqrt(const Fq2& a, Fq2* out) {
+    if (a.is_zero()) { *out = a; return true; }
+    const FqSqrtCtx& sq = fq_sqrt_ctx();
+    const Fq two_inv = fq_small(2).inverse();
+    if (a.c1.is_zero()) {
+        // a in Fq: either sqrt(a) in Fq, or sqrt(-a/5) * u
+        Fq r;
+        if (sq.sqrt(a.c0, &r)) { *out = {r, Fq::zero()}; return true; }
+        if (sq.sqrt(a.c0.neg() * fq_small(5).inverse(), &r)) { *out = {Fq::zero(), r}; return out->sqr() == a; }
+        return false;
+    }
+    // a = c0 + c1 u, u^2 = -5:  x0^2 = (c0 +- alpha)/2 with alpha = sqrt(norm(a)),  x1 = c1 / (2 x0)
+    Fq alpha;
+    if (!sq.sqrt(a.norm(), &alpha)) return false;
+    for (int sign = 0; sign < 2; sign++) {
+        Fq delta = (sign ? a.c0 - alpha : a.c0 + alpha) * two_inv, x0;
+        if (!sq.sqrt(delta, &x0) || x0.is_zero()) continue;
+        Fq2 cand = {x0, a.c1 * x0.dbl().inverse()};
+        if (cand.sqr() == a) { *out = cand; return true; }
+    }
+    return false;
+}
+// lexicographic "greater" on (c1, c0) as canonical integers, the order ark-ff uses for Fp2
+inline bool fq2_gt(const Fq2& a, const Fq2& b) {
+    if (!(a.c1 == b.c1)) return fq_canonical_gt(a.c1, b.c1);
+    return fq_canonical_gt(a.c0, b.c0);
+}
+// G2Projective::rand: x <- Fq2::rand (c0 then c1), greatest <- bool, until on-curve; cofactor
+inline G2Point g2_rand(ChaChaRng& rng) {
+    static const uint32_t cof[SWB_G2_COFACTOR_WORDS] = SWB_G2_COFACTOR_INIT;
+    for (;;) {
+        Fq2 x = {rand_fq(rng), Fq::zero()};
+        x.c1 = rand_fq(rng);
+        const bool greatest = rng.next_bool();
+        Fq2 y;
+        if (!fq2_sqrt(x.sqr() * x + g2_coeff_b(), &y)) continue;
+        Fq2 negy = y.neg();
+        const bool y_lt_negy = fq2_gt(negy, y);
+        G2Point p = {x, (y_lt_negy ^ greatest) ? y : negy, false};
+        return g2_mul_words(p, cof, SWB_G2_COFACTOR_WORDS);
+    }
+}
+
+// ---- ate pairing --------------------------------------------------------------------------------
+struct E12Point {
+    Fq12 x, y;
+    bool infinity;
+};
+inline E12Point untwist(const G2Point& q) {
+    E12Point r;
+    r.infinity = q.infinity;
+    r.x = Fq12::zero();
+    r.y = Fq12::zero();
+    r.x.c0.c1 = q.x;        // x' * v   (w^2 = v)
+    r.y.c1.c1 = q.y;        // y' * v w (w^3 = v w)
+    return r;
+}
+// Miller function f_{x,Q}(P) (denominators omitted: they lie in Fq6 and die in the final exponentiation)
+inline Fq12 miller_loop(const G1Point& p, const G2Point& q) {
+    if (p.infinity || q.infinity) return Fq12::one();
+    const E12Point Q = untwist(q);
+    const Fq12 px = Fq12::from_fq(p.x), py = Fq12::from_fq(p.y);
+    Fq12 tx = Q.x, ty = Q.y;
+    Fq12 f = Fq12::one();
+    const uint64_t x = SWB_BLS_X;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    auto line_and_step = [&](const Fq12& lam, const Fq12& ax, const Fq12& ay) {
+        // line through (tx,ty) with slope lam evaluated at P, then T <- T + A
+        Fq12 l = (py - ty) - lam * (px - tx);
+        Fq12 nx = lam.sqr() - tx - ax;
+        Fq12 ny = lam * (tx - nx) - ty;
+        tx = nx;
+        ty = ny;
+        (void)ay;
+        return l;
+    };
+    for (int i = top - 1; i >= 0; i--) {
+        Fq12 xx = tx.sqr();
+        Fq12 lam = (xx + xx + xx) * (ty + ty).inverse();
+        f = f.sqr() * line_and_step(lam, tx, ty);
+        if ((x >> i) & 1) {
+            Fq12 lam2 = (Q.y - ty) * (Q.x - tx).inverse();
+            f = f * line_and_step(lam2, Q.x, Q.y);
+        }
+    }
+    return f;
+}
+// f^((q^12 - 1)/r) = (conj(f) / f)^((q^6 + 1)/r): conjugation over Fq6 is the q^6-power Frobenius
+inline Fq12 final_exponentiation(const Fq12& f) {
+    static const uint32_t e[SWB_FINAL_EXP_WORDS] = SWB_FINAL_EXP_INIT;
+    Fq12 conj = {f.c0, f.c1.neg()};
+    Fq12 g = conj * f.inverse();
+    return g.pow_words(e, SWB_FINAL_EXP_WORDS);
+}
+inline Fq12 pairing(const G1Point& p, const G2Point& q) { return final_exponentiation(miller_loop(p, q)); }
+// prod_i e(P_i, Q_i) == 1 ?
+inline bool pairing_product_is_one(const std::vector<std::pair<G1Point, G2Point>>& pairs) {
+    Fq12 f = Fq12::one();
+    for (auto& pq : pairs) f = f * miller_loop(pq.first, pq.second);
+    return final_exponentiation(f) == Fq12::one();
+}
+
+}  // namespace marlin
+}  // namespace swb

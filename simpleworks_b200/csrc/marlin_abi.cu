@@ -261,7 +261,7 @@ struct swb_rng { RngHandle h; };
 struct swb_r1cs { R1csHandle* h; };
 struct swb_srs { GpuEngine eng; SrsHandle<GpuEngine>* h; };
 struct swb_pk { PkHandle<GpuEngine>* h; };
-struct swb_vk { VkHandle<GpuEngine>* h; };
+struct swb_vk { VkHandle* h; };
 
 extern "C" {
 
@@ -347,10 +347,11 @@ int swb_marlin_prove(swb_ctx* c, const swb_pk* pk, const swb_r1cs* cs, swb_rng* 
     if (rc) return swb::set_err(c, SWB_EINTERNAL, "prove: %s", err.c_str());
     return SWB_OK;
 }
-int swb_marlin_verify(swb_ctx* c, const swb_vk* vk, const swb_fr* public_inputs, size_t n, const uint8_t* proof, size_t len, int* ok) {
+int swb_marlin_verify(swb_ctx* c, const swb_vk* vk, const swb_fr* public_inputs, size_t n, const uint8_t* proof, size_t len,
+                      swb_rng* rng, int* ok) {
     if (!vk || !ok || (!public_inputs && n) || !proof) return SWB_EARG;
     std::string err;
-    int rc = Api::verify(vk->h, (const uint64_t*)public_inputs, n, proof, len, ok, &err);
+    int rc = Api::verify(vk->h, (const uint64_t*)public_inputs, n, proof, len, rng ? &rng->h : nullptr, ok, &err);
     if (rc) return swb::set_err(c, SWB_EINTERNAL, "verify: %s", err.c_str());
     return SWB_OK;
 }

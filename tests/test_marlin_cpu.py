@@ -38,6 +38,12 @@ def test_blake2s_matches_hashlib(golden_dir):
         assert M.blake2s(data) == G.blake2s(data)
 
 
+def test_pairing_tower_and_bilinearity():
+    """BLS12-377 pairing used by verify: tower relations, G2 cofactor (derived, not transcribed),
+    e(aP, bQ) = e(P, Q)^(ab), non-degeneracy, e^r = 1, pairing-product accept and reject."""
+    assert M.lib().orc_pairing_selftest() == 0
+
+
 @pytest.fixture(scope="module")
 def toy_srs():
     rng = M.Rng()                                   # generate_rand()
