@@ -188,6 +188,15 @@ int  swb_marlin_prove(swb_ctx*, const swb_pk*, const swb_r1cs* cs_with_assignmen
 int  swb_marlin_verify(swb_ctx*, const swb_vk*, const swb_fr* public_inputs, size_t n, const uint8_t* proof, size_t len,
                        swb_rng*, int* ok);
 void swb_bytes_free(uint8_t*);
+/* serialize_verifying_key / deserialize_verifying_key (reference src/marlin/serialization.rs:19-31);
+ * NULL on malformed input.  (Proving keys hold the device-resident committer key and are not
+ * serialised.) */
+int  swb_vk_serialize(const swb_vk*, uint8_t** bytes, size_t* len);
+swb_vk* swb_vk_deserialize(const uint8_t* bytes, size_t len);
+/* R1CS interchange ("SWBR1CS1", layout in csrc/marlin/r1cs.hpp and INTEGRATION.md): constraint
+ * systems synthesised by the reference's Rust gadgets, exported from ConstraintSystemRef */
+swb_r1cs* swb_r1cs_read(const uint8_t* bytes, size_t len);
+int  swb_r1cs_write(const swb_r1cs*, uint8_t** bytes, size_t* len);
 
 #ifdef __cplusplus
 }

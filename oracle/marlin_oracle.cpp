@@ -146,6 +146,10 @@ int orc_marlin_verify(void* vk, const uint64_t* pi, size_t n, const uint8_t* pro
     return Api::verify(static_cast<VkHandle*>(vk), pi, n, proof, len, static_cast<RngHandle*>(rng), ok, &g_err);
 }
 void orc_bytes_free(uint8_t* p) { free(p); }
+void* orc_r1cs_read(const uint8_t* b, size_t n) { return r1cs_from_bytes(b, n); }
+uint8_t* orc_r1cs_write(void* h, size_t* len) { return r1cs_to_bytes(static_cast<R1csHandle*>(h), len); }
+uint8_t* orc_vk_serialize(void* vk, size_t* len) { return vk_to_bytes(static_cast<VkHandle*>(vk), len); }
+void* orc_vk_deserialize(const uint8_t* b, size_t n) { return vk_from_bytes(b, n); }
 
 /* self-test of the pairing tower used by the verifier: field inverses, tower relations, a G2 point
  * of order r from the derived cofactor, bilinearity, non-degeneracy, the product check; returns a

@@ -45,6 +45,14 @@ def lib():
         L.orc_marlin_prove.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]
         L.orc_marlin_verify.argtypes = [vp, vp, sz, ctypes.c_char_p, sz, vp, ctypes.POINTER(i32)]
         L.orc_bytes_free.argtypes = [ctypes.POINTER(ctypes.c_uint8)]
+        L.orc_r1cs_read.restype = vp
+        L.orc_r1cs_read.argtypes = [ctypes.c_char_p, sz]
+        L.orc_r1cs_write.restype = ctypes.POINTER(ctypes.c_uint8)
+        L.orc_r1cs_write.argtypes = [vp, ctypes.POINTER(sz)]
+        L.orc_vk_serialize.restype = ctypes.POINTER(ctypes.c_uint8)
+        L.orc_vk_serialize.argtypes = [vp, ctypes.POINTER(sz)]
+        L.orc_vk_deserialize.restype = vp
+        L.orc_vk_deserialize.argtypes = [ctypes.c_char_p, sz]
         _LIB = L
     return _LIB
 
@@ -90,6 +98,37 @@ class R1cs:
 
     def is_satisfied(self) -> bool:
         return bool(lib().orc_r1cs_is_satisfied(self.h))
+
+    def to_bytes(self) -> bytes:
+        n = ctypes.c_size_t()
+        p = lib().orc_r1cs_write(self.h, ctypes.byref(n))
+        out = bytes(p[:n.value])
+        lib().orc_bytes_free(p)
+        return out
+
+    @classmethod
+    def from_bytes(cls, data: bytes) -> "R1cs":
+        h = lib().orc_r1cs_read(data, len(data))
+        if not h:
+            raise MarlinError("malformed SWBR1CS1 data")
+        obj = cls.__new__(cls)
+        obj.h = ctypes.c_void_p(h)
+        return obj
+
+
+def vk_serialize(vk) -> bytes:
+    n = ctypes.c_size_t()
+    p = lib().orc_vk_serialize(vk, ctypes.byref(n))
+    out = bytes(p[:n.value])
+    lib().orc_bytes_free(p)
+    return out
+
+
+def vk_deserialize(data: bytes):
+    h = lib().orc_vk_deserialize(data, len(data))
+    if not h:
+        raise MarlinError("malformed verifying key")
+    return ctypes.c_void_p(h)
 
 
 def universal_setup(nc, nv, nnz, rng: Rng):

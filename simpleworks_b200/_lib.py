@@ -30,6 +30,7 @@ SYMBOLS = [
     "swb_r1cs_free",
     "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
     "swb_marlin_prove", "swb_marlin_verify", "swb_bytes_free",
+    "swb_vk_serialize", "swb_vk_deserialize", "swb_r1cs_read", "swb_r1cs_write",
 ]
 
 _lib = None
@@ -96,6 +97,10 @@ def load() -> ctypes.CDLL:
         "swb_marlin_prove": (i32, [vp, vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
         "swb_marlin_verify": (i32, [vp, vp, vp, sz, ctypes.c_char_p, sz, vp, ctypes.POINTER(i32)]),
         "swb_bytes_free": (None, [ctypes.POINTER(ctypes.c_uint8)]),
+        "swb_vk_serialize": (i32, [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
+        "swb_vk_deserialize": (vp, [ctypes.c_char_p, sz]),
+        "swb_r1cs_read": (vp, [ctypes.c_char_p, sz]),
+        "swb_r1cs_write": (i32, [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
         "swb_msm_set_window_bits": (i32, [vp, i32]),
         "swb_g1_sum_jacobian": (i32, [vp, vp, sz, vp]),
         "swb_fixed_base_powers": (i32, [vp, vp, vp, sz, vp]),

@@ -319,6 +319,23 @@ class ConstraintSystem:
     def is_satisfied(self) -> bool:
         return bool(self._lib.swb_r1cs_is_satisfied(self._h))
 
+    def to_bytes(self) -> bytes:
+        """SWBR1CS1 interchange bytes (layout: csrc/marlin/r1cs.hpp)"""
+        p = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        if self._lib.swb_r1cs_write(self._h, ctypes.byref(p), ctypes.byref(n)):
+            raise SwbError("r1cs_write failed")
+        out = bytes(p[:n.value])
+        self._lib.swb_bytes_free(p)
+        return out
+
+    @classmethod
+    def from_bytes(cls, data: bytes) -> "ConstraintSystem":
+        h = _lib.load().swb_r1cs_read(data, len(data))
+        if not h:
+            raise SwbError("malformed SWBR1CS1 data")
+        return cls(ctypes.c_void_p(h))
+
     def __del__(self):
         try:
             self._lib.swb_r1cs_free(self._h)
@@ -356,6 +373,20 @@ class Marlin:
         out = bytes(p[:n.value])
         self._lib.swb_bytes_free(p)
         return out
+
+    def serialize_verifying_key(self, vk) -> bytes:
+        p = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self.be._check(self._lib.swb_vk_serialize(vk, ctypes.byref(p), ctypes.byref(n)))
+        out = bytes(p[:n.value])
+        self._lib.swb_bytes_free(p)
+        return out
+
+    def deserialize_verifying_key(self, data: bytes):
+        h = self._lib.swb_vk_deserialize(data, len(data))
+        if not h:
+            raise SwbError("malformed verifying key")
+        return ctypes.c_void_p(h)
 
     def verify_proof(self, vk, public_inputs: np.ndarray, proof: bytes, rng: "Rng | None" = None) -> bool:
         """verify_proof(deserialize_proof(bytes)): pairing check on the host"""

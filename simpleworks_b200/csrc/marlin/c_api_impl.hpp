@@ -79,6 +79,29 @@ inline R1csHandle* r1cs_builtin(int kind, size_t size, uint64_t v0, uint64_t v1)
     return h;
 }
 
+inline uint8_t* bytes_out(const std::vector<uint8_t>& b, size_t* len) {
+    uint8_t* p = (uint8_t*)malloc(b.size() ? b.size() : 1);
+    memcpy(p, b.data(), b.size());
+    *len = b.size();
+    return p;
+}
+inline R1csHandle* r1cs_from_bytes(const uint8_t* p, size_t len) {
+    auto* h = new R1csHandle();
+    if (!r1cs_read(p, len, &h->cs)) { delete h; return nullptr; }
+    return h;
+}
+inline uint8_t* r1cs_to_bytes(const R1csHandle* h, size_t* len) {
+    std::vector<uint8_t> b;
+    r1cs_write(h->cs, &b);
+    return bytes_out(b, len);
+}
+inline uint8_t* vk_to_bytes(const VkHandle* vk, size_t* len) { return bytes_out(vk->vk.serialize(), len); }
+inline VkHandle* vk_from_bytes(const uint8_t* p, size_t len) {
+    auto* h = new VkHandle();
+    if (!VerifyingKey::deserialize(p, len, &h->vk)) { delete h; return nullptr; }
+    return h;
+}
+
 template <class Engine>
 struct MarlinApi {
     static int setup(Engine& eng, size_t nc, size_t nv, size_t nnz, RngHandle* rng, SrsHandle<Engine>** out, std::string* err) {

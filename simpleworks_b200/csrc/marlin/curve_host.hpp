@@ -174,25 +174,6 @@ inline G1Point g1_rand(ChaChaRng& rng) {
     }
 }
 
-// G2Projective::rand consumes the stream the same way over Fq2 = Fq[u]/(u^2 + 5), twist
-// y^2 = x^3 + (0, -1/5).  Only the consumption matters to the prover (h lives in the verifier key
-// of the pairing-based check, which this library does not implement): draw until x^3 + b' is a
-// square in Fq2, i.e. its norm is a square in Fq.
-inline void g2_rand_consume(ChaChaRng& rng) {
-    Fq five = Fq::one();
-    five = five + five + five + five + five;
-    const Fq b1 = five.inverse().neg();      // -1/5
-    for (;;) {
-        Fq x0 = rand_fq(rng), x1 = rand_fq(rng);
-        (void)rng.next_bool();
-        // x^2 = (x0^2 - 5 x1^2, 2 x0 x1);  x^3 = x^2 * x
-        Fq s0 = x0.sqr() - five * x1.sqr(), s1 = (x0 * x1).dbl();
-        Fq c0 = s0 * x0 - five * (s1 * x1), c1 = s0 * x1 + s1 * x0 + b1;
-        Fq norm = c0.sqr() + five * c1.sqr();
-        if (fq_sqrt_ctx().is_square(norm)) return;
-    }
-}
-
 // ---- bytes ------------------------------------------------------------------------------------
 inline void put_fr_canonical(std::vector<uint8_t>& out, const Fr& a) {     // 32 B LE
     Fr c = a.to_canonical();
@@ -224,6 +205,13 @@ inline void put_g1_compressed(std::vector<uint8_t>& out, const G1Point& p) {
     }
     put_fq_canonical(out, p.x);
     if (fq_canonical_gt(p.y, p.y.neg())) out[at + 47] |= 0x80;
+}
+inline bool get_u64(const uint8_t*& p, const uint8_t* end, uint64_t* v) {
+    if (end - p < 8) return false;
+    *v = 0;
+    for (int b = 0; b < 8; b++) *v |= (uint64_t)p[b] << (8 * b);
+    p += 8;
+    return true;
 }
 inline bool get_fr_canonical(const uint8_t*& p, const uint8_t* end, Fr* out) {
     if (end - p < 32) return false;

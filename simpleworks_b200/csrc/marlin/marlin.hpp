@@ -251,7 +251,71 @@ struct VerifyingKey {
             if (sp.first == bound) return &sp.second;
         return nullptr;
     }
+    // serialize_verifying_key / deserialize_verifying_key (reference src/marlin/serialization.rs:19-31):
+    // index_info (4 x u64), index_comms, then MarlinKZG10's VerifierKey -- g, gamma_g (48 B), h, beta_h
+    // (96 B), Some(degree_bounds_and_shift_powers), max_degree, supported_degree -- in ark-serialize's
+    // compressed conventions.  Layout follows SURVEY row a7; unpinned against real arkworks bytes.
+    std::vector<uint8_t> serialize() const;
+    static bool deserialize(const uint8_t* p, size_t len, VerifyingKey* out);
 };
+
+inline void put_commitment_canonical(std::vector<uint8_t>& out, const Commitment& c) {
+    put_g1_compressed(out, c.comm);
+    out.push_back(c.has_shifted ? 1 : 0);
+    if (c.has_shifted) put_g1_compressed(out, c.shifted);
+}
+inline bool get_commitment_canonical(const uint8_t*& p, const uint8_t* end, Commitment* c) {
+    if (!get_g1_compressed(p, end, &c->comm) || p >= end) return false;
+    c->has_shifted = *p++ != 0;
+    return !c->has_shifted || get_g1_compressed(p, end, &c->shifted);
+}
+inline std::vector<uint8_t> VerifyingKey::serialize() const {
+    std::vector<uint8_t> out;
+    put_u64(out, info.num_variables);
+    put_u64(out, info.num_constraints);
+    put_u64(out, info.num_non_zero);
+    put_u64(out, info.num_instance);
+    put_u64(out, index_comms.size());
+    for (auto& c : index_comms) put_commitment_canonical(out, c);
+    put_g1_compressed(out, g);
+    put_g1_compressed(out, gamma_g);
+    put_g2_compressed(out, h);
+    put_g2_compressed(out, beta_h);
+    out.push_back(1);                                   // Option::Some
+    put_u64(out, shift_powers.size());
+    for (auto& sp : shift_powers) {
+        put_u64(out, sp.first);
+        put_g1_compressed(out, sp.second);
+    }
+    put_u64(out, max_degree);
+    put_u64(out, ahp_max_degree(info.num_constraints, info.num_variables, info.num_non_zero));
+    return out;
+}
+inline bool VerifyingKey::deserialize(const uint8_t* p, size_t len, VerifyingKey* out) {
+    const uint8_t* end = p + len;
+    uint64_t v[4], n;
+    for (int i = 0; i < 4; i++)
+        if (!get_u64(p, end, &v[i])) return false;
+    out->info = IndexInfo{(size_t)v[0], (size_t)v[1], (size_t)v[2], (size_t)v[3]};
+    if (!get_u64(p, end, &n) || n > 64) return false;
+    out->index_comms.resize(n);
+    for (auto& c : out->index_comms)
+        if (!get_commitment_canonical(p, end, &c)) return false;
+    if (!get_g1_compressed(p, end, &out->g) || !get_g1_compressed(p, end, &out->gamma_g)) return false;
+    if (!get_g2_compressed(p, end, &out->h) || !get_g2_compressed(p, end, &out->beta_h)) return false;
+    if (p >= end || *p++ != 1) return false;
+    if (!get_u64(p, end, &n) || n > 64) return false;
+    out->shift_powers.resize(n);
+    for (auto& sp : out->shift_powers) {
+        uint64_t b;
+        if (!get_u64(p, end, &b) || !get_g1_compressed(p, end, &sp.second)) return false;
+        sp.first = (size_t)b;
+    }
+    uint64_t md, sd;
+    if (!get_u64(p, end, &md) || !get_u64(p, end, &sd)) return false;
+    out->max_degree = (size_t)md;
+    return p == end;
+}
 
 inline void put_commitment_bytes(std::vector<uint8_t>& out, const Commitment& c) {   // ToBytes, 195 B
     put_g1_uncompressed(out, c.comm);

@@ -191,6 +191,40 @@ inline G2Point g2_rand(ChaChaRng& rng) {
     }
 }
 
+// CanonicalSerialize for G2Affine, compressed: x = c0 (48 B) || c1 (48 B), SWFlags in the top bits of
+// the last byte (bit 7: y is the larger of {y, -y}; bit 6: infinity)
+inline void put_g2_compressed(std::vector<uint8_t>& out, const G2Point& p) {
+    const size_t at = out.size();
+    put_fq_canonical(out, p.infinity ? Fq::zero() : p.x.c0);
+    put_fq_canonical(out, p.infinity ? Fq::zero() : p.x.c1);
+    if (p.infinity) out[at + 95] |= 0x40;
+    else if (fq2_gt(p.y, p.y.neg())) out[at + 95] |= 0x80;
+}
+inline bool get_g2_compressed(const uint8_t*& p, const uint8_t* end, G2Point* out) {
+    if (end - p < 96) return false;
+    uint8_t buf[96];
+    memcpy(buf, p, 96);
+    const uint8_t flags = buf[95] & 0xC0;
+    buf[95] &= 0x3F;
+    p += 96;
+    if (flags & 0x40) { *out = G2Point::identity(); return true; }
+    Fq c[2];
+    for (int k = 0; k < 2; k++) {
+        Fq t;
+        for (int i = 0; i < 12; i++) {
+            const uint8_t* b = buf + 48 * k + 4 * i;
+            t.l[i] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+        }
+        c[k] = t.from_canonical();
+    }
+    Fq2 x = {c[0], c[1]}, y;
+    if (!fq2_sqrt(x.sqr() * x + g2_coeff_b(), &y)) return false;
+    const Fq2 negy = y.neg();
+    const bool want_larger = (flags & 0x80) != 0;
+    *out = {x, (fq2_gt(y, negy) == want_larger) ? y : negy, false};
+    return true;
+}
+
 // ---- ate pairing --------------------------------------------------------------------------------
 struct E12Point {
     Fq12 x, y;

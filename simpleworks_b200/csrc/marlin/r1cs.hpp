@@ -69,6 +69,16 @@ struct R1cs {
     }
 };
 
+// ---- interchange format -------------------------------------------------------------
+// What a Rust-side exporter writes from ConstraintSystemRef::to_matrices() + the assignments, so that
+// circuits synthesised by the reference's gadgets prove here unchanged (INTEGRATION.md has the
+// exporter).  All integers little endian:
+//   "SWBR1CS1" | u64 num_instance | u64 num_witness | u64 num_constraints
+//   for M in A, B, C: for each constraint: u64 nnz, then nnz x (Fr canonical 32 B, u64 column)
+//   u8 has_assignment | [num_instance x Fr canonical | num_witness x Fr canonical]
+inline void r1cs_write(const R1cs& cs, std::vector<uint8_t>* out);
+inline bool r1cs_read(const uint8_t* p, size_t len, R1cs* cs);
+
 // examples/manual-constraints.rs:16-31: instance [1, a], witness [b], (a - b) * 1 = 0
 inline R1cs circuit_manual_constraints(uint64_t a_val, uint64_t b_val) {
     R1cs cs;
@@ -128,6 +138,72 @@ inline R1cs circuit_mul_chain(size_t num_constraints, uint64_t seed0, uint64_t s
     cs.witness.assign(x.begin() + 1, x.end());
     cs.has_assignment = true;
     return cs;
+}
+
+}  // namespace marlin
+}  // namespace swb
+
+#include "curve_host.hpp"
+
+namespace swb {
+namespace marlin {
+
+inline void r1cs_write(const R1cs& cs, std::vector<uint8_t>* out) {
+    const char magic[8] = {'S', 'W', 'B', 'R', '1', 'C', 'S', '1'};
+    out->insert(out->end(), magic, magic + 8);
+    put_u64(*out, cs.num_instance);
+    put_u64(*out, cs.num_witness);
+    put_u64(*out, cs.num_constraints());
+    const std::vector<SparseRow>* ms[3] = {&cs.a, &cs.b, &cs.c};
+    for (int m = 0; m < 3; m++)
+        for (auto& row : *ms[m]) {
+            put_u64(*out, row.e.size());
+            for (auto& e : row.e) {
+                put_fr_canonical(*out, e.first);
+                put_u64(*out, e.second);
+            }
+        }
+    out->push_back(cs.has_assignment ? 1 : 0);
+    if (cs.has_assignment) {
+        for (auto& x : cs.instance) put_fr_canonical(*out, x);
+        for (auto& x : cs.witness) put_fr_canonical(*out, x);
+    }
+}
+inline bool r1cs_read(const uint8_t* p, size_t len, R1cs* cs) {
+    const uint8_t* end = p + len;
+    if (len < 8 || memcmp(p, "SWBR1CS1", 8) != 0) return false;
+    p += 8;
+    uint64_t ni, nw, nc;
+    if (!get_u64(p, end, &ni) || !get_u64(p, end, &nw) || !get_u64(p, end, &nc) || ni == 0) return false;
+    if (nc > ((uint64_t)1 << 32) || ni + nw > ((uint64_t)1 << 32)) return false;
+    *cs = R1cs();
+    cs->num_instance = (size_t)ni;
+    cs->num_witness = (size_t)nw;
+    std::vector<SparseRow>* ms[3] = {&cs->a, &cs->b, &cs->c};
+    for (int m = 0; m < 3; m++) {
+        ms[m]->resize((size_t)nc);
+        for (auto& row : *ms[m]) {
+            uint64_t k;
+            if (!get_u64(p, end, &k) || k > ni + nw) return false;
+            row.e.resize((size_t)k);
+            for (auto& e : row.e) {
+                uint64_t col;
+                if (!get_fr_canonical(p, end, &e.first) || !get_u64(p, end, &col) || col >= ni + nw) return false;
+                e.second = (uint32_t)col;
+            }
+        }
+    }
+    if (p >= end) return false;
+    cs->has_assignment = *p++ != 0;
+    if (cs->has_assignment) {
+        cs->instance.resize((size_t)ni);
+        cs->witness.resize((size_t)nw);
+        for (auto& x : cs->instance)
+            if (!get_fr_canonical(p, end, &x)) return false;
+        for (auto& x : cs->witness)
+            if (!get_fr_canonical(p, end, &x)) return false;
+    }
+    return p == end;
 }
 
 }  // namespace marlin

@@ -357,4 +357,23 @@ int swb_marlin_verify(swb_ctx* c, const swb_vk* vk, const swb_fr* public_inputs,
 }
 void swb_bytes_free(uint8_t* p) { free(p); }
 
+swb_r1cs* swb_r1cs_read(const uint8_t* bytes, size_t len) {
+    R1csHandle* h = bytes ? r1cs_from_bytes(bytes, len) : nullptr;
+    return h ? new swb_r1cs{h} : nullptr;
+}
+int swb_r1cs_write(const swb_r1cs* cs, uint8_t** bytes, size_t* len) {
+    if (!cs || !bytes || !len) return SWB_EARG;
+    *bytes = r1cs_to_bytes(cs->h, len);
+    return SWB_OK;
+}
+int swb_vk_serialize(const swb_vk* vk, uint8_t** bytes, size_t* len) {
+    if (!vk || !bytes || !len) return SWB_EARG;
+    *bytes = vk_to_bytes(vk->h, len);
+    return SWB_OK;
+}
+swb_vk* swb_vk_deserialize(const uint8_t* bytes, size_t len) {
+    VkHandle* h = bytes ? vk_from_bytes(bytes, len) : nullptr;
+    return h ? new swb_vk{h} : nullptr;
+}
+
 }  // extern "C"

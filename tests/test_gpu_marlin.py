@@ -83,3 +83,27 @@ def test_custom_constraint_system_through_the_abi(gpu):
     proof = gpu.generate_proof(cs, pk, rng)
     assert gpu.verify_proof(vk, O.fr_mont([35]), proof)
     assert not gpu.verify_proof(vk, O.fr_mont([36]), proof)
+
+
+def test_vk_bytes_and_r1cs_interchange(gpu):
+    """Proofs and verifying keys travel as bytes (simple_merkle_tree.rs:122-148); a constraint system
+    imported from the SWBR1CS1 interchange format yields the same proof."""
+    from simpleworks_b200.binding import ConstraintSystem, Rng
+    rng = Rng()
+    srs = gpu.generate_universal_srs(100, 25, 300, rng)
+    cs = ConstraintSystem.builtin("mul-chain", 20, 2, 9)
+    pk, vk = gpu.generate_proving_and_verifying_keys(srs, cs)
+    proof = gpu.generate_proof(cs, pk, Rng())
+    vk2 = gpu.deserialize_verifying_key(gpu.serialize_verifying_key(vk))
+    assert gpu.verify_proof(vk2, O.fr_mont([2]), proof, Rng())
+    assert not gpu.verify_proof(vk2, O.fr_mont([5]), proof)
+    cs2 = ConstraintSystem.from_bytes(cs.to_bytes())
+    pk2, _ = gpu.generate_proving_and_verifying_keys(srs, cs2)
+    assert gpu.generate_proof(cs2, pk2, Rng()) == proof
+    # the CPU arm reads the same interchange bytes and agrees byte for byte
+    crng = CPU.Rng()
+    csrs = CPU.universal_setup(100, 25, 300, crng)
+    ccs = CPU.R1cs.from_bytes(cs.to_bytes())
+    cpk, cvk = CPU.index(csrs, ccs)
+    assert CPU.prove(cpk, ccs, CPU.Rng()) == proof
+    assert CPU.vk_serialize(cvk) == gpu.serialize_verifying_key(vk)

@@ -115,3 +115,26 @@ def test_chain_circuit_medium(toy_srs):
     proof = M.prove(pk, cs, rng)
     assert M.verify(vk, O.fr_mont([7]), proof)
     assert not M.verify(vk, O.fr_mont([8]), proof)
+
+
+def test_verifying_key_and_r1cs_round_trip(toy_srs):
+    """serialize_verifying_key -> deserialize_verifying_key still verifies (the shape of
+    src/merkle_tree/simple_merkle_tree.rs:122-148, which ships proofs as bytes); the R1CS interchange
+    format reproduces the same proof."""
+    srs, _ = toy_srs
+    cs = M.R1cs("chain", size=30, v0=2, v1=9)
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, M.Rng())
+    vk2 = M.vk_deserialize(M.vk_serialize(vk))
+    assert M.vk_serialize(vk2) == M.vk_serialize(vk)
+    assert M.verify(vk2, O.fr_mont([2]), proof)
+    assert not M.verify(vk2, O.fr_mont([3]), proof)
+    with pytest.raises(M.MarlinError):
+        M.vk_deserialize(M.vk_serialize(vk)[:-3])
+    blob = cs.to_bytes()
+    cs2 = M.R1cs.from_bytes(blob)
+    assert cs2.is_satisfied() and cs2.to_bytes() == blob
+    pk2, _ = M.index(srs, cs2)
+    assert M.prove(pk2, cs2, M.Rng()) == proof
+    with pytest.raises(M.MarlinError):
+        M.R1cs.from_bytes(blob[:-1])
