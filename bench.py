@@ -106,13 +106,6 @@ def synth_scalars_host(n: int, seed: int) -> np.ndarray:
     return a
 
 
-def msm_plan(n: int) -> tuple[int, int]:
-    """mirror of pick_window() in csrc/msm.cu: window bits and number of windows"""
-    lg = max(0, (n - 1).bit_length())
-    c = min(16, max(4, lg - 6))
-    return c, (254 + c - 1) // c
-
-
 def marlin_extra(be, args) -> dict:
     """End-to-end Marlin (BASELINE configs[3]): synthetic mul-chain R1CS, setup / index / prove /
     verify through the protocol-level C ABI on this GPU; the CPU arm (same protocol source on the
@@ -235,7 +228,7 @@ def main():
     assert n_total % world == 0
     n_local = n_total // world
     lo = rank * n_local
-    c_bits, n_win = msm_plan(n_local)
+    c_bits, n_win = be.msm_plan(n_local)
 
     # ---- synthetic inputs: bases = beta^i * G (the SRS shape), this rank's index slice ---------
     # slice [lo, lo+n_local) of the powers = powers of beta applied to g' = beta^lo * G

@@ -120,6 +120,8 @@ int  swb_msm_g1_fr_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* 
 /* the same with host-resident Montgomery scalars (what a polynomial's coefficient vector is) */
 int  swb_msm_g1_fr(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scalars_host, size_t n,
                    swb_g1_jacobian* out_host);
+/* the signed-digit window width c and window count ceil(254/c) an n-point MSM will use */
+int  swb_msm_plan(swb_ctx*, size_t n, int* window_bits, int* windows);
 /* window width override for tuning/tests (0 = automatic) */
 int  swb_msm_set_window_bits(swb_ctx*, int c);
 /* sum of n Jacobian points on the host side of the ABI (combining per-GPU partial MSMs); pure

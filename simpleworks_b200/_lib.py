@@ -22,7 +22,7 @@ SYMBOLS = [
     "swb_fr_batch_inverse_dev", "swb_measure_mul_peak", "swb_measure_imad_peak",
     "swb_profile_enable", "swb_profile_last",
     "swb_bases_load", "swb_bases_load_dev", "swb_bases_from_powers", "swb_bases_export", "swb_bases_len", "swb_bases_free",
-    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_g1_fr", "swb_msm_set_window_bits", "swb_g1_sum_jacobian",
+    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_g1_fr", "swb_msm_plan", "swb_msm_set_window_bits", "swb_g1_sum_jacobian",
     "swb_fixed_base_powers",
     "swb_ntt_fr", "swb_ntt_fr_dev", "swb_ntt_fr_batch_dev",
     "swb_rng_test_rng", "swb_rng_next_u64", "swb_rng_free",
@@ -101,6 +101,7 @@ def load() -> ctypes.CDLL:
         "swb_vk_deserialize": (vp, [ctypes.c_char_p, sz]),
         "swb_r1cs_read": (vp, [ctypes.c_char_p, sz]),
         "swb_r1cs_write": (i32, [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
+        "swb_msm_plan": (i32, [vp, sz, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
         "swb_msm_set_window_bits": (i32, [vp, i32]),
         "swb_g1_sum_jacobian": (i32, [vp, vp, sz, vp]),
         "swb_fixed_base_powers": (i32, [vp, vp, vp, sz, vp]),

@@ -207,6 +207,11 @@ class Backend:
             self._check(self._lib.swb_bases_load_dev(self._h, self._dev_ptr(affine), n, ctypes.byref(h)))
         return Bases(self, h, n)
 
+    def msm_plan(self, n: int) -> tuple[int, int]:
+        c, w = ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.swb_msm_plan(self._h, n, ctypes.byref(c), ctypes.byref(w)))
+        return c.value, w.value
+
     def set_msm_window_bits(self, c: int):
         self._check(self._lib.swb_msm_set_window_bits(self._h, c))
 

@@ -52,10 +52,10 @@ static int pick_window(swb_ctx* c, size_t n) {
     if (c->msm_window_override) return c->msm_window_override;
     int lg = 0;
     while (((size_t)1 << lg) < n) lg++;
-    int cb = lg - 6;
-    if (cb < 4) cb = 4;
-    if (cb > 16) cb = 16;
-    return cb;
+    // measured on B200 (tools/msm_sweep.py, profiles/r1_msm_window_sweep.json): best signed-window width
+    // per log2(n); small sizes are launch-latency bound and flat in c
+    static const int best[27] = {4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 9, 9, 9, 9, 9, 9, 9, 10, 10, 13, 15, 16, 17, 18, 19, 19, 20};
+    return lg <= 26 ? best[lg] : 20;
 }
 
 static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery,
@@ -100,10 +100,14 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
     bf.heavy = (uint32_t*)get_scratch(c, "msm_heavy", ((size_t)pl.nb + 2) * 4);
     bf.partial = (G1Xyzz*)get_scratch(c, "msm_partial", (size_t)pl.pcap * sizeof(G1Xyzz));
     bf.buckets = (G1Xyzz*)get_scratch(c, "msm_buckets", (size_t)pl.nb * sizeof(G1Xyzz));
-    bf.seg = (G1Xyzz*)get_scratch(c, "msm_seg", (size_t)MSM_RED_THREADS * nwin * 2 * sizeof(G1Xyzz));
+    {
+        const size_t segs = (size_t)nwin * (pl.B < (uint32_t)MSM_SEG_LEN ? 1 : pl.B / MSM_SEG_LEN);
+        bf.seg = (G1Xyzz*)get_scratch(c, "msm_seg", (2 * segs + 2) * sizeof(G1Xyzz));
+        bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", (2 * (segs / MSM_SEG_LEN + nwin) + 2) * sizeof(G1Xyzz));
+    }
     bf.wins = (G1Xyzz*)get_scratch(c, "msm_wins", (size_t)MSM_MAX_WINDOWS * sizeof(G1Xyzz));
     if (!bf.keys || !bf.vals || !bf.range_cnt || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||
-        !bf.buckets || !bf.seg || !bf.wins)
+        !bf.buckets || !bf.seg || !bf.seg2 || !bf.wins)
         return SWB_ENOMEM;
     const uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;
     StageTimer tm(c, "msm");
@@ -207,9 +211,17 @@ void swb_bases_free(swb_bases* b) {
     delete b;
 }
 
+int swb_msm_plan(swb_ctx* c, size_t n, int* window_bits, int* windows) {
+    if (!c) return SWB_EARG;
+    const int cb = pick_window(c, n ? n : 1);
+    if (window_bits) *window_bits = cb;
+    if (windows) *windows = (254 + cb - 1) / cb;
+    return SWB_OK;
+}
+
 int swb_msm_set_window_bits(swb_ctx* c, int cb) {
     if (!c) return SWB_EARG;
-    SWB_REQUIRE(c, cb == 0 || (cb >= 2 && cb <= 20), "msm_set_window_bits: c must be 0 or in [2,20]");
+    SWB_REQUIRE(c, cb == 0 || (cb >= 2 && cb <= 22), "msm_set_window_bits: c must be 0 or in [2,22]");
     c->msm_window_override = cb;
     return SWB_OK;
 }

@@ -6,7 +6,8 @@
 namespace swb {
 
 constexpr int MSM_MAX_WINDOWS = 128;
-constexpr int MSM_RED_THREADS = 256;   // segments per window in the bucket reduction
+constexpr int MSM_RED_THREADS = 256;   // block size of the heavy-bucket gather
+constexpr int MSM_SEG_LEN = 32;        // segment / group length of the multi-level bucket reduction
 constexpr int MSM_GATHER_INLINE = 32;  // buckets with more partial sums than this go to the block-wide path
 
 struct MsmPlan {
@@ -31,7 +32,8 @@ struct MsmBuffers {
     uint32_t* heavy;     // [1 + nb] counter + list of buckets with many partial sums
     G1Xyzz* partial;     // [pcap]
     G1Xyzz* buckets;     // [nb]
-    G1Xyzz* seg;         // [2][MSM_RED_THREADS * nwin]
+    G1Xyzz* seg;         // [2][nwin * B / MSM_SEG_LEN]  level-0 (C, S) of the bucket reduction
+    G1Xyzz* seg2;        // ping-pong partner for the upper levels
     G1Xyzz* wins;        // [MSM_MAX_WINDOWS]
 };
 

@@ -65,65 +65,47 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_gather_heavy(G1Xyzz* __
     }
 }
 
-// ---- 5a. per-segment running sums: S = sum B_j, Wt = sum (j_local+1) B_j -------------------------
-__global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_s, G1Xyzz* __restrict__ seg_w,
-                                                       const G1Xyzz* __restrict__ buckets, uint32_t B, uint32_t L,
-                                                       uint32_t nseg_total) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // global segment id (window-major)
+// ---- 5. window sums: R_w = sum_{k=1..B} k * B_k, as a multi-level segmented reduction -------------
+// Level 0 cuts the B buckets of a window into segments of L: S_s = sum B, C_s = sum (j_local+1) B.
+// Then R = sum_s C_s + L * sum_s s * S_s, which has the same shape one level up: grouping G
+// consecutive segments, S'_g = sum_j S_{gG+j},  C'_g = sum_j C_{gG+j} + M * sum_j j * S_{gG+j}  with
+// M the product of the segment lengths below (a power of two: M * x is log2(M) doublings), and
+// R = sum_g C'_g + (M G) * sum_g g * S'_g.  Every level is one thread per group; the last level
+// leaves R in C_0.  Bucket counts up to 2^22 per window stay parallel this way.
+__global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_c, G1Xyzz* __restrict__ seg_s,
+                                                       const G1Xyzz* __restrict__ buckets, uint32_t L, uint32_t nseg_total) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // global segment id (window-major); B is a multiple of L
     if (g >= nseg_total) return;
-    const G1Xyzz* base = buckets + (size_t)g * L;          // B is a multiple of L
-    (void)B;
+    const G1Xyzz* base = buckets + (size_t)g * L;
     G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
     for (uint32_t j = L; j-- > 0;) {
         running.add(base[j]);
         acc.add(running);
     }
     seg_s[g] = running;
-    seg_w[g] = acc;
+    seg_c[g] = acc;
 }
 
-// ---- 5b. one block per window: total = sum_s Wt_s + L * sum_{j>=1} suffix_j(S) --------------
-__global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_window_reduce(G1Xyzz* __restrict__ win_sums,
-                                                                        const G1Xyzz* __restrict__ seg_s,
-                                                                        const G1Xyzz* __restrict__ seg_w, uint32_t nseg,
-                                                                        uint32_t log_L) {
-    extern __shared__ unsigned char smem_raw[];
-    G1Xyzz* bufA = reinterpret_cast<G1Xyzz*>(smem_raw);
-    G1Xyzz* bufB = bufA + MSM_RED_THREADS;
-    const uint32_t t = threadIdx.x, w = blockIdx.x;
-    G1Xyzz mine = t < nseg ? seg_s[(size_t)w * nseg + t] : G1Xyzz::identity();
-    // inclusive suffix scan (Hillis-Steele): suffix_t = sum_{s >= t} S_s
-    bufA[t] = mine;
-    __syncthreads();
-    G1Xyzz* src = bufA;
-    G1Xyzz* dst = bufB;
-    for (uint32_t d = 1; d < MSM_RED_THREADS; d <<= 1) {
-        G1Xyzz v = src[t];
-        if (t + d < MSM_RED_THREADS) v.add(src[t + d]);
-        dst[t] = v;
-        __syncthreads();
-        G1Xyzz* tmp = src; src = dst; dst = tmp;
+__global__ void __launch_bounds__(128) k_msm_reduce_level(G1Xyzz* __restrict__ out_c, G1Xyzz* __restrict__ out_s,
+                                                           const G1Xyzz* __restrict__ in_c, const G1Xyzz* __restrict__ in_s,
+                                                           uint32_t m, uint32_t m_out, uint32_t G, uint32_t log_M, uint32_t nwin) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m_out * nwin) return;
+    const uint32_t w = t / m_out, g = t % m_out;
+    const size_t base = (size_t)w * m + (size_t)g * G;
+    const uint32_t cnt = (g + 1) * G <= m ? G : m - g * G;
+    G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity(), csum = G1Xyzz::identity();
+    for (uint32_t j = cnt; j-- > 1;) {                     // sum_j j * S_j as a running sum
+        running.add(in_s[base + j]);
+        acc.add(running);
     }
-    G1Xyzz v = src[t];
-    __syncthreads();
-    if (t == 0) v = G1Xyzz::identity();                     // j >= 1 only
-    for (uint32_t i = 0; i < log_L; i++) v = v.dbl();        // times L
-    if (t < nseg) v.add(seg_w[(size_t)w * nseg + t]);
-    // tree reduction
-    src[t] = v;
-    __syncthreads();
-    for (uint32_t d = MSM_RED_THREADS >> 1; d > 0; d >>= 1) {
-        if (t < d) {
-            G1Xyzz a = src[t];
-            a.add(src[t + d]);
-            src[t] = a;
-        }
-        __syncthreads();
-    }
-    if (t == 0) win_sums[w] = src[0];
+    running.add(in_s[base]);
+    for (uint32_t j = 0; j < cnt; j++) csum.add(in_c[base + j]);
+    for (uint32_t i = 0; i < log_M; i++) acc = acc.dbl();
+    csum.add(acc);
+    out_s[(size_t)w * m_out + g] = running;
+    out_c[(size_t)w * m_out + g] = csum;
 }
-
-
 
 int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     k_msm_partial_bounds<<<(pl.nb + 1 + 255) / 256, 256, 0, c->stream>>>(bf.pstart, bf.pkey, bf.range_off + pl.nranges, pl.nb, bf.heavy);
@@ -138,18 +120,32 @@ int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
 }
 
 int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
-    const uint32_t B = pl.B;
-    uint32_t nseg = B < (uint32_t)MSM_RED_THREADS ? B : (uint32_t)MSM_RED_THREADS;
-    uint32_t L = B / nseg, log_L = 0;
-    while ((1u << log_L) < L) log_L++;
-    const uint32_t nseg_total = nseg * (uint32_t)pl.nwin;
-    G1Xyzz* seg = bf.seg;
-    k_msm_segments<<<(nseg_total + 127) / 128, 128, 0, c->stream>>>(seg, seg + nseg_total, bf.buckets, B, L, nseg_total);
+    const uint32_t B = pl.B, nwin = (uint32_t)pl.nwin;
+    const uint32_t L = B < MSM_SEG_LEN ? B : (uint32_t)MSM_SEG_LEN;
+    uint32_t log_M = 0;
+    while ((1u << log_M) < L) log_M++;
+    uint32_t m = B / L;                                   // segments per window
+    G1Xyzz *cur_c = bf.seg, *cur_s = bf.seg + (size_t)nwin * m;
+    G1Xyzz *alt_c = bf.seg2, *alt_s = nullptr;
+    k_msm_segments<<<(nwin * m + 127) / 128, 128, 0, c->stream>>>(cur_c, cur_s, bf.buckets, L, nwin * m);
     SWB_LAUNCH_CHECK(c, "k_msm_segments");
-    const size_t red_smem = 2 * MSM_RED_THREADS * sizeof(G1Xyzz);
-    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_window_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-    k_msm_window_reduce<<<pl.nwin, MSM_RED_THREADS, red_smem, c->stream>>>(bf.wins, seg, seg + nseg_total, nseg, log_L);
-    SWB_LAUNCH_CHECK(c, "k_msm_window_reduce");
+    const uint32_t G = MSM_SEG_LEN;
+    uint32_t log_G = 0;
+    while ((1u << log_G) < G) log_G++;
+    while (m > 1) {
+        const uint32_t m_out = (m + G - 1) / G;
+        alt_s = alt_c + (size_t)nwin * m_out;
+        k_msm_reduce_level<<<(nwin * m_out + 127) / 128, 128, 0, c->stream>>>(alt_c, alt_s, cur_c, cur_s, m, m_out, G, log_M, nwin);
+        SWB_LAUNCH_CHECK(c, "k_msm_reduce_level");
+        G1Xyzz* old = cur_c;                              // ping-pong: the old input region is free again
+        cur_c = alt_c;
+        cur_s = alt_s;
+        alt_c = old;
+        m = m_out;
+        log_M += log_G;
+    }
+    // m == 1: window w's result is cur_c[w]
+    SWB_CUDA(c, cudaMemcpyAsync(bf.wins, cur_c, sizeof(G1Xyzz) * nwin, cudaMemcpyDeviceToDevice, c->stream));
     return SWB_OK;
 }
 
