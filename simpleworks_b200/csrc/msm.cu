@@ -5,15 +5,19 @@
 // src/marlin/mod.rs:75,92; src/merkle_tree/simple_merkle_tree.rs:83,119).  arkworks uses unsigned
 // c-bit windows with 2^c - 1 Jacobian buckets per window and one rayon task per window; here:
 //
-//   1. k_msm_digits     scalars -> signed c-bit digits (halves the bucket count); one
-//                        (bucket id, point index | sign) pair per scalar and window
-//   2. radix sort        pairs grouped by bucket id over all windows at once
-//   3. k_msm_bounds     bucket boundaries by binary search in the sorted keys
-//   4. k_msm_accumulate one thread per bucket: XYZZ += +-base (8M + 2S mixed additions)
-//   5. k_msm_segments / k_msm_window_reduce
-//                        sum_k k * B_k per window: per-segment running sums, then a
-//                        block-cooperative suffix scan + tree reduction in shared memory
-//   6. host              Horner over the W window sums (c doublings each) and normalisation
+//   1. k_msm_digits        scalars -> signed c-bit digits (halves the bucket count); one
+//                           (bucket, point index | sign) pair per scalar and window, window-major
+//   2. radix_sort_segmented pairs grouped by bucket inside each window (radix_sort.cu)
+//   3. k_msm_range_count    the sorted positions are cut into fixed-length ranges; runs per range,
+//                           exclusive scan = where each range writes its partial sums
+//   4. k_msm_accumulate     one thread per range: XYZZ += +-base (mixed additions), one partial
+//                           sum per run of equal bucket ids -- work per thread is bounded whatever
+//                           the scalar distribution
+//   5. k_msm_gather(_heavy) partial sums of one bucket -> the bucket
+//   6. k_msm_segments / k_msm_reduce_level
+//                           sum_k k * B_k per window: per-segment (count, weighted) pairs,
+//                           combined level by level
+//   7. host                 Horner over the W window sums (c doublings each) and normalisation
 //
 // The result is the affine value (as a Z = 1 Jacobian), which is unique, hence bit-identical to
 // what arkworks' callers see after into_affine().
@@ -93,7 +97,6 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
     MsmBuffers bf{};
     bf.keys = (uint32_t*)get_scratch(c, "msm_keys", pl.total * 4 * 2);
     bf.vals = (uint32_t*)get_scratch(c, "msm_vals", pl.total * 4 * 2);
-    bf.range_cnt = (uint32_t*)get_scratch(c, "msm_rcnt", ((size_t)pl.nranges + 2) * 4);
     bf.range_off = (uint32_t*)get_scratch(c, "msm_roff", ((size_t)pl.nranges + 2) * 4);
     bf.pkey = (uint32_t*)get_scratch(c, "msm_pkey", (size_t)pl.pcap * 4);
     bf.pstart = (uint32_t*)get_scratch(c, "msm_pstart", ((size_t)pl.nb + 2) * 4);
@@ -106,7 +109,7 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
         bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", (2 * (segs / MSM_SEG_LEN + nwin) + 2) * sizeof(G1Xyzz));
     }
     bf.wins = (G1Xyzz*)get_scratch(c, "msm_wins", (size_t)MSM_MAX_WINDOWS * sizeof(G1Xyzz));
-    if (!bf.keys || !bf.vals || !bf.range_cnt || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||
+    if (!bf.keys || !bf.vals || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||
         !bf.buckets || !bf.seg || !bf.seg2 || !bf.wins)
         return SWB_ENOMEM;
     const uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;

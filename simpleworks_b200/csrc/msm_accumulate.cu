@@ -30,8 +30,8 @@ __device__ __forceinline__ G1Aff ld_aff(const Fq* __restrict__ xy, size_t i) {
 __global__ void __launch_bounds__(128) k_msm_accumulate(G1Xyzz* __restrict__ partial, uint32_t* __restrict__ pkey,
                                                          const uint32_t* __restrict__ range_off,
                                                          const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                         const Fq* __restrict__ bases, size_t total, uint32_t nb, uint32_t len,
-                                                         uint32_t nranges) {
+                                                         const Fq* __restrict__ bases, size_t total, size_t n, uint32_t B,
+                                                         uint32_t len, uint32_t nranges) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nranges) return;
     const size_t p0 = (size_t)r * len;
@@ -41,16 +41,18 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(G1Xyzz* __restrict__ par
     G1Xyzz acc = G1Xyzz::identity();
     // software pipeline: the next point is in flight while the current one is added
     uint32_t k_next = keys[p0], v_next = vals[p0];
-    G1Aff pt_next = ld_aff(bases, v_next & 0x7fffffffu);
+    G1Aff pt_next;
+    if (k_next < B) pt_next = ld_aff(bases, v_next & 0x7fffffffu);
     for (size_t p = p0; p < p1; p++) {
-        const uint32_t k = k_next, v = v_next;
+        const uint32_t kl = k_next, v = v_next;
         G1Aff pt = pt_next;
-        if (k >= nb) break;
         if (p + 1 < p1) {
             k_next = keys[p + 1];
             v_next = vals[p + 1];
-            pt_next = ld_aff(bases, v_next & 0x7fffffffu);
+            if (k_next < B) pt_next = ld_aff(bases, v_next & 0x7fffffffu);
         }
+        if (kl >= B) continue;                              // zero digit (tail of a window's segment)
+        const uint32_t k = (uint32_t)(p / n) * B + kl;      // global bucket id
         if (k != cur) {
             if (cur != 0xffffffffu) {
                 partial[out] = acc;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(G1Xyzz* __restrict__ par
 int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,
                           const uint32_t* sorted_vals, const Fq* bases) {
     k_msm_accumulate<<<(pl.nranges + 127) / 128, 128, 0, c->stream>>>(bf.partial, bf.pkey, bf.range_off, sorted_keys, sorted_vals,
-                                                                     bases, pl.total, pl.nb, pl.range_len, pl.nranges);
+                                                                     bases, pl.total, pl.n, pl.B, pl.range_len, pl.nranges);
     SWB_LAUNCH_CHECK(c, "k_msm_accumulate");
     return SWB_OK;
 }

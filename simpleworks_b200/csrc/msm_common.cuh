@@ -25,8 +25,7 @@ struct MsmPlan {
 struct MsmBuffers {
     uint32_t* keys;      // [2][total]
     uint32_t* vals;      // [2][total]
-    uint32_t* range_cnt; // [nranges + 1] runs per range, then its exclusive scan
-    uint32_t* range_off; // [nranges + 1]
+    uint32_t* range_off; // [nranges + 1] runs per range, scanned in place: where each range writes
     uint32_t* pkey;      // [pcap] bucket id of each partial sum
     uint32_t* pstart;    // [nb + 1] first partial of each bucket
     uint32_t* heavy;     // [1 + nb] counter + list of buckets with many partial sums

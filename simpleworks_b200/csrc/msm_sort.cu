@@ -1,16 +1,16 @@
-// MSM stages 1-3: signed-digit decomposition, radix sort of (bucket, point) pairs, and the
-// per-range run counts that tell the accumulation kernel where to write.
-#include <cub/cub.cuh>
-
+// MSM stages 1-3: signed-digit decomposition, radix sort of (bucket, point) pairs (radix_sort.cu),
+// and the per-range run counts that tell the accumulation kernel where to write.
 #include "msm_common.cuh"
+#include "radix_sort.hpp"
 
 namespace swb {
 
 // ---- 1. signed-digit decomposition --------------------------------------------------------
-// keys[w*n + i] = w*B + |d| - 1  (or `invalid` when d == 0), vals = i | sign << 31
+// keys[w*n + i] = |d| - 1 within window w (or B when d == 0: sorts to the end of the window's segment),
+// vals = i | sign << 31
 __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                      const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
-                                                     int montgomery, uint32_t invalid) {
+                                                     int montgomery) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t B = 1u << (c - 1);
@@ -32,68 +32,59 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
             v = (v & ((1u << c) - 1u)) + carry;
             uint32_t neg = 0;
             if (v > B) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
-            keys[(size_t)w * n + i] = v ? (uint32_t)w * B + v - 1 : invalid;
+            keys[(size_t)w * n + i] = v ? v - 1 : B;
             vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
         }
     }
 }
 
 // ---- 3. number of runs of equal (valid) keys inside each range of `len` sorted positions -----
-// Thread r owns sorted positions [r*len, (r+1)*len).  A run is a maximal stretch of one bucket id
-// inside the range; k_msm_accumulate emits exactly one partial sum per run, so the exclusive scan
-// of these counts is where each range writes.
+// Range r owns sorted positions [r*len, (r+1)*len), len a power of two >= 16.  Position p belongs
+// to window p / n; its global bucket id is (p / n) * B + key, and key == B marks a zero digit (the
+// tail of every window's segment).  A run is a maximal stretch of one global bucket id inside the
+// range; k_msm_accumulate emits exactly one partial sum per run, so the exclusive scan of these
+// counts is where each range writes.  One thread per position (coalesced), one atomic per half warp.
 __global__ void __launch_bounds__(256) k_msm_range_count(uint32_t* __restrict__ cnt, const uint32_t* __restrict__ keys,
-                                                          size_t total, uint32_t nb, uint32_t len, uint32_t nranges) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > nranges) return;
-    if (r == nranges) { cnt[r] = 0; return; }
-    const size_t p0 = (size_t)r * len;
-    const size_t p1 = p0 + len < total ? p0 + len : total;
-    uint32_t runs = 0, prev = 0xffffffffu;
-    for (size_t p = p0; p < p1; p++) {
+                                                          size_t total, size_t n, uint32_t B, uint32_t len) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool starts = false;
+    if (p < total) {
         const uint32_t k = keys[p];
-        if (k >= nb) break;                 // digit-0 entries are sorted to the end
-        runs += (k != prev);
-        prev = k;
+        if (k < B) {
+            starts = true;                                     // first position of a range or window, or after a zero digit
+            if (p % len != 0 && p % n != 0) starts = keys[p - 1] != k;
+        }
     }
-    cnt[r] = runs;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, starts);
+    const uint32_t lane = threadIdx.x & 31;
+    if ((lane & 15) == 0 && p < total) {
+        const uint32_t c = __popc(ballot & (lane ? 0xffff0000u : 0x0000ffffu));
+        if (c) atomicAdd(&cnt[p / len], c);
+    }
 }
 
 int msm_launch_digits_sort(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
                            const uint32_t** sorted_keys, const uint32_t** sorted_vals) {
     const size_t total = pl.total;
-    uint32_t* keys2 = bf.keys + total;
-    uint32_t* vals2 = bf.vals + total;
     {
         size_t blocks = (pl.n + 255) / 256;
         size_t cap = (size_t)c->sm_count * 8;
         if (blocks > cap) blocks = cap;
         k_msm_digits<<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb, pl.nwin,
-                                                              montgomery, pl.nb);
+                                                              montgomery);
         SWB_LAUNCH_CHECK(c, "k_msm_digits");
     }
-    {
-        int end_bit = 1;
-        while ((1ull << end_bit) <= pl.nb) end_bit++;
-        size_t tmp_bytes = 0;
-        SWB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, bf.keys, keys2, bf.vals, vals2, total, 0, end_bit, c->stream));
-        void* tmp = get_scratch(c, "msm_sort_tmp", tmp_bytes);
-        if (!tmp) return SWB_ENOMEM;
-        SWB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, bf.keys, keys2, bf.vals, vals2, total, 0, end_bit, c->stream));
-        c->launches += 4;
-    }
-    k_msm_range_count<<<(pl.nranges + 1 + 255) / 256, 256, 0, c->stream>>>(bf.range_cnt, keys2, total, pl.nb, pl.range_len, pl.nranges);
+    uint32_t *sk = nullptr, *sv = nullptr;
+    // keys are 0 .. B (B = 2^(cb-1) marks a zero digit): cb bits, sorted inside each window's segment
+    int rc = radix_sort_segmented(c, bf.keys, bf.keys + total, bf.vals, bf.vals + total, pl.n, (uint32_t)pl.nwin, pl.cb, &sk, &sv);
+    if (rc != SWB_OK) return rc;
+    SWB_CUDA(c, cudaMemsetAsync(bf.range_off, 0, ((size_t)pl.nranges + 1) * sizeof(uint32_t), c->stream));
+    k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.n, pl.B, pl.range_len);
     SWB_LAUNCH_CHECK(c, "k_msm_range_count");
-    {
-        size_t tmp_bytes = 0;
-        SWB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, bf.range_cnt, bf.range_off, pl.nranges + 1, c->stream));
-        void* tmp = get_scratch(c, "msm_scan_tmp", tmp_bytes);
-        if (!tmp) return SWB_ENOMEM;
-        SWB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, bf.range_cnt, bf.range_off, pl.nranges + 1, c->stream));
-        c->launches += 2;
-    }
-    *sorted_keys = keys2;
-    *sorted_vals = vals2;
+    rc = exclusive_scan_u32(c, bf.range_off, (size_t)pl.nranges + 1);
+    if (rc != SWB_OK) return rc;
+    *sorted_keys = sk;
+    *sorted_vals = sv;
     return SWB_OK;
 }
 

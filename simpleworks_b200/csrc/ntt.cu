@@ -81,7 +81,11 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
                                                            const Fr* __restrict__ tw_coset) {
     extern __shared__ uint4 smem[];
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t, tile = R * T;
-    Tile tl{smem, smem + tile};
+    // final mode keeps the tile row-major [t][j] with rows padded by one element: the transposing
+    // store walks t fastest, and a stride of (R+1) 16-byte words spreads it over the banks
+    const uint32_t row = p.mode == 0 ? 0u : R + 1u;
+    const uint32_t planes = p.mode == 0 ? tile : row * T;
+    Tile tl{smem, smem + planes};
     const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
     Fr* out = p.out + (size_t)blockIdx.y * p.batch_stride;
     const uint32_t tid = threadIdx.x;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
     for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
         uint32_t j, t, e;
         if (p.mode == 0) { t = idx & (T - 1); j = idx >> p.log_t; e = idx; }
-        else { j = idx & (R - 1); t = idx >> p.log_r; e = idx; }        // final mode tile is [t][j]
+        else { j = idx & (R - 1); t = idx >> p.log_r; e = t * row + j; }  // final mode tile is [t][j], padded rows
         const size_t gi = in_base + (size_t)j * in_j_stride + (size_t)t * in_t_stride;
         Fr v = ld_fr(in + gi);
         if (p.pre_coset) v = v * tw_lookup(tw_coset, (uint32_t)gi);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
 
     // ---- R-point DIF network along j ----------------------------------------------------------
     // element (j,t) sits at j*T+t (column mode) or t*R+j (final mode)
-    const uint32_t js = p.mode == 0 ? T : 1u, ts = p.mode == 0 ? 1u : R;
+    const uint32_t js = p.mode == 0 ? T : 1u, ts = p.mode == 0 ? 1u : row;
     const uint32_t nbf = tile >> 1;
     for (uint32_t s = 0; s < p.log_r; s++) {
         const uint32_t log_half = p.log_r - 1 - s, half = 1u << log_half;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
     } else {
         for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
             const uint32_t t = idx & (T - 1), k = idx >> p.log_t;
-            Fr v = tl.get(t * R + bitrev(k, p.log_r));
+            Fr v = tl.get(t * row + bitrev(k, p.log_r));
             const size_t go = out_base + (size_t)k * out_k_stride + (size_t)t * out_t_stride;
             if (p.post_coset) v = v * tw_lookup(tw_coset, (uint32_t)go);
             if (p.post_scale) v = v * p.scale;
@@ -221,7 +225,7 @@ int ntt_build_tables(swb_ctx* c) {
         k_build_pow_table<<<12, 256, 0, c->stream>>>(tabs[k], bases[k][0], bases[k][1], bases[k][2]);
         SWB_LAUNCH_CHECK(c, "k_build_pow_table");
     }
-    SWB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_TILE_LOG) * 32));
+    SWB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_TILE_LOG) * 32 + 32 * 256));
     SWB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SWB_OK;
 }
@@ -292,7 +296,7 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
             blocks = n >> (dig[s] + log_t);
         }
         p.log_t = log_t;
-        const size_t smem = ((size_t)32) << (dig[s] + log_t);
+        const size_t smem = (((size_t)32) << (dig[s] + log_t)) + (last ? ((size_t)32 << log_t) : 0);   // + padded rows
         const Fr* coset_tab = inverse ? c->tw_geninv : c->tw_gen;
         dim3 grid((unsigned)blocks, (unsigned)batch);
         k_ntt_pass<<<grid, NTT_THREADS, smem, c->stream>>>(p, c->tw_root, coset_tab);
