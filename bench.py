@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_CPU_LOG_N", "20")))
     ap.add_argument("--marlin-log-n", type=int, default=int(os.environ.get("SWB_BENCH_MARLIN_LOG_N", "20")))
     ap.add_argument("--marlin-cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_MARLIN_CPU_LOG_N", "16")))
+    ap.add_argument("--no-tables", action="store_true",
+                    help="plain MSM path: no window tables (swb_bases_precompute) over the resident bases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -243,6 +245,14 @@ def main():
     t0 = time.perf_counter()
     bases = be.bases_from_powers(g, beta, n_local)
     t_bases = time.perf_counter() - t0
+    n_sets, t_tables = n_win, 0.0
+    if not args.no_tables:
+        # the SRS is fixed, so its window tables are built once at load time, like the bases themselves
+        t0 = time.perf_counter()
+        bases.precompute(0)
+        t_tables = time.perf_counter() - t0
+        c_bits, n_win = bases.table_info()
+        n_sets = 1
     scalars_host = synth_scalars_host(n_local, 1234 + rank)
     pinned = torch.from_numpy(scalars_host.view(np.int64)).pin_memory()
     scalars_dev = pinned.to(dev)
@@ -394,6 +404,7 @@ def main():
             "limb_products_per_s": (nn / 2) * log_ntt * 128 / ms * 1e3,
             "int_frac": (nn / 2) * log_ntt * 128 / ms * 1e3 / imad_wide, "passes": be.last_stages()}
         extra["setup_bases_s"] = t_bases
+        extra["setup_tables_s"] = t_tables
         extra["stages_ms_avg"] = {k: v / args.steps for k, v in stage_sum.items()}
         if world == 1:
             try:
@@ -407,11 +418,14 @@ def main():
         "vs_baseline": None, "dtype": "u32-limbs(Fq 377-bit, Fr 253-bit)", "data": "synthetic",
         "config": {"workload": f"bls12-377 G1 variable-base MSM 2^{args.log_n}", "points_per_gpu": n_local,
                    "window_bits": c_bits, "windows": n_win, "scalars": "uniform < 2^252",
-                   "bases": "SRS powers beta^i*G generated on device", "parallelism": f"index-sharded x{world}",
+                   "bases": "SRS powers beta^i*G generated on device and kept resident" +
+                            ("" if args.no_tables else f", with their {n_win}-level window tables 2^({c_bits}j)*P built once at load "
+                             f"({n_win * n_local * 96 / 2**30:.1f} GiB per GPU; --no-tables = plain path)"),
+                   "bucket_sets": n_sets, "parallelism": f"index-sharded x{world}",
                    "l2": "256 MiB buffer rewritten between steps; inputs (>= 2 GiB) exceed L2"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_local) * 32 * world,
-                "d2h_bytes_per_step": (144 + n_win * 192) * world, "ms_per_step": sum(e2e_ms) / len(e2e_ms)},
+                "d2h_bytes_per_step": (144 + n_sets * 192) * world, "ms_per_step": sum(e2e_ms) / len(e2e_ms)},
         "gpu_launches": int(launches), "extra": extra,
     }
     print(json.dumps(line), flush=True)

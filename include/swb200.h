@@ -103,6 +103,17 @@ int  swb_bases_load_dev(swb_ctx*, const swb_g1_affine* dev, size_t n, swb_bases*
 int  swb_bases_from_powers(swb_ctx*, const swb_g1_jacobian* g_host, const swb_fr* beta_host, size_t n, swb_bases** out);
 /* copy n bases starting at offset back to the host as 104-byte GroupAffine records */
 int  swb_bases_export(swb_ctx*, const swb_bases*, size_t offset, size_t n, swb_g1_affine* out_host);
+/* Window tables: besides each base P_i keep 2^(c*j) * P_i for j < ceil(253 / c), so that MSMs over
+ * these bases accumulate all windows into ONE set of 2^(c-1) buckets (one bucket reduction, no
+ * doublings) and scalars above r/2 are replaced by r - s on the negated point, which saves the carry
+ * window.  window_bits = 0 picks c from the number of bases.  Memory grows ceil(253/c)-fold.
+ * Calling this asserts that every base lies in the prime-order subgroup (true for the KZG powers
+ * beta^i * G that ark-poly-commit's kzg10::commit passes to VariableBaseMSM); results are then
+ * identical to the plain path.  MSMs much smaller than the table (n * levels < 8 * 2^(c-1)) keep
+ * using the plain path on level 0. */
+int  swb_bases_precompute(swb_ctx*, swb_bases*, int window_bits);
+/* window_bits / levels of the tables, both 0 when none were built */
+int  swb_bases_table_info(const swb_bases*, int* window_bits, int* levels);
 size_t swb_bases_len(const swb_bases*);
 void swb_bases_free(swb_bases*);
 

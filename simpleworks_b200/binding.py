@@ -71,6 +71,17 @@ class Bases:
         self._h = handle
         self.n = n
 
+    def precompute(self, window_bits: int = 0) -> "Bases":
+        """Build the window tables 2^(c*j) * P_i (swb_bases_precompute): later MSMs over these bases use
+        one shared set of buckets.  Only for bases in the prime-order subgroup (KZG powers)."""
+        self._b._check(self._b._lib.swb_bases_precompute(self._b._h, self._h, window_bits))
+        return self
+
+    def table_info(self):
+        c, w = ctypes.c_int(0), ctypes.c_int(0)
+        self._b._lib.swb_bases_table_info(self._h, ctypes.byref(c), ctypes.byref(w))
+        return c.value, w.value
+
     def free(self):
         if self._h:
             self._b._lib.swb_bases_free(self._h)

@@ -42,6 +42,9 @@ struct swb_bases {
     swb_ctx* ctx = nullptr;
     swb::Fq* xy = nullptr;   // n records of 96 bytes: x | y ; identity = (0,0)
     size_t n = 0;
+    // window tables (swb_bases_precompute): xy then holds tab_w levels of n records,
+    // level j = 2^(tab_c * j) * base
+    int tab_c = 0, tab_w = 0;
 };
 
 namespace swb {

@@ -85,6 +85,46 @@ __global__ void k_bases_export(uint8_t* __restrict__ out, const Fq* __restrict__
     dst[25] = 0u;
 }
 
+// ---- window tables for the MSM -------------------------------------------------------------------
+// tab[j*N + i] = 2^(c*j) * base_i for j < W (level 0 = the bases themselves), all affine.  With them
+// every c-bit digit of a scalar selects its own precomputed point and all W windows share ONE set of
+// buckets, so the MSM needs a single bucket reduction and no Horner doublings (msm.cu).  One thread
+// per base: c doublings per level in XYZZ, then one inversion for the base's W - 1 new points
+// (Montgomery's trick over zz*zzz).
+constexpr int TAB_MAX_LEVELS = 32;
+__global__ void __launch_bounds__(128) k_bases_tables(Fq* __restrict__ tab, size_t N, int c, int W) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    G1Xyzz q = G1Xyzz::identity();
+    {
+        const Fq x = tab[2 * i], y = tab[2 * i + 1];
+        if (!(x.is_zero() && y.is_zero())) {
+            q.x = x; q.y = y;
+            q.zz = Fq::one(); q.zzz = Fq::one();
+        }
+    }
+    Fq pref[TAB_MAX_LEVELS], zz[TAB_MAX_LEVELS], zzz[TAB_MAX_LEVELS];
+    Fq run = Fq::one();
+    for (int j = 1; j < W; j++) {
+        for (int k = 0; k < c; k++) q = q.dbl();
+        const bool inf = q.is_identity();       // only for bases outside the odd-order subgroup
+        tab[2 * (j * N + i)] = inf ? Fq::zero() : q.x;
+        tab[2 * (j * N + i) + 1] = inf ? Fq::zero() : q.y;
+        zz[j] = inf ? Fq::one() : q.zz;
+        zzz[j] = inf ? Fq::one() : q.zzz;
+        pref[j] = run;
+        run = run * (zz[j] * zzz[j]);
+    }
+    Fq inv = run.inverse();
+    for (int j = W - 1; j >= 1; j--) {
+        const Fq tinv = inv * pref[j];          // (zz_j * zzz_j)^-1
+        inv = inv * (zz[j] * zzz[j]);
+        Fq* slot = tab + 2 * (j * N + i);
+        slot[0] = slot[0] * (tinv * zzz[j]);    // x = X / zz
+        slot[1] = slot[1] * (tinv * zz[j]);     // y = Y / zzz
+    }
+}
+
 }  // namespace swb
 
 using namespace swb;
@@ -188,5 +228,62 @@ extern "C" int swb_bases_export(swb_ctx* c, const swb_bases* b, size_t offset, s
     SWB_LAUNCH_CHECK(c, "k_bases_export");
     SWB_CUDA(c, cudaMemcpyAsync(out_host, d_out, n * 104, cudaMemcpyDeviceToHost, c->stream));
     SWB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SWB_OK;
+}
+
+// pick the digit width that minimises (additions) + (bucket work) for MSMs over all N bases; the
+// two weights are the measured cost of one mixed addition and of one bucket in gather + reduce
+static int tables_pick_window(size_t N) {
+    int best = 8;
+    double best_cost = 1e300;
+    for (int cb = 8; cb <= 23; cb++) {
+        const int W = (253 + cb - 1) / cb;
+        const double cost = (double)N * W * 0.37 + (double)((size_t)1 << (cb - 1)) * 3.7;
+        if (cost < best_cost) { best_cost = cost; best = cb; }
+    }
+    return best;
+}
+
+extern "C" int swb_bases_precompute(swb_ctx* c, swb_bases* b, int window_bits) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, b != nullptr, "bases_precompute: NULL bases");
+    SWB_REQUIRE(c, b->ctx == c, "bases_precompute: bases belong to another context");
+    SWB_REQUIRE(c, window_bits == 0 || (window_bits >= 4 && window_bits <= 24), "bases_precompute: window_bits must be 0 or in [4,24]");
+    if (b->tab_w) return SWB_OK;                 // already built
+    if (b->n == 0) return SWB_OK;
+    const int cb = window_bits ? window_bits : tables_pick_window(b->n);
+    const int W = (253 + cb - 1) / cb;
+    SWB_REQUIRE(c, W <= TAB_MAX_LEVELS, "bases_precompute: too many levels for this window width");
+    SWB_REQUIRE(c, b->n * (size_t)W < ((size_t)1 << 31), "bases_precompute: n * levels must be < 2^31");
+    SWB_CUDA(c, cudaSetDevice(c->device));
+    Fq* tab = nullptr;
+    const size_t bytes = b->n * (size_t)W * 96;
+    cudaError_t e = cudaMalloc(&tab, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(c, SWB_ENOMEM, "bases_precompute: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    e = cudaMemcpyAsync(tab, b->xy, b->n * 96, cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) {
+        k_bases_tables<<<(unsigned)((b->n + 127) / 128), 128, 0, c->stream>>>(tab, b->n, cb, W);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        cudaFree(tab);
+        return cuda_fail(c, e, "k_bases_tables");
+    }
+    cudaFree(b->xy);
+    b->xy = tab;
+    b->tab_c = cb;
+    b->tab_w = W;
+    return SWB_OK;
+}
+
+extern "C" int swb_bases_table_info(const swb_bases* b, int* window_bits, int* levels) {
+    if (!b) return SWB_EARG;
+    if (window_bits) *window_bits = b->tab_c;
+    if (levels) *levels = b->tab_w;
     return SWB_OK;
 }

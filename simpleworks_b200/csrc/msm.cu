@@ -74,16 +74,23 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
     }
     SWB_REQUIRE(c, scalars_dev != nullptr, "msm: NULL scalars");
     SWB_CUDA(c, cudaSetDevice(c->device));
-    const int cb = pick_window(c, n);
-    const int nwin = (254 + cb - 1) / cb;
-    SWB_REQUIRE(c, nwin <= MSM_MAX_WINDOWS, "msm: too many windows");
+    // window tables are worth it once the shared buckets hold a few points each
+    const bool tables = bases->tab_w > 0 && !c->msm_window_override &&
+                        n * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1));
+    const int cb = tables ? bases->tab_c : pick_window(c, n);
+    const int ndig = tables ? bases->tab_w : (254 + cb - 1) / cb;
+    const int nwin = tables ? 1 : ndig;
+    SWB_REQUIRE(c, ndig <= MSM_MAX_WINDOWS, "msm: too many windows");
     MsmPlan pl{};
     pl.n = n;
     pl.cb = cb;
+    pl.ndig = ndig;
     pl.nwin = nwin;
+    pl.tab_stride = tables ? bases->n : 0;
     pl.B = 1u << (cb - 1);
     pl.nb = (uint32_t)nwin * pl.B;
-    pl.total = n * (size_t)nwin;
+    pl.total = n * (size_t)ndig;
+    pl.seg_len = tables ? pl.total : n;
     SWB_REQUIRE(c, pl.total < ((size_t)1 << 32), "msm: n * windows must be < 2^32");
     {
         // enough threads to fill the GPU (>= ~512 per SM) but at most 128 additions each
@@ -104,9 +111,9 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
     bf.partial = (G1Xyzz*)get_scratch(c, "msm_partial", (size_t)pl.pcap * sizeof(G1Xyzz));
     bf.buckets = (G1Xyzz*)get_scratch(c, "msm_buckets", (size_t)pl.nb * sizeof(G1Xyzz));
     {
-        const size_t segs = (size_t)nwin * (pl.B < (uint32_t)MSM_SEG_LEN ? 1 : pl.B / MSM_SEG_LEN);
+        const size_t segs = (size_t)nwin * (pl.B / msm_reduce_seg_len((uint32_t)nwin, pl.B));
         bf.seg = (G1Xyzz*)get_scratch(c, "msm_seg", (2 * segs + 2) * sizeof(G1Xyzz));
-        bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", (2 * (segs / MSM_SEG_LEN + nwin) + 2) * sizeof(G1Xyzz));
+        bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", (2 * (segs / MSM_GROUP_MIN + nwin) + 2) * sizeof(G1Xyzz));
     }
     bf.wins = (G1Xyzz*)get_scratch(c, "msm_wins", (size_t)MSM_MAX_WINDOWS * sizeof(G1Xyzz));
     if (!bf.keys || !bf.vals || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||

@@ -10,13 +10,27 @@ constexpr int MSM_RED_THREADS = 256;   // block size of the heavy-bucket gather
 constexpr int MSM_SEG_LEN = 32;        // segment / group length of the multi-level bucket reduction
 constexpr int MSM_GATHER_INLINE = 32;  // buckets with more partial sums than this go to the block-wide path
 
+constexpr int MSM_GROUP_MIN = 4;       // smallest segment / group length (used while a level has few threads)
+
+// Segment length of level 0 of the bucket reduction: every thread walks its segment serially (two
+// additions per bucket, ~10 us each for a lone thread), so short segments while there are too few of
+// them to fill the GPU, MSM_SEG_LEN once there are plenty.
+inline uint32_t msm_reduce_seg_len(uint32_t nwin, uint32_t B) {
+    uint32_t L = B < (uint32_t)MSM_SEG_LEN ? B : (uint32_t)MSM_SEG_LEN;
+    while (L > (uint32_t)MSM_GROUP_MIN && (size_t)nwin * (B / L) < 32768) L >>= 1;
+    return L;
+}
+
 struct MsmPlan {
     size_t n;            // points
     int cb;              // window bits
-    int nwin;            // windows
-    uint32_t B;          // buckets per window = 2^(cb-1)
-    uint32_t nb;         // total buckets
-    size_t total;        // n * nwin (bucket, point) pairs
+    int ndig;            // digits (windows) per scalar
+    int nwin;            // bucket sets: ndig on the plain path, 1 with window tables
+    size_t seg_len;      // pairs per bucket set: n on the plain path, n * ndig with window tables
+    size_t tab_stride;   // records per table level (0 = plain path)
+    uint32_t B;          // buckets per set = 2^(cb-1)
+    uint32_t nb;         // total buckets = nwin * B
+    size_t total;        // n * ndig (bucket, point) pairs
     uint32_t range_len;  // sorted positions per accumulation thread
     uint32_t nranges;    // ceil(total / range_len)
     uint32_t pcap;       // capacity of the partial-sum list (nranges + nb)

@@ -121,7 +121,7 @@ int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
 
 int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     const uint32_t B = pl.B, nwin = (uint32_t)pl.nwin;
-    const uint32_t L = B < MSM_SEG_LEN ? B : (uint32_t)MSM_SEG_LEN;
+    const uint32_t L = msm_reduce_seg_len(nwin, B);
     uint32_t log_M = 0;
     while ((1u << log_M) < L) log_M++;
     uint32_t m = B / L;                                   // segments per window
@@ -129,10 +129,12 @@ int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     G1Xyzz *alt_c = bf.seg2, *alt_s = nullptr;
     k_msm_segments<<<(nwin * m + 127) / 128, 128, 0, c->stream>>>(cur_c, cur_s, bf.buckets, L, nwin * m);
     SWB_LAUNCH_CHECK(c, "k_msm_segments");
-    const uint32_t G = MSM_SEG_LEN;
-    uint32_t log_G = 0;
-    while ((1u << log_G) < G) log_G++;
     while (m > 1) {
+        // a group costs its thread ~3 G serial additions: short groups while the level has few threads
+        uint32_t G = MSM_SEG_LEN;
+        while (G > (uint32_t)MSM_GROUP_MIN && (size_t)nwin * ((m + G - 1) / G) < 8192) G >>= 1;
+        uint32_t log_G = 0;
+        while ((1u << log_G) < G) log_G++;
         const uint32_t m_out = (m + G - 1) / G;
         alt_s = alt_c + (size_t)nwin * m_out;
         k_msm_reduce_level<<<(nwin * m_out + 127) / 128, 128, 0, c->stream>>>(alt_c, alt_s, cur_c, cur_s, m, m_out, G, log_M, nwin);

@@ -6,11 +6,39 @@
 namespace swb {
 
 // ---- 1. signed-digit decomposition --------------------------------------------------------
-// keys[w*n + i] = |d| - 1 within window w (or B when d == 0: sorts to the end of the window's segment),
-// vals = i | sign << 31
+__device__ __forceinline__ bool fr_geq_mod(const uint32_t* a) {   // a (8 limbs) >= r
+    for (int k = 7; k >= 0; k--) {
+        const uint32_t m = FrParams::mod(k);
+        if (a[k] != m) return a[k] > m;
+    }
+    return true;
+}
+__device__ __forceinline__ void fr_sub_mod(uint32_t* a) {         // a -= r
+    uint64_t borrow = 0;
+    for (int k = 0; k < 8; k++) {
+        const uint64_t d = (uint64_t)a[k] - FrParams::mod(k) - borrow;
+        a[k] = (uint32_t)d;
+        borrow = (d >> 32) & 1u;
+    }
+}
+__device__ __forceinline__ void fr_mod_minus(uint32_t* a) {       // a = r - a
+    uint64_t borrow = 0;
+    for (int k = 0; k < 8; k++) {
+        const uint64_t d = (uint64_t)FrParams::mod(k) - a[k] - borrow;
+        a[k] = (uint32_t)d;
+        borrow = (d >> 32) & 1u;
+    }
+}
+
+// Plain path (tab_stride == 0): window w of scalar i -> keys[w*n + i] = |d| - 1 (or B when d == 0:
+// sorts to the end of the window's segment), vals[w*n + i] = i | sign << 31; nwin covers 254 bits so
+// that the top carry has a window of its own, and nothing is assumed about the bases.
+// Table path (tab_stride == N > 0): the point of window w is table entry w*N + i, all windows share
+// the buckets, and a scalar above r/2 is replaced by r - s with every sign flipped (bases in the
+// prime-order subgroup), so nwin = ceil(253 / c) windows suffice.
 __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                      const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
-                                                     int montgomery) {
+                                                     int montgomery, size_t tab_stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t B = 1u << (c - 1);
@@ -21,6 +49,20 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
         s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
         s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
         if (montgomery) s = s.to_canonical();
+        uint32_t flip = 0;
+        if (tab_stride) {
+            while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
+            uint32_t t[8];                                    // 2s >= r  <=>  s > r/2
+            uint32_t top = 0;
+            for (int k = 0; k < 8; k++) {
+                t[k] = (s.l[k] << 1) | top;
+                top = s.l[k] >> 31;
+            }
+            if (top || fr_geq_mod(t)) {
+                fr_mod_minus(s.l);
+                flip = 1;
+            }
+        }
         uint32_t carry = 0;
         for (int w = 0; w < nwin; w++) {
             const int bit = w * c, limb = bit >> 5, off = bit & 31;
@@ -33,7 +75,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
             uint32_t neg = 0;
             if (v > B) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
             keys[(size_t)w * n + i] = v ? v - 1 : B;
-            vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
+            vals[(size_t)w * n + i] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | ((neg ^ flip) << 31);
         }
     }
 }
@@ -70,16 +112,16 @@ int msm_launch_digits_sort(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, 
         size_t blocks = (pl.n + 255) / 256;
         size_t cap = (size_t)c->sm_count * 8;
         if (blocks > cap) blocks = cap;
-        k_msm_digits<<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb, pl.nwin,
-                                                              montgomery);
+        k_msm_digits<<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb, pl.ndig,
+                                                              montgomery, pl.tab_stride);
         SWB_LAUNCH_CHECK(c, "k_msm_digits");
     }
     uint32_t *sk = nullptr, *sv = nullptr;
-    // keys are 0 .. B (B = 2^(cb-1) marks a zero digit): cb bits, sorted inside each window's segment
-    int rc = radix_sort_segmented(c, bf.keys, bf.keys + total, bf.vals, bf.vals + total, pl.n, (uint32_t)pl.nwin, pl.cb, &sk, &sv);
+    // keys are 0 .. B (B = 2^(cb-1) marks a zero digit): cb bits, sorted inside each bucket set's segment
+    int rc = radix_sort_segmented(c, bf.keys, bf.keys + total, bf.vals, bf.vals + total, pl.seg_len, (uint32_t)pl.nwin, pl.cb, &sk, &sv);
     if (rc != SWB_OK) return rc;
     SWB_CUDA(c, cudaMemsetAsync(bf.range_off, 0, ((size_t)pl.nranges + 1) * sizeof(uint32_t), c->stream));
-    k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.n, pl.B, pl.range_len);
+    k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.seg_len, pl.B, pl.range_len);
     SWB_LAUNCH_CHECK(c, "k_msm_range_count");
     rc = exclusive_scan_u32(c, bf.range_off, (size_t)pl.nranges + 1);
     if (rc != SWB_OK) return rc;

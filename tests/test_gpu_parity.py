@@ -217,6 +217,56 @@ def test_msm_skewed_and_empty(be, srs_points):
     bases.free()
 
 
+@pytest.mark.parametrize("n,c", [(1 << 14, 0), (1 << 14, 8), (1 << 16, 0), (1 << 16, 12), (5000, 10)])
+def test_msm_window_tables_vs_oracle(be, srs_points, n, c):
+    """swb_bases_precompute: same results as the plain path / the oracle, including scalars above
+    r/2 (negated), 0, 1, r - 1, the (r +- 1)/2 boundary, offsets and sub-ranges."""
+    bases = be.load_bases(srs_points[:n]).precompute(c)
+    cb, levels = bases.table_info()
+    assert levels == -(-253 // cb) and (c == 0 or cb == c)
+    scalars = _rand_fr(n, 900 + n + c)
+    scalars[0] = 0
+    scalars[1] = O.ints_to_limbs([1], 4)[0]
+    scalars[2] = O.ints_to_limbs([G.R_MOD - 1], 4)[0]
+    scalars[3] = O.ints_to_limbs([(G.R_MOD - 1) // 2], 4)[0]
+    scalars[4] = O.ints_to_limbs([(G.R_MOD + 1) // 2], 4)[0]
+    scalars[5] = O.ints_to_limbs([(1 << 252) - 1], 4)[0]
+    scalars[6:40, 1:] = 0
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[:n]), scalars))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, scalars)), want)
+    mont = O.fr_mont(O.limbs_to_ints(scalars))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, be.to_device(mont), montgomery=True)), want)
+    # sub-range with an offset (still large enough to take the table path) and a tiny one (plain path)
+    m = n // 2
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[100:100 + m]), scalars[:m]))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, np.ascontiguousarray(scalars[:m]), offset=100)), want)
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[7:7 + 9]), scalars[:9]))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, np.ascontiguousarray(scalars[:9]), offset=7)), want)
+    # exported bases are still the originals
+    assert np.array_equal(be.export_bases(bases, 0, 64), srs_points[:64])
+    bases.free()
+
+
+def test_msm_window_tables_skew_and_identity(be, srs_points):
+    n = 1 << 14
+    pts = srs_points[:n].copy()
+    pts[5] = O.affine_from_points([None])[0]           # a base at infinity stays at infinity in every level
+    bases = be.load_bases(pts).precompute(9)
+    rs = np.random.RandomState(5)
+    scalars = _rand_fr(n, 13)
+    kind = rs.randint(0, 4, size=n)
+    scalars[kind < 2] = 0
+    scalars[kind == 2] = 0
+    scalars[kind == 2, 0] = 1
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(pts), scalars))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, scalars)), want)
+    same = np.repeat(_rand_fr(1, 14), n, axis=0)
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(pts), same))
+    assert np.array_equal(O.g1_to_affine(be.msm(bases, same)), want)
+    assert O.points_from_jacobian(be.msm(bases, np.zeros((n, 4), dtype=np.uint64)))[0] is None
+    bases.free()
+
+
 def test_fixed_base_powers_vs_oracle(be):
     g = O.g1_mul(O.g1_generator(), 5)
     beta = O.fr_mont([0xDEADBEEFCAFEBABE1234])

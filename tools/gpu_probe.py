@@ -64,6 +64,28 @@ def main():
         ms = timeit(lambda: be.msm(bases, s))
         out[f"msm_2^{log_n}_ms"] = ms
         print(f"msm 2^{log_n}: {ms:.3f} ms  {(1 << log_n) / ms / 1e3:.2f} Mpts/s", flush=True)
+    bases.free()
+    if os.environ.get("MSM_TABLES"):
+        # window tables sized for each MSM (swb_bases_precompute); MSM_TABLES=auto or a list of digit widths
+        spec = os.environ["MSM_TABLES"]
+        widths = [0] if spec == "auto" else [int(x) for x in spec.split(",")]
+        for log_n in msizes:
+            s = rand_fr(1 << log_n, 100 + log_n)
+            for cw in widths:
+                tb = be.load_bases(pts[: 1 << log_n])
+                t0 = time.time()
+                try:
+                    tb.precompute(cw)
+                except Exception as e:  # e.g. too many levels for a narrow width
+                    print(f"tables c={cw} 2^{log_n}: {e}", flush=True)
+                    tb.free()
+                    continue
+                dt = time.time() - t0
+                ms = timeit(lambda: be.msm(tb, s))
+                out[f"msm_tables_c{cw}_2^{log_n}_ms"] = ms
+                print(f"msm+tables{tb.table_info()} 2^{log_n}: {ms:.3f} ms  {(1 << log_n) / ms / 1e3:.2f} Mpts/s  (precompute {dt:.2f} s)",
+                      flush=True)
+                tb.free()
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/probe.json", "w"), indent=1)
 

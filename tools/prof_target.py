@@ -17,6 +17,8 @@ x = torch.randint(-2 ** 63, 2 ** 63 - 1, (1 << log_n, 4), dtype=torch.int64, dev
 x[:, 3] &= 0x0FFFFFFFFFFFFFFF
 if what == "msm":
     bases = be.bases_from_powers(_gen.g1_generator_jacobian(), _gen.fr_mont(0x5357423230300001), 1 << log_n)
+    if os.environ.get("MSM_TABLES"):
+        bases.precompute(0)
     for _ in range(3):
         be.msm(bases, x)
 else:
