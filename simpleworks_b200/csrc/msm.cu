@@ -102,8 +102,8 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
         pl.pcap = pl.nranges + pl.nb;
     }
     MsmBuffers bf{};
-    bf.keys = (uint32_t*)get_scratch(c, "msm_keys", pl.total * 4 * 2);
-    bf.vals = (uint32_t*)get_scratch(c, "msm_vals", pl.total * 4 * 2);
+    bf.keys = (uint32_t*)get_scratch(c, "msm_keys", msm_alt_offset(pl.total) * 4 * 2);
+    bf.vals = (uint32_t*)get_scratch(c, "msm_vals", msm_alt_offset(pl.total) * 4 * 2);
     bf.range_off = (uint32_t*)get_scratch(c, "msm_roff", ((size_t)pl.nranges + 2) * 4);
     bf.pkey = (uint32_t*)get_scratch(c, "msm_pkey", (size_t)pl.pcap * 4);
     bf.pstart = (uint32_t*)get_scratch(c, "msm_pstart", ((size_t)pl.nb + 2) * 4);

@@ -32,27 +32,59 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(G1Xyzz* __restrict__ par
                                                          const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                          const Fq* __restrict__ bases, size_t total, size_t n, uint32_t B,
                                                          uint32_t len, uint32_t nranges) {
+    // The thread walks its range sequentially; reading keys/vals one word at a time would fetch a
+    // whole DRAM sector per word for every lane (ranges are len*4 bytes apart).  So each thread pulls
+    // 8 positions (two 16-byte loads per array) into its own column of a small shared-memory queue.
+    __shared__ uint32_t qk[8][128], qv[8][128];
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nranges) return;
-    const size_t p0 = (size_t)r * len;
+    const uint32_t t = threadIdx.x;
+    const size_t p0 = (size_t)r * len;                      // len is a power of two >= 16: 32-byte aligned chunks
     const size_t p1 = p0 + len < total ? p0 + len : total;
+    auto fetch = [&](size_t q, uint32_t* k, uint32_t* v) {
+        const uint32_t j = (uint32_t)(q - p0) & 7u;
+        if (j == 0) {
+            if (q + 8 <= total) {
+                const uint4 k0 = *reinterpret_cast<const uint4*>(keys + q), k1 = *reinterpret_cast<const uint4*>(keys + q + 4);
+                const uint4 v0 = *reinterpret_cast<const uint4*>(vals + q), v1 = *reinterpret_cast<const uint4*>(vals + q + 4);
+                qk[0][t] = k0.x; qk[1][t] = k0.y; qk[2][t] = k0.z; qk[3][t] = k0.w;
+                qk[4][t] = k1.x; qk[5][t] = k1.y; qk[6][t] = k1.z; qk[7][t] = k1.w;
+                qv[0][t] = v0.x; qv[1][t] = v0.y; qv[2][t] = v0.z; qv[3][t] = v0.w;
+                qv[4][t] = v1.x; qv[5][t] = v1.y; qv[6][t] = v1.z; qv[7][t] = v1.w;
+            } else {
+                for (uint32_t e = 0; q + e < total; e++) {
+                    qk[e][t] = keys[q + e];
+                    qv[e][t] = vals[q + e];
+                }
+            }
+        }
+        *k = qk[j][t];
+        *v = qv[j][t];
+    };
     uint32_t out = range_off[r];
     uint32_t cur = 0xffffffffu;
     G1Xyzz acc = G1Xyzz::identity();
+    // bucket set of position p is p / n; tracked incrementally (a range may cross set boundaries)
+    uint32_t set_base = (uint32_t)(p0 / n) * B;
+    size_t set_end = (p0 / n + 1) * n;
     // software pipeline: the next point is in flight while the current one is added
-    uint32_t k_next = keys[p0], v_next = vals[p0];
+    uint32_t k_next, v_next;
+    fetch(p0, &k_next, &v_next);
     G1Aff pt_next;
     if (k_next < B) pt_next = ld_aff(bases, v_next & 0x7fffffffu);
     for (size_t p = p0; p < p1; p++) {
         const uint32_t kl = k_next, v = v_next;
         G1Aff pt = pt_next;
         if (p + 1 < p1) {
-            k_next = keys[p + 1];
-            v_next = vals[p + 1];
+            fetch(p + 1, &k_next, &v_next);
             if (k_next < B) pt_next = ld_aff(bases, v_next & 0x7fffffffu);
         }
-        if (kl >= B) continue;                              // zero digit (tail of a window's segment)
-        const uint32_t k = (uint32_t)(p / n) * B + kl;      // global bucket id
+        if (p == set_end) {
+            set_base += B;
+            set_end += n;
+        }
+        if (kl >= B) continue;                              // zero digit (tail of a set's segment)
+        const uint32_t k = set_base + kl;                   // global bucket id
         if (k != cur) {
             if (cur != 0xffffffffu) {
                 partial[out] = acc;

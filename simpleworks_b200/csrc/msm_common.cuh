@@ -21,6 +21,10 @@ inline uint32_t msm_reduce_seg_len(uint32_t nwin, uint32_t B) {
     return L;
 }
 
+// the sort ping-pongs between two halves of the key / value buffers; the second half starts on a
+// 256-byte boundary so that the accumulation kernel can read either with 16-byte loads
+inline size_t msm_alt_offset(size_t total) { return (total + 63) & ~(size_t)63; }
+
 struct MsmPlan {
     size_t n;            // points
     int cb;              // window bits
@@ -37,8 +41,8 @@ struct MsmPlan {
 };
 
 struct MsmBuffers {
-    uint32_t* keys;      // [2][total]
-    uint32_t* vals;      // [2][total]
+    uint32_t* keys;      // [2][msm_alt_offset(total)]
+    uint32_t* vals;      // [2][msm_alt_offset(total)]
     uint32_t* range_off; // [nranges + 1] runs per range, scanned in place: where each range writes
     uint32_t* pkey;      // [pcap] bucket id of each partial sum
     uint32_t* pstart;    // [nb + 1] first partial of each bucket

@@ -118,7 +118,7 @@ int msm_launch_digits_sort(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, 
     }
     uint32_t *sk = nullptr, *sv = nullptr;
     // keys are 0 .. B (B = 2^(cb-1) marks a zero digit): cb bits, sorted inside each bucket set's segment
-    int rc = radix_sort_segmented(c, bf.keys, bf.keys + total, bf.vals, bf.vals + total, pl.seg_len, (uint32_t)pl.nwin, pl.cb, &sk, &sv);
+    int rc = radix_sort_segmented(c, bf.keys, bf.keys + msm_alt_offset(total), bf.vals, bf.vals + msm_alt_offset(total), pl.seg_len, (uint32_t)pl.nwin, pl.cb, &sk, &sv);
     if (rc != SWB_OK) return rc;
     SWB_CUDA(c, cudaMemsetAsync(bf.range_off, 0, ((size_t)pl.nranges + 1) * sizeof(uint32_t), c->stream));
     k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.seg_len, pl.B, pl.range_len);
