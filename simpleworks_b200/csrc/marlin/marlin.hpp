@@ -236,6 +236,19 @@ struct ProvingKey {
     std::vector<Fr> t_coef;
     std::vector<Commitment> index_comms;
     CommitterKey<Engine> ck;
+    // the same matrices where the engine keeps its vectors (device memory for the CUDA engine):
+    // A, B, C in CSR over z = (instance | witness), and the regrouped entries above (tagged by matrix)
+    Engine* eng = nullptr;
+    void *m_a = nullptr, *m_b = nullptr, *m_c = nullptr, *m_t = nullptr;
+    ProvingKey() {}
+    ProvingKey(const ProvingKey&) = delete;
+    ProvingKey& operator=(const ProvingKey&) = delete;
+    ~ProvingKey() {
+        if (!eng) return;
+        void* ms[4] = {m_a, m_b, m_c, m_t};
+        for (void* m : ms)
+            if (m) eng->csr_free(m);
+    }
 };
 // IndexVerifierKey: index info + index commitments + MarlinKZG10's VerifierKey (g, gamma_g, h, beta_h,
 // degree_bounds_and_shift_powers); self-contained, independent of the engine
@@ -429,6 +442,23 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
                     pk->t_row[at] = (uint32_t)r; pk->t_mat[at] = (uint8_t)m; pk->t_coef[at] = e.first;
                 }
     }
+    {
+        pk->eng = srs.eng;          // lives as long as the SRS, which the key references anyway (ck.srs)
+        auto upload_rows = [&](const std::vector<SparseRow>& m) {
+            std::vector<uint32_t> start(m.size() + 1, 0), col;
+            std::vector<Fr> coef;
+            for (size_t r = 0; r < m.size(); r++) start[r + 1] = start[r] + (uint32_t)m[r].e.size();
+            col.reserve(start.back());
+            coef.reserve(start.back());
+            for (auto& row : m)
+                for (auto& e : row.e) { col.push_back(e.second); coef.push_back(e.first); }
+            return eng.csr_upload(start, col, coef, nullptr);
+        };
+        pk->m_a = upload_rows(pk->a);
+        pk->m_b = upload_rows(pk->b);
+        pk->m_c = upload_rows(pk->c);
+        pk->m_t = eng.csr_upload(pk->t_start, pk->t_row, pk->t_coef, &pk->t_mat);
+    }
     const char* names[6] = {"row", "col", "a_val", "b_val", "c_val", "row_col"};
     typename Engine::Vec rowcol_v = eng.vfrom(rowcol);
     const typename Engine::Vec* evs[6] = {&pk->row_evals, &pk->col_evals, &pk->val_a_evals, &pk->val_b_evals, &pk->val_c_evals, &rowcol_v};
@@ -592,12 +622,22 @@ inline void build_lcs(const Domain& H, const Domain& K, const Challenges& ch, co
 // prove (AHPForR1CS prover rounds + MarlinKZG10 commit/open)
 // ------------------------------------------------------------------------------------------------
 template <class Engine>
-Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rng) {
+Proof prove(Engine& eng, const ProvingKey<Engine>& pk, const R1cs& cs, ChaChaRng& zk_rng) {
     if (!cs.has_assignment) throw MarlinError("prove: constraint system has no assignment");
-    cs.pad_instance();
-    cs.make_square();
-    if (cs.num_variables() != pk.info.num_variables || cs.num_constraints() != pk.info.num_constraints)
-        throw MarlinError("prove: constraint system does not match the proving key");
+    // the assignment after pad_input_for_indexer_and_prover + make_matrices_square (the matrices
+    // themselves live in the proving key): instance padded with zeros to a power of two, dummy
+    // witnesses of value one when there are more constraints than variables
+    std::vector<Fr> instance = cs.instance, witness = cs.witness;
+    {
+        size_t target = 1;
+        while (target < instance.size()) target <<= 1;
+        instance.resize(target, Fr::zero());
+        size_t nv = instance.size() + witness.size(), nc = cs.num_constraints();
+        if (nc < nv) nc = nv;
+        else if (nv < nc) { witness.resize(witness.size() + (nc - nv), Fr::one()); nv = nc; }
+        if (nv != pk.info.num_variables || nc != pk.info.num_constraints || instance.size() != pk.info.num_instance)
+            throw MarlinError("prove: constraint system does not match the proving key");
+    }
     using Vec = typename Engine::Vec;
     const Domain &H = pk.dom_h, &K = pk.dom_k, &X = pk.dom_x;
     const size_t nh = H.n, nx = X.n, ratio = nh / nx;
@@ -618,26 +658,22 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     };
     ScopedPhase ph_total("total");
     std::unique_ptr<ScopedPhase> ph(new ScopedPhase("r0_init"));
-    // ---- init: z_A = A z, z_B = B z (sparse, host) ------------------------------------------------
-    auto matvec = [&](const std::vector<SparseRow>& m) {
-        std::vector<Fr> out(nh, Fr::zero());
-#pragma omp parallel for schedule(static)
-        for (size_t r = 0; r < m.size(); r++) {
-            Fr s = Fr::zero();
-            for (auto& e : m[r].e) s = s + e.first * cs.value(e.second);
-            out[r] = s;
-        }
-        return out;
-    };
-    std::vector<Fr> za_ev = matvec(pk.a), zb_ev = matvec(pk.b);
+    // ---- init: z_A = A z, z_B = B z on the engine (prover_init) ------------------------------------
+    Vec z_vec;
     {
-        std::vector<Fr> zc_ev = matvec(pk.c);
-        bool bad = false;
-#pragma omp parallel for schedule(static) reduction(|| : bad)
-        for (size_t i = 0; i < nh; i++) bad = bad || !(za_ev[i] * zb_ev[i] == zc_ev[i]);
-        if (bad) throw MarlinError("prove: constraint system is not satisfied");
+        std::vector<Fr> z = instance;
+        z.insert(z.end(), witness.begin(), witness.end());
+        z_vec = eng.vfrom(z);
     }
-    std::vector<Fr> public_input(cs.instance.begin() + 1, cs.instance.end());   // padded, without the one
+    Vec za_ev = eng.vspmv(pk.m_a, z_vec, nh, nullptr), zb_ev = eng.vspmv(pk.m_b, z_vec, nh, nullptr);
+    {
+        Vec chk = eng.vspmv(pk.m_c, z_vec, nh, nullptr);
+        Vec prod = eng.vclone(za_ev);
+        eng.vmul(prod, zb_ev);
+        eng.vsub(chk, prod);
+        if (eng.vlen(chk) != 0) throw MarlinError("prove: constraint system is not satisfied");
+    }
+    std::vector<Fr> public_input(instance.begin() + 1, instance.end());   // padded, without the one
     FiatShamirRng fs;
     {
         std::vector<uint8_t> init;
@@ -649,25 +685,16 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     }
     // ---- round 1 ---------------------------------------------------------------------------------
     ph.reset(); ph.reset(new ScopedPhase("r1_polys"));
-    Vec x_hat = eng.vfrom(cs.instance);
+    Vec x_hat = eng.vfrom(instance);
     ntt(x_hat, X, true);
     Vec w_poly;
     const Fr rho_w = rand_fr(zk_rng);
     {
+        ScopedPhase sp("r1_polys.w");
         // w on H: 0 on the X-subdomain, witness - x^ elsewhere
-        std::vector<Fr> wit_on_h(nh, Fr::zero()), mask01(nh, Fr::one());
-#pragma omp parallel for schedule(static)
-        for (size_t k = 0; k < nh; k++) {
-            if (k % ratio == 0) { mask01[k] = Fr::zero(); continue; }
-            const size_t wi = k - k / ratio - 1;
-            if (wi < cs.witness.size()) wit_on_h[k] = cs.witness[wi];
-        }
         Vec xh_on_h = eng.vclone(x_hat);
         ntt(xh_on_h, H, false);
-        Vec w_ev = eng.vfrom(wit_on_h);
-        eng.vsub(w_ev, xh_on_h);
-        Vec m01 = eng.vfrom(mask01);
-        eng.vmul(w_ev, m01);
+        Vec w_ev = eng.vwitness_evals(z_vec, instance.size(), xh_on_h, ratio);
         ntt(w_ev, H, true);
         // + rho_w * (X^nh - 1), then / v_X
         eng.vresize(w_ev, nh + 1);
@@ -676,8 +703,8 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
         Vec rem;
         eng.vdiv_vanishing(w_ev, nx, &w_poly, &rem);
     }
-    auto blinded_interp = [&](const std::vector<Fr>& ev, const Fr& rho) {
-        Vec p = eng.vfrom(ev);
+    auto blinded_interp = [&](Vec& ev, const Fr& rho) {
+        Vec p = std::move(ev);
         ntt(p, H, true);
         eng.vresize(p, nh + 1);
         eng.vset(p, 0, eng.vget(p, 0) - rho);
@@ -685,16 +712,23 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
         return p;
     };
     const Fr rho_a = rand_fr(zk_rng);
-    Vec za_poly = blinded_interp(za_ev, rho_a);
+    Vec za_poly, zb_poly;
+    {
+        ScopedPhase sp("r1_polys.z");
+        za_poly = blinded_interp(za_ev, rho_a);
+    }
     const Fr rho_b = rand_fr(zk_rng);
-    Vec zb_poly = blinded_interp(zb_ev, rho_b);
+    {
+        ScopedPhase sp("r1_polys.z");
+        zb_poly = blinded_interp(zb_ev, rho_b);
+    }
     Vec mask;
     {
-        Poly mh = rand_poly(3 * nh - 1, zk_rng);               // degree 3|H| + 2 zk - 3
+        ScopedPhase sp("r1_polys.mask");
+        mask = eng.vrand(zk_rng, 3 * nh);                      // degree 3|H| + 2 zk - 3
         Fr r0 = Fr::zero();
-        for (size_t i = 0; i < mh.size(); i += nh) r0 = r0 + mh[i];
-        mh[0] = mh[0] - r0;                                    // sum over H becomes zero
-        mask = eng.vfrom(mh);
+        for (size_t i = 0; i < 3 * nh; i += nh) r0 = r0 + eng.vget(mask, i);
+        eng.vset(mask, 0, eng.vget(mask, 0) - r0);             // sum over H becomes zero
     }
     std::vector<LabeledPoly<Engine>> first(4);
     first[0].label = "w"; first[0].poly = std::move(w_poly); first[0].hiding = true;
@@ -720,20 +754,12 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, R1cs cs, ChaChaRng& zk_rn
     eng.vlin(r_alpha, ch.alpha, Fr::one().neg());
     eng.vbatch_inverse(r_alpha);
     eng.vscale(r_alpha, vh_alpha);
-    // t on H: t(H[pos(c)]) = sum_M eta_M sum_r M[r][c] r_alpha(H[r])   (sparse transpose product, host)
+    // t on H: t(H[pos(c)]) = sum_M eta_M sum_r M[r][c] r_alpha(H[r])   (sparse transpose product on the engine)
     Vec t_poly;
     {
-        const std::vector<Fr> r_alpha_ev = eng.vhost(r_alpha);
-        std::vector<Fr> t_ev(nh, Fr::zero());
+        ScopedPhase sp("r2_polys.t");
         const Fr etas[3] = {ch.eta_a, ch.eta_b, ch.eta_c};
-#pragma omp parallel for schedule(static)
-        for (size_t p = 0; p < nh; p++) {
-            Fr acc = Fr::zero();
-            for (uint32_t k = pk.t_start[p]; k < pk.t_start[p + 1]; k++)
-                acc = acc + etas[pk.t_mat[k]] * pk.t_coef[k] * r_alpha_ev[pk.t_row[k]];
-            t_ev[p] = acc;
-        }
-        t_poly = eng.vfrom(t_ev);
+        t_poly = eng.vspmv(pk.m_t, r_alpha, nh, etas);
     }
     ntt(t_poly, H, true);
     ntt(r_alpha, H, true);                                   // now the polynomial r(alpha, X)

@@ -59,6 +59,8 @@ public:
     }
     uint64_t position() const { return pos_; }
     void seek(uint64_t pos) { pos_ = pos; }
+    const uint32_t* key_words() const { return key_; }      // for engines that expand the stream themselves
+    int rounds() const { return rounds_; }
 
 private:
     static inline uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }

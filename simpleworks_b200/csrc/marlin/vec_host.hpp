@@ -4,6 +4,7 @@
 // interface on device memory so that polynomials stay in HBM between NTTs and MSMs.
 #pragma once
 #include "poly.hpp"
+#include "rng.hpp"
 
 namespace swb {
 namespace marlin {
@@ -46,6 +47,54 @@ struct HostVecOps {
     void vbatch_inverse(Vec& v) { batch_inverse(v); }
     Vec vshift_down(const Vec& p, size_t k) { return k < p.size() ? Vec(p.begin() + k, p.end()) : Vec(); }
     Vec vdomain(uint32_t log_n) { return Domain((size_t)1 << log_n).elements(); }
+    // n consecutive Fr::rand draws (DensePolynomial::rand)
+    Vec vrand(ChaChaRng& rng, size_t n) {
+        Vec v(n);
+        rand_fr_bulk(rng, v.data(), n);
+        return v;
+    }
+    // sparse matrices in CSR form (optionally a 0/1/2 tag per entry selecting one of three weights)
+    struct HostCsr {
+        std::vector<uint32_t> start, col;
+        std::vector<Fr> coef;
+        std::vector<uint8_t> tag;
+    };
+    void* csr_upload(const std::vector<uint32_t>& start, const std::vector<uint32_t>& col, const std::vector<Fr>& coef,
+                     const std::vector<uint8_t>* tag) {
+        HostCsr* m = new HostCsr();
+        m->start = start; m->col = col; m->coef = coef;
+        if (tag) m->tag = *tag;
+        return m;
+    }
+    void csr_free(void* h) { delete static_cast<HostCsr*>(h); }
+    Vec vspmv(const void* h, const Vec& x, size_t nout, const Fr* weights) {
+        const HostCsr& m = *static_cast<const HostCsr*>(h);
+        const size_t nrows = m.start.size() - 1;
+        Vec out(nout, Fr::zero());
+#pragma omp parallel for schedule(static)
+        for (size_t r = 0; r < nrows; r++) {
+            Fr acc = Fr::zero();
+            for (uint32_t k = m.start[r]; k < m.start[r + 1]; k++) {
+                Fr term = m.coef[k] * x[m.col[k]];
+                if (!m.tag.empty()) term = term * weights[m.tag[k]];
+                acc = acc + term;
+            }
+            out[r] = acc;
+        }
+        return out;
+    }
+    // w on H before interpolation: 0 on the X-subdomain, witness - x^ elsewhere (z = instance | witness)
+    Vec vwitness_evals(const Vec& z, size_t ninst, const Vec& xh_on_h, size_t ratio) {
+        const size_t nh = xh_on_h.size();
+        Vec out(nh, Fr::zero());
+#pragma omp parallel for schedule(static)
+        for (size_t k = 0; k < nh; k++) {
+            if (k % ratio == 0) continue;
+            const size_t wi = ninst + (k - k / ratio - 1);
+            out[k] = (wi < z.size() ? z[wi] : Fr::zero()) - xh_on_h[k];
+        }
+        return out;
+    }
 };
 
 }  // namespace marlin

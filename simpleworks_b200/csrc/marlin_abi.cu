@@ -4,6 +4,7 @@
 // engine in libswb200.
 #include "ctx.hpp"
 #include "marlin/c_api_impl.hpp"
+#include "marlin_ops.hpp"
 #include "polyops.hpp"
 
 using namespace swb;
@@ -76,8 +77,24 @@ struct GpuEngine {
         Vec v;
         v.c = c;
         v.n = v.cap = n;
-        if (n) cu(cudaMallocAsync((void**)&v.p, n * sizeof(Fr), c->stream), "cudaMallocAsync");
+        if (!n) return v;
+        if (c->trace >= 2) {
+            const auto t0 = std::chrono::steady_clock::now();
+            cu(cudaMallocAsync((void**)&v.p, n * sizeof(Fr), c->stream), "cudaMallocAsync");
+            host_profile().acc["op:alloc(host side)"] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        } else {
+            cu(cudaMallocAsync((void**)&v.p, n * sizeof(Fr), c->stream), "cudaMallocAsync");
+        }
         return v;
+    }
+    void pool_stats(const char* when) {
+        if (c->trace < 2) return;
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0;
+        if (cudaDeviceGetMemPool(&pool, c->device) != cudaSuccess) return;
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        fprintf(stderr, "[swb trace] pool %s: reserved %.1f MiB, used %.1f MiB\n", when, reserved / 1048576.0, used / 1048576.0);
     }
     Vec vzeros(size_t n) {
         OpTimer ot_(c, "vzeros");
@@ -211,6 +228,60 @@ struct GpuEngine {
         if (v.n != ((size_t)1 << log_n)) throw MarlinError("vntt: size mismatch");
         ck(swb_ntt_fr_dev(c, reinterpret_cast<swb_fr*>(v.p), log_n, inverse, coset), "ntt");
     }
+    // ---- prover-specific vectors (marlin_ops.cu) ----------------------------------------------------
+    Vec vrand(ChaChaRng& rng, size_t n) {
+        OpTimer ot_(c, "vrand");
+        Vec v = alloc(n);
+        uint64_t used = 0;
+        ck(rand_fr_dev(c, v.p, n, rng.key_words(), rng.rounds(), rng.position(), &used), "vrand");
+        rng.seek(rng.position() + used);
+        return v;
+    }
+    struct DevCsr {
+        uint32_t *start = nullptr, *col = nullptr;
+        Fr* coef = nullptr;
+        uint8_t* tag = nullptr;
+        size_t nrows = 0;
+    };
+    template <class T>
+    T* upload(const std::vector<T>& h) {
+        T* d = nullptr;
+        cu(cudaMalloc((void**)&d, (h.size() ? h.size() : 1) * sizeof(T)), "cudaMalloc");
+        if (!h.empty()) cu(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream), "H2D");
+        return d;
+    }
+    void* csr_upload(const std::vector<uint32_t>& start, const std::vector<uint32_t>& col, const std::vector<Fr>& coef,
+                     const std::vector<uint8_t>* tag) {
+        DevCsr* m = new DevCsr();
+        m->nrows = start.size() - 1;
+        m->start = upload(start);
+        m->col = upload(col);
+        m->coef = upload(coef);
+        if (tag) m->tag = upload(*tag);
+        cu(cudaStreamSynchronize(c->stream), "sync");        // the host vectors may be temporaries
+        return m;
+    }
+    void csr_free(void* h) {
+        DevCsr* m = static_cast<DevCsr*>(h);
+        if (!m) return;
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(m->start); cudaFree(m->col); cudaFree(m->coef); cudaFree(m->tag);
+        delete m;
+    }
+    Vec vspmv(const void* h, const Vec& x, size_t nout, const Fr* weights) {
+        OpTimer ot_(c, "vspmv");
+        const DevCsr& m = *static_cast<const DevCsr*>(h);
+        Vec out = alloc(nout);
+        ck(csr_spmv_dev(c, out.p, nout, m.nrows, m.start, m.col, m.coef, m.tag, x.p, weights), "vspmv");
+        return out;
+    }
+    Vec vwitness_evals(const Vec& z, size_t ninst, const Vec& xh_on_h, size_t ratio) {
+        OpTimer ot_(c, "vwitness_evals");
+        Vec out = alloc(xh_on_h.n);
+        ck(witness_evals_dev(c, out.p, xh_on_h.n, ratio, z.p, ninst, z.n, xh_on_h.p), "vwitness_evals");
+        return out;
+    }
     // ---- bases / MSM --------------------------------------------------------------------------------
     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n) {
         swb_g1_jacobian gj;
@@ -343,7 +414,9 @@ int swb_marlin_prove(swb_ctx* c, const swb_pk* pk, const swb_r1cs* cs, swb_rng* 
     if (!c || !pk || !cs || !rng || !proof || !len) return SWB_EARG;
     std::string err;
     GpuEngine eng(c);
+    eng.pool_stats("before prove");
     int rc = Api::prove(eng, pk->h, cs->h, &rng->h, proof, len, &err);
+    eng.pool_stats("after prove");
     if (rc) return swb::set_err(c, SWB_EINTERNAL, "prove: %s", err.c_str());
     return SWB_OK;
 }
