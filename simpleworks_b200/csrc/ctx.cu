@@ -31,6 +31,42 @@ int cuda_fail(swb_ctx* c, cudaError_t e, const char* what) {
     return set_err(c, SWB_ECUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
 }
 
+void* vec_alloc(swb_ctx* c, size_t bytes, size_t* granted) {
+    const size_t unit = (size_t)2 << 20;
+    const size_t want = bytes ? (bytes + unit - 1) / unit * unit : unit;
+    auto it = c->vec_cache.lower_bound(want);
+    if (it != c->vec_cache.end() && it->first <= want + want / 4) {      // close fit: do not burn a big block on a small vector
+        void* p = it->second;
+        *granted = it->first;
+        c->vec_cache_bytes -= it->first;
+        c->vec_cache.erase(it);
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        // out of memory: give the cache back and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(c->stream);
+        for (auto& kv : c->vec_cache) cudaFree(kv.second);
+        c->vec_cache.clear();
+        c->vec_cache_bytes = 0;
+        e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_err(c, SWB_ENOMEM, "vec_alloc: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return nullptr;
+        }
+    }
+    *granted = want;
+    return p;
+}
+void vec_free(swb_ctx* c, void* p, size_t granted) {
+    if (!p) return;
+    c->vec_cache.emplace(granted, p);
+    c->vec_cache_bytes += granted;
+}
+
 void* get_scratch(swb_ctx* c, const char* tag, size_t bytes) {
     auto& s = c->scratch[tag];
     if (s.bytes >= bytes && s.p) return s.p;
@@ -115,6 +151,7 @@ void swb_destroy(swb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->vec_cache) cudaFree(kv.second);
     for (auto& kv : c->scratch)
         if (kv.second.p) cudaFree(kv.second.p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -135,6 +172,11 @@ const char* swb_last_error(const swb_ctx* c) {
 
 int swb_set_stream(swb_ctx* c, void* s) {
     if (!c) return SWB_EARG;
+    // scratch and cached blocks are reused in stream order: drain the old stream before work moves
+    if (c->stream != (cudaStream_t)s) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
     c->stream = (cudaStream_t)s;
     return SWB_OK;
 }

@@ -36,6 +36,10 @@ struct swb_ctx {
     std::map<std::string, Scratch> scratch;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+
+    // cache of freed device blocks for the engine's vectors (vec_alloc / vec_free below), by size
+    std::multimap<size_t, void*> vec_cache;
+    size_t vec_cache_bytes = 0;
 };
 
 struct swb_bases {
@@ -50,6 +54,13 @@ struct swb_bases {
 namespace swb {
 
 int set_err(swb_ctx* c, int code, const char* fmt, ...);
+// Device blocks for short-lived vectors (the prover allocates and frees hundreds per proof).  All work of
+// a context is ordered on one stream, so a freed block can be handed to the next request at once;
+// blocks are rounded to 2 MiB and kept until swb_destroy, which keeps cudaMalloc/cudaFree (and the
+// driver's own pool maintenance) out of the steady state.  *granted is the block's real size, to be
+// passed back to vec_free.  nullptr + error set on failure.
+void* vec_alloc(swb_ctx* c, size_t bytes, size_t* granted);
+void vec_free(swb_ctx* c, void* p, size_t granted);
 int cuda_fail(swb_ctx* c, cudaError_t e, const char* what);
 // returns device scratch of at least `bytes`, tagged; nullptr + error set on failure
 void* get_scratch(swb_ctx* c, const char* tag, size_t bytes);

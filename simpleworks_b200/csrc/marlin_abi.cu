@@ -12,28 +12,29 @@ using namespace swb::marlin;
 
 namespace {
 
-// Fr vector in HBM, owned; stream-ordered allocation from the device's default pool
+// Fr vector in HBM, owned; blocks come from the context's stream-ordered cache (ctx.hpp: vec_alloc)
 struct DVec {
     swb_ctx* c = nullptr;
     Fr* p = nullptr;
-    size_t n = 0, cap = 0;
+    size_t n = 0, cap = 0;       // elements in use / elements the block holds
+    size_t blk = 0;              // block size in bytes, for vec_free
     DVec() {}
     DVec(const DVec&) = delete;
     DVec& operator=(const DVec&) = delete;
-    DVec(DVec&& o) noexcept : c(o.c), p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    DVec(DVec&& o) noexcept : c(o.c), p(o.p), n(o.n), cap(o.cap), blk(o.blk) { o.p = nullptr; o.n = o.cap = o.blk = 0; }
     DVec& operator=(DVec&& o) noexcept {
         if (this != &o) {
             release();
-            c = o.c; p = o.p; n = o.n; cap = o.cap;
-            o.p = nullptr; o.n = o.cap = 0;
+            c = o.c; p = o.p; n = o.n; cap = o.cap; blk = o.blk;
+            o.p = nullptr; o.n = o.cap = o.blk = 0;
         }
         return *this;
     }
     ~DVec() { release(); }
     void release() {
-        if (p && c) cudaFreeAsync(p, c->stream);
+        if (p && c) vec_free(c, p, blk);
         p = nullptr;
-        n = cap = 0;
+        n = cap = blk = 0;
     }
     size_t size() const { return n; }
 };
@@ -59,14 +60,7 @@ struct OpTimer {
 struct GpuEngine {
     using Vec = DVec;
     swb_ctx* c;
-    explicit GpuEngine(swb_ctx* ctx) : c(ctx) {
-        cudaSetDevice(c->device);
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
-            uint64_t keep = ~0ull;           // keep freed blocks cached: the rounds re-allocate the same sizes
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
+    explicit GpuEngine(swb_ctx* ctx) : c(ctx) { cudaSetDevice(c->device); }
     [[noreturn]] void fail(const char* what) { throw MarlinError(std::string(what) + ": " + swb_last_error(c)); }
     void ck(int rc, const char* what) { if (rc != SWB_OK) fail(what); }
     void cu(cudaError_t e, const char* what) {
@@ -76,25 +70,12 @@ struct GpuEngine {
     Vec alloc(size_t n) {
         Vec v;
         v.c = c;
-        v.n = v.cap = n;
         if (!n) return v;
-        if (c->trace >= 2) {
-            const auto t0 = std::chrono::steady_clock::now();
-            cu(cudaMallocAsync((void**)&v.p, n * sizeof(Fr), c->stream), "cudaMallocAsync");
-            host_profile().acc["op:alloc(host side)"] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        } else {
-            cu(cudaMallocAsync((void**)&v.p, n * sizeof(Fr), c->stream), "cudaMallocAsync");
-        }
+        v.p = static_cast<Fr*>(vec_alloc(c, n * sizeof(Fr), &v.blk));
+        if (!v.p) fail("vec_alloc");
+        v.n = n;
+        v.cap = v.blk / sizeof(Fr);
         return v;
-    }
-    void pool_stats(const char* when) {
-        if (c->trace < 2) return;
-        cudaMemPool_t pool;
-        uint64_t reserved = 0, used = 0;
-        if (cudaDeviceGetMemPool(&pool, c->device) != cudaSuccess) return;
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-        fprintf(stderr, "[swb trace] pool %s: reserved %.1f MiB, used %.1f MiB\n", when, reserved / 1048576.0, used / 1048576.0);
     }
     Vec vzeros(size_t n) {
         OpTimer ot_(c, "vzeros");
@@ -414,9 +395,7 @@ int swb_marlin_prove(swb_ctx* c, const swb_pk* pk, const swb_r1cs* cs, swb_rng* 
     if (!c || !pk || !cs || !rng || !proof || !len) return SWB_EARG;
     std::string err;
     GpuEngine eng(c);
-    eng.pool_stats("before prove");
     int rc = Api::prove(eng, pk->h, cs->h, &rng->h, proof, len, &err);
-    eng.pool_stats("after prove");
     if (rc) return swb::set_err(c, SWB_EINTERNAL, "prove: %s", err.c_str());
     return SWB_OK;
 }
