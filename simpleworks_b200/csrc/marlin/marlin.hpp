@@ -374,26 +374,47 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     pk->dom_h = Domain(cs.num_constraints());
     pk->dom_x = Domain(cs.num_instance);
     const Domain& H = pk->dom_h;
-    // joint sparsity pattern, row by row, columns in increasing order
-    std::vector<std::vector<std::pair<uint32_t, Fr>>> ja(cs.a.size()), jb(cs.a.size()), jc(cs.a.size());
-    size_t nnz = 0;
-    std::vector<uint32_t> er, ec;
-    std::vector<Fr> va, vb, vc;
-    for (size_t r = 0; r < cs.a.size(); r++) {
-        std::map<uint32_t, std::array<Fr, 3>> cols;
-        auto put = [&](const SparseRow& row, int which) {
-            for (auto& e : row.e) {
-                auto it = cols.find(e.second);
-                if (it == cols.end()) it = cols.emplace(e.second, std::array<Fr, 3>{Fr::zero(), Fr::zero(), Fr::zero()}).first;
-                it->second[which] = it->second[which] + e.first;
+    // joint sparsity pattern, row by row, columns in increasing order; rows are independent, so
+    // they are merged in parallel: pass 1 counts the distinct columns of each row, pass 2 fills
+    struct Ent { uint32_t col; uint8_t which; Fr coef; };
+    const size_t nrows = cs.a.size();
+    auto merged_row = [&](size_t r, std::vector<Ent>& tmp) {
+        tmp.clear();
+        const SparseRow* rows[3] = {&cs.a[r], &cs.b[r], &cs.c[r]};
+        for (uint8_t w = 0; w < 3; w++)
+            for (auto& e : rows[w]->e) tmp.push_back(Ent{e.second, w, e.first});
+        std::stable_sort(tmp.begin(), tmp.end(), [](const Ent& x, const Ent& y) { return x.col < y.col; });
+    };
+    std::vector<size_t> row_off(nrows + 1, 0);
+#pragma omp parallel
+    {
+        std::vector<Ent> tmp;
+#pragma omp for schedule(static)
+        for (size_t r = 0; r < nrows; r++) {
+            merged_row(r, tmp);
+            size_t distinct = 0;
+            for (size_t k = 0; k < tmp.size(); k++) distinct += (k == 0 || tmp[k].col != tmp[k - 1].col);
+            row_off[r + 1] = distinct;
+        }
+    }
+    for (size_t r = 0; r < nrows; r++) row_off[r + 1] += row_off[r];
+    const size_t nnz = row_off[nrows];
+    std::vector<uint32_t> er(nnz), ec(nnz);
+    std::vector<Fr> va(nnz, Fr::zero()), vb(nnz, Fr::zero()), vc(nnz, Fr::zero());
+#pragma omp parallel
+    {
+        std::vector<Ent> tmp;
+#pragma omp for schedule(static)
+        for (size_t r = 0; r < nrows; r++) {
+            merged_row(r, tmp);
+            size_t at = row_off[r];
+            for (size_t k = 0; k < tmp.size(); k++) {
+                if (k && tmp[k].col != tmp[k - 1].col) at++;
+                er[at] = (uint32_t)r;
+                ec[at] = tmp[k].col;
+                Fr& dst = tmp[k].which == 0 ? va[at] : tmp[k].which == 1 ? vb[at] : vc[at];
+                dst = dst + tmp[k].coef;
             }
-        };
-        put(cs.a[r], 0); put(cs.b[r], 1); put(cs.c[r], 2);
-        for (auto& kv : cols) {
-            er.push_back((uint32_t)r);
-            ec.push_back(kv.first);
-            va.push_back(kv.second[0]); vb.push_back(kv.second[1]); vc.push_back(kv.second[2]);
-            nnz++;
         }
     }
     pk->info = IndexInfo{nvar, cs.num_constraints(), nnz, cs.num_instance};
@@ -401,7 +422,6 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     const Domain& K = pk->dom_k;
     if (ahp_max_degree(pk->info.num_constraints, nvar, nnz) > srs.max_degree)
         throw MarlinError("index: circuit exceeds the universal SRS bound");
-    pk->a = cs.a; pk->b = cs.b; pk->c = cs.c;
     const std::vector<Fr> h_el = H.elements();
     // For entry k = (r, c): row_k = H[pos(c)] (the variable side, summed against z), col_k = H[r]
     // (the constraint side, paired with r(alpha, .)).  val_M(k) = M[r][c] / u_H(row_k, row_k) with
@@ -411,6 +431,7 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     pk->ent_col.resize(nnz);
     std::vector<Fr> row(K.n, h_el[0]), col(K.n, h_el[0]), vala(K.n, Fr::zero()), valb(K.n, Fr::zero()), valc(K.n, Fr::zero()),
         rowcol(K.n);
+#pragma omp parallel for schedule(static)
     for (size_t k = 0; k < nnz; k++) {
         const size_t pos = H.reindex_by_subdomain(pk->dom_x, ec[k]);
         pk->ent_row[k] = er[k];
@@ -420,6 +441,7 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
         const Fr scale = row[k] * H.size_inv;
         vala[k] = va[k] * scale; valb[k] = vb[k] * scale; valc[k] = vc[k] * scale;
     }
+#pragma omp parallel for schedule(static)
     for (size_t k = 0; k < K.n; k++) rowcol[k] = row[k] * col[k];
     pk->row_evals = eng.vfrom(row); pk->col_evals = eng.vfrom(col);
     pk->val_a_evals = eng.vfrom(vala); pk->val_b_evals = eng.vfrom(valb); pk->val_c_evals = eng.vfrom(valc);
@@ -442,6 +464,7 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
                     pk->t_row[at] = (uint32_t)r; pk->t_mat[at] = (uint8_t)m; pk->t_coef[at] = e.first;
                 }
     }
+    pk->a = std::move(cs.a); pk->b = std::move(cs.b); pk->c = std::move(cs.c);   // cs is this function's own copy
     {
         pk->eng = srs.eng;          // lives as long as the SRS, which the key references anyway (ck.srs)
         auto upload_rows = [&](const std::vector<SparseRow>& m) {

@@ -107,3 +107,23 @@ def test_vk_bytes_and_r1cs_interchange(gpu):
     cpk, cvk = CPU.index(csrs, ccs)
     assert CPU.prove(cpk, ccs, CPU.Rng()) == proof
     assert CPU.vk_serialize(cvk) == gpu.serialize_verifying_key(vk)
+
+
+def test_gpu_proofs_match_committed_fixtures(gpu):
+    """The GPU engine reproduces tests/golden/marlin_proofs.json (proof and verifying-key bytes of the toy
+    circuits under the fixed test_rng() seed) without the CPU arm in the loop."""
+    import hashlib
+    import json
+    import os
+    from simpleworks_b200.binding import ConstraintSystem, Rng
+    names = {"manual": "manual-constraints", "uint8_eq": "test-circuit", "chain": "mul-chain"}
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "marlin_proofs.json")))["cases"]
+    for tag, case in g.items():
+        rng = Rng()
+        srs = gpu.generate_universal_srs(*case["bounds"], rng)
+        a = case["args"]
+        cs = ConstraintSystem.builtin(names[case["kind"]], a.get("size", 0), a["v0"], a["v1"])
+        pk, vk = gpu.generate_proving_and_verifying_keys(srs, cs)
+        proof = gpu.generate_proof(cs, pk, rng)
+        assert hashlib.sha256(proof).hexdigest() == case["proof_sha256"], tag
+        assert hashlib.sha256(gpu.serialize_verifying_key(vk)).hexdigest() == case["vk_sha256"], tag

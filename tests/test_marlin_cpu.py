@@ -138,3 +138,20 @@ def test_verifying_key_and_r1cs_round_trip(toy_srs):
     assert M.prove(pk2, cs2, M.Rng()) == proof
     with pytest.raises(M.MarlinError):
         M.R1cs.from_bytes(blob[:-1])
+
+
+def test_proof_and_vk_bytes_match_committed_fixtures(golden_dir):
+    """tests/golden/marlin_proofs.json (made by make_marlin_golden.py): the CPU arm keeps producing the
+    committed bytes -- a regression pin of the restatement across refactors, not an arkworks vector."""
+    import hashlib
+    g = json.load(open(os.path.join(golden_dir, "marlin_proofs.json")))["cases"]
+    assert len(g) >= 4
+    for tag, case in g.items():
+        rng = M.Rng()
+        srs = M.universal_setup(*case["bounds"], rng)
+        cs = M.R1cs(case["kind"], **case["args"])
+        pk, vk = M.index(srs, cs)
+        proof = M.prove(pk, cs, rng)
+        assert len(proof) == case["proof_len"], tag
+        assert hashlib.sha256(proof).hexdigest() == case["proof_sha256"], tag
+        assert hashlib.sha256(M.vk_serialize(vk)).hexdigest() == case["vk_sha256"], tag
