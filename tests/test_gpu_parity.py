@@ -267,6 +267,37 @@ def test_msm_window_tables_skew_and_identity(be, srs_points):
     bases.free()
 
 
+@pytest.mark.parametrize("tables", [False, True])
+def test_msm_repeated_negated_and_infinite_bases(be, srs_points, tables):
+    """Bases repeated (P + P inside a bucket needs a doubling), negated (P - P cancels), at infinity, odd
+    lengths and position ranges cut mid-run, on the plain path and with window tables."""
+    n = 6001
+    pts = srs_points[:n].copy()
+    ref = O.points_from_affine(pts[:4])
+    neg0 = O.affine_from_points([(ref[0][0], G.Q_MOD - ref[0][1])])[0]
+    for i in range(40, 80):
+        pts[i] = pts[0]                                  # many copies of P ...
+    for i in range(80, 100):
+        pts[i] = neg0                                    # ... and of -P
+    pts[100] = O.affine_from_points([None])[0]
+    pts[101] = O.affine_from_points([None])[0]
+    scalars = _rand_fr(n, 4242)
+    scalars[40:100] = scalars[0]                         # same digits => same buckets, adjacent after the sort
+    scalars[100:103] = scalars[0]
+    scalars[200:1200] = scalars[200]                     # one long run per window
+    want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(pts), scalars))
+    bases = be.load_bases(pts)
+    if tables:
+        bases.precompute(9)
+    try:
+        assert np.array_equal(O.g1_to_affine(be.msm(bases, scalars)), want)
+        for m in (1, 2, 3, 17, 4097):
+            w = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(pts[:m]), scalars[:m]))
+            assert np.array_equal(O.g1_to_affine(be.msm(bases, np.ascontiguousarray(scalars[:m]))), w), m
+    finally:
+        bases.free()
+
+
 def test_fixed_base_powers_vs_oracle(be):
     g = O.g1_mul(O.g1_generator(), 5)
     beta = O.fr_mont([0xDEADBEEFCAFEBABE1234])
