@@ -55,6 +55,7 @@ struct CpuEngine : HostVecOps {
         }
     }
     void free_bases(void* h) { delete static_cast<CpuBases*>(h); }
+    void bases_tune(void*, size_t) {}     // nothing to restructure on the CPU arm
     G1Point msm(void* h, size_t offset, const Vec& scalars, size_t n) {
         const Fr* scalars_mont = scalars.data();
         auto* b = static_cast<CpuBases*>(h);

@@ -376,6 +376,10 @@ class Marlin:
     def srs_max_degree(self, srs) -> int:
         return int(self._lib.swb_srs_max_degree(srs))
 
+    def srs_set_tune_after(self, srs, n_msms: int):
+        """After n_msms commit/open MSMs the SRS powers get window tables (0 = never, 1 = at once)."""
+        self.be._check(self._lib.swb_srs_set_tune_after(srs, n_msms))
+
     def generate_proving_and_verifying_keys(self, srs, cs: ConstraintSystem):
         pk, vk = ctypes.c_void_p(), ctypes.c_void_p()
         self.be._check(self._lib.swb_marlin_index(self.be._h, srs, cs._h, ctypes.byref(pk), ctypes.byref(vk)))

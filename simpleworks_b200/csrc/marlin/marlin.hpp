@@ -20,6 +20,7 @@
 //     void* bases_from_powers(const G1Point& g, const Fr& beta, size_t n);     // resident beta^i * g
 //     void  export_bases(void* h, size_t offset, size_t n, G1Point* out);
 //     void  free_bases(void* h);
+//     void  bases_tune(void* h, size_t typical_n);   // optional restructuring for MSMs of about typical_n scalars
 //     G1Point msm(void* h, size_t offset, const Vec& scalars_mont, size_t n);  // sum s_i * base[offset+i]
 //   };
 //
@@ -70,6 +71,18 @@ struct UniversalSrs {
     std::vector<G1Point> powers_of_gamma_g;   // beta^i * gamma_g, i <= hiding_bound + 1 (the only ones trim keeps)
     G1Point g, gamma_g;
     G2Point h, beta_h;                        // verifier side (the trapdoor beta itself is dropped after setup)
+    // commit/open traffic over powers_of_g; once an SRS has served a proof's worth of MSMs the engine
+    // may restructure the bases for them (window tables on the CUDA engine), see kzg_msm
+    mutable size_t msm_calls = 0, msm_points = 0;
+    mutable bool tuned = false;
+    // number of MSMs after which the engine tunes the bases (0 = never).  Default 24 = one index + one
+    // proof: a one-shot setup/index/prove never pays for it, a prover that keeps going gets the faster
+    // path from its second proof on.  SWB_MARLIN_TABLES overrides the default, swb_srs_set_tune_after
+    // one SRS.
+    long tune_after = [] {
+        const char* e = getenv("SWB_MARLIN_TABLES");
+        return e ? atol(e) : 24L;
+    }();
     ~UniversalSrs() {
         if (eng && powers_of_g) eng->free_bases(powers_of_g);
     }
@@ -111,8 +124,16 @@ G1Point kzg_msm(const CommitterKey<Engine>& ck, size_t offset, const typename En
     const size_t n = ck.srs->eng->vlen(p);
     if (n == 0) return G1Point::identity();
     if (offset + n > ck.srs->max_degree + 1) throw MarlinError("polynomial degree exceeds the SRS");
+    const UniversalSrs<Engine>& srs = *ck.srs;
+    if (!srs.tuned && srs.tune_after > 0 && (long)srs.msm_calls >= srs.tune_after) {
+        srs.tuned = true;
+        ScopedPhase ph("bases_tune");
+        srs.eng->bases_tune(srs.powers_of_g, srs.msm_points / srs.msm_calls);
+    }
+    srs.msm_calls++;
+    srs.msm_points += n;
     ScopedPhase ph("msm");
-    return ck.srs->eng->msm(ck.srs->powers_of_g, offset, p, n);
+    return srs.eng->msm(srs.powers_of_g, offset, p, n);
 }
 inline G1Point gamma_msm(const std::vector<G1Point>& gamma, const Poly& blind) {
     G1Xyzz acc = G1Xyzz::identity();
