@@ -113,7 +113,7 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
     {
         const size_t segs = (size_t)nwin * (pl.B / msm_reduce_seg_len((uint32_t)nwin, pl.B));
         bf.seg = (G1Xyzz*)get_scratch(c, "msm_seg", (2 * segs + 2) * sizeof(G1Xyzz));
-        bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", (2 * (segs / MSM_GROUP_MIN + nwin) + 2) * sizeof(G1Xyzz));
+        bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", ((size_t)nwin * 24 * 33 + 2) * sizeof(G1Xyzz));   // [sets][jobs][blocks + 1]
     }
     bf.wins = (G1Xyzz*)get_scratch(c, "msm_wins", (size_t)MSM_MAX_WINDOWS * sizeof(G1Xyzz));
     if (!bf.keys || !bf.vals || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||

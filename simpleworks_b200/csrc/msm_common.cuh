@@ -7,17 +7,17 @@ namespace swb {
 
 constexpr int MSM_MAX_WINDOWS = 128;
 constexpr int MSM_RED_THREADS = 256;   // block size of the heavy-bucket gather
-constexpr int MSM_SEG_LEN = 32;        // segment / group length of the multi-level bucket reduction
+constexpr int MSM_SEG_LEN = 32;        // longest segment of the bucket reduction's running-sum level
 constexpr int MSM_GATHER_INLINE = 32;  // buckets with more partial sums than this go to the block-wide path
 
-constexpr int MSM_GROUP_MIN = 4;       // smallest segment / group length (used while a level has few threads)
+constexpr int MSM_SEG_MIN = 4;         // shortest segment (used while there are few segments)
 
-// Segment length of level 0 of the bucket reduction: every thread walks its segment serially (two
-// additions per bucket, ~10 us each for a lone thread), so short segments while there are too few of
-// them to fill the GPU, MSM_SEG_LEN once there are plenty.
+// Segment length of the running-sum level of the bucket reduction: every thread walks its segment
+// serially (two additions per bucket, 15-25 us each for a lone thread), so short segments while there
+// are too few of them to fill the GPU, MSM_SEG_LEN once there are plenty.
 inline uint32_t msm_reduce_seg_len(uint32_t nwin, uint32_t B) {
     uint32_t L = B < (uint32_t)MSM_SEG_LEN ? B : (uint32_t)MSM_SEG_LEN;
-    while (L > (uint32_t)MSM_GROUP_MIN && (size_t)nwin * (B / L) < 32768) L >>= 1;
+    while (L > (uint32_t)MSM_SEG_MIN && (size_t)nwin * (B / L) < 32768) L >>= 1;
     return L;
 }
 
@@ -49,8 +49,8 @@ struct MsmBuffers {
     uint32_t* heavy;     // [1 + nb] counter + list of buckets with many partial sums
     G1Xyzz* partial;     // [pcap]
     G1Xyzz* buckets;     // [nb]
-    G1Xyzz* seg;         // [2][nwin * B / MSM_SEG_LEN]  level-0 (C, S) of the bucket reduction
-    G1Xyzz* seg2;        // ping-pong partner for the upper levels
+    G1Xyzz* seg;         // [2][nwin * B / L]  per-segment weighted and plain sums of the bucket reduction
+    G1Xyzz* seg2;        // per-job partial sums and values of the bucket reduction
     G1Xyzz* wins;        // [MSM_MAX_WINDOWS]
 };
 

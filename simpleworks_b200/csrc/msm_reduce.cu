@@ -65,16 +65,19 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_gather_heavy(G1Xyzz* __
     }
 }
 
-// ---- 5. window sums: R_w = sum_{k=1..B} k * B_k, as a multi-level segmented reduction -------------
-// Level 0 cuts the B buckets of a window into segments of L: S_s = sum B, C_s = sum (j_local+1) B.
-// Then R = sum_s C_s + L * sum_s s * S_s, which has the same shape one level up: grouping G
-// consecutive segments, S'_g = sum_j S_{gG+j},  C'_g = sum_j C_{gG+j} + M * sum_j j * S_{gG+j}  with
-// M the product of the segment lengths below (a power of two: M * x is log2(M) doublings), and
-// R = sum_g C'_g + (M G) * sum_g g * S'_g.  Every level is one thread per group; the last level
-// leaves R in C_0.  Bucket counts up to 2^22 per window stay parallel this way.
-__global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_c, G1Xyzz* __restrict__ seg_s,
+// ---- 5. bucket-set sums: R_w = sum_{k=1..B} k * B_k ------------------------------------------------
+// Level 0 cuts the B buckets of a set into m = B / L segments: P_s = sum of the segment's buckets,
+// W_s = sum (j_local + 1) B (running sums, one thread per segment), so that
+//     R = sum_s W_s + L * sum_s s * P_s.
+// The second term is taken bit by bit of the segment index: sum_s s P_s = sum_b 2^b T_b with
+// T_b = sum of P_s over the segments whose index has bit b set -- plain sums, which reduce as parallel
+// trees instead of serial running sums (a lone thread needs ~10 us per XYZZ addition, and a chain of
+// levels of running sums cost 2-3 ms whatever the size).  k_msm_bit_sums: job 0 = sum W_s, job 1 + b =
+// T_b, a few blocks per job; k_msm_bit_tree: the blocks' partial results of one job, then 2^b L by
+// doublings; k_msm_bit_final: the jobs of one set.
+__global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_w, G1Xyzz* __restrict__ seg_p,
                                                        const G1Xyzz* __restrict__ buckets, uint32_t L, uint32_t nseg_total) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // global segment id (window-major); B is a multiple of L
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // global segment id (set-major); B is a multiple of L
     if (g >= nseg_total) return;
     const G1Xyzz* base = buckets + (size_t)g * L;
     G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
@@ -82,29 +85,70 @@ __global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_c
         running.add(base[j]);
         acc.add(running);
     }
-    seg_s[g] = running;
-    seg_c[g] = acc;
+    seg_p[g] = running;
+    seg_w[g] = acc;
 }
 
-__global__ void __launch_bounds__(128) k_msm_reduce_level(G1Xyzz* __restrict__ out_c, G1Xyzz* __restrict__ out_s,
-                                                           const G1Xyzz* __restrict__ in_c, const G1Xyzz* __restrict__ in_s,
-                                                           uint32_t m, uint32_t m_out, uint32_t G, uint32_t log_M, uint32_t nwin) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m_out * nwin) return;
-    const uint32_t w = t / m_out, g = t % m_out;
-    const size_t base = (size_t)w * m + (size_t)g * G;
-    const uint32_t cnt = (g + 1) * G <= m ? G : m - g * G;
-    G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity(), csum = G1Xyzz::identity();
-    for (uint32_t j = cnt; j-- > 1;) {                     // sum_j j * S_j as a running sum
-        running.add(in_s[base + j]);
-        acc.add(running);
+__global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_bit_sums(G1Xyzz* __restrict__ out, const G1Xyzz* __restrict__ seg_w,
+                                                                   const G1Xyzz* __restrict__ seg_p, uint32_t m, uint32_t per) {
+    extern __shared__ unsigned char smem_raw[];
+    G1Xyzz* buf = reinterpret_cast<G1Xyzz*>(smem_raw);
+    const uint32_t t = threadIdx.x, blk = blockIdx.x, job = blockIdx.y, w = blockIdx.z;
+    const uint32_t lo = blk * per, hi = lo + per < m ? lo + per : m;
+    const G1Xyzz* src = (job == 0 ? seg_w : seg_p) + (size_t)w * m;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t s = lo + t; s < hi; s += MSM_RED_THREADS)
+        if (job == 0 || ((s >> (job - 1)) & 1u)) acc.add(src[s]);
+    buf[t] = acc;
+    __syncthreads();
+    for (uint32_t d = MSM_RED_THREADS >> 1; d > 0; d >>= 1) {
+        if (t < d) {
+            G1Xyzz a = buf[t];
+            a.add(buf[t + d]);
+            buf[t] = a;
+        }
+        __syncthreads();
     }
-    running.add(in_s[base]);
-    for (uint32_t j = 0; j < cnt; j++) csum.add(in_c[base + j]);
-    for (uint32_t i = 0; i < log_M; i++) acc = acc.dbl();
-    csum.add(acc);
-    out_s[(size_t)w * m_out + g] = running;
-    out_c[(size_t)w * m_out + g] = csum;
+    if (t == 0) out[((size_t)w * gridDim.y + job) * gridDim.x + blk] = buf[0];
+}
+
+// one warp per (job, set): sum the bpj partial results, then weight job 1 + b by 2^b * L
+__global__ void __launch_bounds__(32) k_msm_bit_tree(G1Xyzz* __restrict__ val, const G1Xyzz* __restrict__ part, uint32_t bpj,
+                                                      uint32_t log_L) {
+    __shared__ G1Xyzz buf[32];
+    const uint32_t i = threadIdx.x, job = blockIdx.x, w = blockIdx.y, njobs = gridDim.x;
+    buf[i] = i < bpj ? part[((size_t)w * njobs + job) * bpj + i] : G1Xyzz::identity();
+    __syncwarp();
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        if (i < d) {
+            G1Xyzz a = buf[i];
+            a.add(buf[i + d]);
+            buf[i] = a;
+        }
+        __syncwarp();
+    }
+    if (i == 0) {
+        G1Xyzz x = buf[0];
+        if (job > 0)
+            for (uint32_t k = 0; k < job - 1 + log_L; k++) x = x.dbl();
+        val[(size_t)w * njobs + job] = x;
+    }
+}
+// one warp per set: sum its (at most 32) weighted job values
+__global__ void __launch_bounds__(32) k_msm_bit_final(G1Xyzz* __restrict__ wins, const G1Xyzz* __restrict__ val, uint32_t njobs) {
+    __shared__ G1Xyzz buf[32];
+    const uint32_t i = threadIdx.x, w = blockIdx.x;
+    buf[i] = i < njobs ? val[(size_t)w * njobs + i] : G1Xyzz::identity();
+    __syncwarp();
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        if (i < d) {
+            G1Xyzz a = buf[i];
+            a.add(buf[i + d]);
+            buf[i] = a;
+        }
+        __syncwarp();
+    }
+    if (i == 0) wins[w] = buf[0];
 }
 
 int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
@@ -122,32 +166,29 @@ int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
 int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     const uint32_t B = pl.B, nwin = (uint32_t)pl.nwin;
     const uint32_t L = msm_reduce_seg_len(nwin, B);
-    uint32_t log_M = 0;
-    while ((1u << log_M) < L) log_M++;
-    uint32_t m = B / L;                                   // segments per window
-    G1Xyzz *cur_c = bf.seg, *cur_s = bf.seg + (size_t)nwin * m;
-    G1Xyzz *alt_c = bf.seg2, *alt_s = nullptr;
-    k_msm_segments<<<(nwin * m + 127) / 128, 128, 0, c->stream>>>(cur_c, cur_s, bf.buckets, L, nwin * m);
+    uint32_t log_L = 0;
+    while ((1u << log_L) < L) log_L++;
+    const uint32_t m = B / L;                             // segments per set (a power of two)
+    uint32_t nbits = 0;
+    while ((1u << nbits) < m) nbits++;
+    const uint32_t njobs = 1 + nbits;                     // <= 1 + 22
+    G1Xyzz *seg_w = bf.seg, *seg_p = bf.seg + (size_t)nwin * m;
+    k_msm_segments<<<(nwin * m + 127) / 128, 128, 0, c->stream>>>(seg_w, seg_p, bf.buckets, L, nwin * m);
     SWB_LAUNCH_CHECK(c, "k_msm_segments");
-    while (m > 1) {
-        // a group costs its thread ~3 G serial additions: short groups while the level has few threads
-        uint32_t G = MSM_SEG_LEN;
-        while (G > (uint32_t)MSM_GROUP_MIN && (size_t)nwin * ((m + G - 1) / G) < 8192) G >>= 1;
-        uint32_t log_G = 0;
-        while ((1u << log_G) < G) log_G++;
-        const uint32_t m_out = (m + G - 1) / G;
-        alt_s = alt_c + (size_t)nwin * m_out;
-        k_msm_reduce_level<<<(nwin * m_out + 127) / 128, 128, 0, c->stream>>>(alt_c, alt_s, cur_c, cur_s, m, m_out, G, log_M, nwin);
-        SWB_LAUNCH_CHECK(c, "k_msm_reduce_level");
-        G1Xyzz* old = cur_c;                              // ping-pong: the old input region is free again
-        cur_c = alt_c;
-        cur_s = alt_s;
-        alt_c = old;
-        m = m_out;
-        log_M += log_G;
-    }
-    // m == 1: window w's result is cur_c[w]
-    SWB_CUDA(c, cudaMemcpyAsync(bf.wins, cur_c, sizeof(G1Xyzz) * nwin, cudaMemcpyDeviceToDevice, c->stream));
+    // a few blocks per job so that no thread adds more than ~8 segments serially
+    uint32_t bpj = 1;
+    while (bpj < 32 && (size_t)bpj * MSM_RED_THREADS * 8 < m) bpj <<= 1;
+    const uint32_t per = (m + bpj - 1) / bpj;
+    G1Xyzz* part = bf.seg2;                               // [nwin][njobs][bpj], then [nwin][njobs] values
+    G1Xyzz* val = part + (size_t)nwin * njobs * bpj;
+    const size_t smem = MSM_RED_THREADS * sizeof(G1Xyzz);
+    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_bit_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_msm_bit_sums<<<dim3(bpj, njobs, nwin), MSM_RED_THREADS, smem, c->stream>>>(part, seg_w, seg_p, m, per);
+    SWB_LAUNCH_CHECK(c, "k_msm_bit_sums");
+    k_msm_bit_tree<<<dim3(njobs, nwin), 32, 0, c->stream>>>(val, part, bpj, log_L);
+    SWB_LAUNCH_CHECK(c, "k_msm_bit_tree");
+    k_msm_bit_final<<<nwin, 32, 0, c->stream>>>(bf.wins, val, njobs);
+    SWB_LAUNCH_CHECK(c, "k_msm_bit_final");
     return SWB_OK;
 }
 
