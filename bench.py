@@ -106,6 +106,26 @@ def synth_scalars_host(n: int, seed: int) -> np.ndarray:
     return a
 
 
+def marlin_gpu_run(be, lg, proofs):
+    """setup / index / `proofs` proofs / verify of the 2^lg - 2 constraint mul-chain circuit on this GPU"""
+    from simpleworks_b200 import _gen
+    from simpleworks_b200.binding import ConstraintSystem, Marlin, Rng
+    m = Marlin(be)
+    n = (1 << lg) - 2
+    rng = Rng()
+    t0 = time.perf_counter(); srs = m.generate_universal_srs(1 << lg, 1 << lg, 3 << lg, rng); t1 = time.perf_counter()
+    cs = ConstraintSystem.builtin("mul-chain", n, 3, 5)
+    t2 = time.perf_counter(); pk, vk = m.generate_proving_and_verifying_keys(srs, cs); t3 = time.perf_counter()
+    ts, proof = [], None
+    for _ in range(proofs):
+        ta = time.perf_counter(); proof = m.generate_proof(cs, pk, Rng()); ts.append(time.perf_counter() - ta)
+    tv = time.perf_counter(); ok = m.verify_proof(vk, _gen.fr_mont(3), proof); tv = time.perf_counter() - tv
+    return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t3 - t2, "prove_s": min(ts), "prove_s_all": ts,
+            "prove_s_note": "the 2nd proof includes the one-off window tables over the SRS powers "
+                            "(swb_srs_set_tune_after, default: after one index + one proof)",
+            "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts), "proof_bytes": len(proof)}, proof
+
+
 def marlin_extra(be, args) -> dict:
     """End-to-end Marlin (BASELINE configs[3]): synthetic mul-chain R1CS, setup / index / prove /
     verify through the protocol-level C ABI on this GPU; the CPU arm (same protocol source on the
@@ -114,23 +134,10 @@ def marlin_extra(be, args) -> dict:
     from oracle import pymarlin as C
     from simpleworks_b200 import _gen
     from simpleworks_b200.binding import ConstraintSystem, Marlin, Rng
-    m = Marlin(be)
     out = {"circuit": "mul-chain x_i*x_{i+1}=x_{i+2}, 1 public input", "verifier": "pairing check on the host (BLS12-377 ate pairing)"}
 
     def gpu_run(lg, proofs):
-        n = (1 << lg) - 2
-        rng = Rng()
-        t0 = time.perf_counter(); srs = m.generate_universal_srs(1 << lg, 1 << lg, 3 << lg, rng); t1 = time.perf_counter()
-        cs = ConstraintSystem.builtin("mul-chain", n, 3, 5)
-        t2 = time.perf_counter(); pk, vk = m.generate_proving_and_verifying_keys(srs, cs); t3 = time.perf_counter()
-        ts, proof = [], None
-        for _ in range(proofs):
-            ta = time.perf_counter(); proof = m.generate_proof(cs, pk, Rng()); ts.append(time.perf_counter() - ta)
-        tv = time.perf_counter(); ok = m.verify_proof(vk, _gen.fr_mont(3), proof); tv = time.perf_counter() - tv
-        return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t3 - t2, "prove_s": min(ts), "prove_s_all": ts,
-                "prove_s_note": "the 2nd proof includes the one-off window tables over the SRS powers "
-                                "(swb_srs_set_tune_after, default: after one index + one proof)",
-                "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts), "proof_bytes": len(proof)}, proof
+        return marlin_gpu_run(be, lg, proofs)
 
     big, _ = gpu_run(args.marlin_log_n, 4)
     out["gpu"] = big
@@ -413,6 +420,17 @@ def main():
                 extra["marlin"] = marlin_extra(be, args)
             except Exception as e:     # the headline must not die with the side measurement
                 extra["marlin"] = {"error": repr(e)}
+        else:
+            # whole proofs are independent: one prover per GPU (SURVEY 8e "replicas"), slowest rank counts
+            try:
+                bases.free()
+                r, _ = marlin_gpu_run(be, args.marlin_log_n, 4)
+                worst = torch.tensor([r["prove_s"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+                extra["marlin_replicas"] = {"log_constraints": args.marlin_log_n, "provers": world, "prove_s_max_over_ranks": float(worst.item()),
+                                            "proofs_per_s": world / float(worst.item()), "rank0": r}
+            except Exception as e:
+                extra["marlin_replicas"] = {"error": repr(e)}
 
     line = {
         "metric": "msm_g1_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
