@@ -210,6 +210,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if os.environ.get("SWB_BENCH_FAULT_S"):     # debugging aid: dump every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["SWB_BENCH_FAULT_S"]), exit=True)
 
     if args.impl == "reference":
         run_reference(args)
@@ -234,6 +237,12 @@ def main():
         dist.barrier()
     be = Backend(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    t_start = time.perf_counter()
+
+    def progress(msg):
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    progress(f"library loaded, world={world}")
 
     n_total = 1 << args.log_n
     assert n_total % world == 0
@@ -275,6 +284,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    progress(f"bases ready ({t_bases:.1f}s + tables {t_tables:.1f}s)")
     # ---- resident-input timing ("value") ------------------------------------------------------------
     be.profile(True)
     result = None
@@ -330,6 +340,23 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_total * args.steps / float(te.item())
 
+    # ---- N > 1: whole proofs are independent, so one Marlin prover per GPU (SURVEY 8e "replicas"); every
+    # rank takes part, the slowest one counts ------------------------------------------------------------
+    marlin_replicas = None
+    if world > 1 and not args.no_extra:
+        r, mine, err = None, float("inf"), None
+        try:
+            bases.free()
+            r, _ = marlin_gpu_run(be, args.marlin_log_n, 4)
+            mine = r["prove_s"]
+        except Exception as e:     # every rank still joins the collective below
+            err = repr(e)
+        worst = torch.tensor([mine], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        w = float(worst.item())
+        marlin_replicas = {"log_constraints": args.marlin_log_n, "provers": world, "prove_s_max_over_ranks": w,
+                           "proofs_per_s": world / w if w < float("inf") else 0.0, "rank0": r, "error": err}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -370,6 +397,7 @@ def main():
                 "note": "128 B/point algorithmic over the whole step; sanity counter only"},
     }
 
+    progress("timed regions done")
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -412,6 +440,7 @@ def main():
             "hbm_gbs_algorithmic": 64.0 * nn / ms / 1e6, "hbm_frac": 64.0 * nn / ms / 1e6 / hbm_peak,
             "limb_products_per_s": (nn / 2) * log_ntt * 128 / ms * 1e3,
             "int_frac": (nn / 2) * log_ntt * 128 / ms * 1e3 / imad_wide, "passes": be.last_stages()}
+        progress("ntt extra done")
         extra["setup_bases_s"] = t_bases
         extra["setup_tables_s"] = t_tables
         extra["stages_ms_avg"] = {k: v / args.steps for k, v in stage_sum.items()}
@@ -420,17 +449,8 @@ def main():
                 extra["marlin"] = marlin_extra(be, args)
             except Exception as e:     # the headline must not die with the side measurement
                 extra["marlin"] = {"error": repr(e)}
-        else:
-            # whole proofs are independent: one prover per GPU (SURVEY 8e "replicas"), slowest rank counts
-            try:
-                bases.free()
-                r, _ = marlin_gpu_run(be, args.marlin_log_n, 4)
-                worst = torch.tensor([r["prove_s"]], dtype=torch.float64, device=dev)
-                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-                extra["marlin_replicas"] = {"log_constraints": args.marlin_log_n, "provers": world, "prove_s_max_over_ranks": float(worst.item()),
-                                            "proofs_per_s": world / float(worst.item()), "rank0": r}
-            except Exception as e:
-                extra["marlin_replicas"] = {"error": repr(e)}
+        elif marlin_replicas is not None:
+            extra["marlin_replicas"] = marlin_replicas
 
     line = {
         "metric": "msm_g1_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
