@@ -178,7 +178,9 @@ void swb_rng_free(swb_rng*);
 
 swb_r1cs* swb_r1cs_new(size_t num_instance /* incl. the constant one */, size_t num_witness);
 /* built-in instances: 0 manual-constraints (v0 = a, v1 = b), 1 test-circuit UInt8 equality
- * (v0, v1), 2 synthetic chain x_i * x_{i+1} = x_{i+2} with `size` constraints (v0, v1 = seeds) */
+ * (v0, v1), 2 synthetic chain x_i * x_{i+1} = x_{i+2} with `size` constraints (v0, v1 = seeds),
+ * 3 synthetic general-shape instance: `size` constraints, v0 random terms per row of A and B (columns
+ * may repeat), 3 public inputs, seed v1 */
 swb_r1cs* swb_r1cs_builtin(int kind, size_t size, uint64_t v0, uint64_t v1);
 int  swb_r1cs_add_constraint(swb_r1cs*, const swb_fr* a_coef, const uint32_t* a_col, size_t na,
                              const swb_fr* b_coef, const uint32_t* b_col, size_t nb,

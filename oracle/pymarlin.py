@@ -88,12 +88,26 @@ def blake2s(data: bytes) -> bytes:
     return out.raw
 
 
+def random_sparse_public_inputs(seed: int) -> list:
+    """the three public inputs of R1cs('random_sparse', v1=seed): first draws of its xorshift generator"""
+    m = (1 << 64) - 1
+    st = (seed * 0x9E3779B97F4A7C15 + 0x1234567) & m
+    out = []
+    for _ in range(3):
+        st ^= (st << 13) & m
+        st ^= st >> 7
+        st ^= (st << 17) & m
+        out.append(st >> 8)
+    return out
+
+
 class R1cs:
     """kind: 'manual' (examples/manual-constraints.rs), 'uint8_eq' (examples/test-circuit.rs),
-    'chain' (synthetic x_i * x_{i+1} = x_{i+2})."""
+    'chain' (synthetic x_i * x_{i+1} = x_{i+2}), 'random_sparse' (size constraints, v0 terms per row, seed v1;
+    3 public inputs, see random_sparse_public_inputs)."""
 
     def __init__(self, kind: str, size: int = 0, v0: int = 1, v1: int = 1):
-        k = {"manual": 0, "uint8_eq": 1, "chain": 2}[kind]
+        k = {"manual": 0, "uint8_eq": 1, "chain": 2, "random_sparse": 3}[kind]
         self.h = ctypes.c_void_p(lib().orc_r1cs_builtin(k, size, v0, v1))
 
     def is_satisfied(self) -> bool:

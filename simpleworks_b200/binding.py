@@ -296,7 +296,7 @@ class ConstraintSystem:
     """What a ConstraintSystemRef exposes to Marlin (src/marlin/mod.rs:16): sparse A, B, C rows and
     the instance / witness assignments.  Columns: instance first (0 = constant one), then witness."""
 
-    BUILTIN = {"manual-constraints": 0, "test-circuit": 1, "mul-chain": 2}
+    BUILTIN = {"manual-constraints": 0, "test-circuit": 1, "mul-chain": 2, "random-sparse": 3}
 
     def __init__(self, handle):
         self._lib = _lib.load()

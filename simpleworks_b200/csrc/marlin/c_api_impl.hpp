@@ -74,6 +74,7 @@ inline R1csHandle* r1cs_builtin(int kind, size_t size, uint64_t v0, uint64_t v1)
         case 0: h->cs = circuit_manual_constraints(v0, v1); break;
         case 1: h->cs = circuit_uint8_equality((uint8_t)v0, (uint8_t)v1); break;
         case 2: h->cs = circuit_mul_chain(size, v0, v1); break;
+        case 3: h->cs = circuit_random_sparse(size, v0, v1); break;
         default: delete h; return nullptr;
     }
     return h;

@@ -140,6 +140,40 @@ inline R1cs circuit_mul_chain(size_t num_constraints, uint64_t seed0, uint64_t s
     return cs;
 }
 
+// synthetic general-shape instance (not in the reference: its real circuits need ark-r1cs-std): three
+// public inputs, `terms` random (coefficient, variable) pairs per row of A and of B -- columns may
+// repeat inside a row, as they can after gadget synthesis -- and one fresh witness per constraint holding
+// (A z)(B z), so the instance is satisfied by construction.  A xorshift generator keeps it deterministic.
+inline R1cs circuit_random_sparse(size_t num_constraints, uint64_t terms, uint64_t seed) {
+    R1cs cs;
+    cs.num_instance = 4;
+    cs.num_witness = num_constraints;
+    cs.a.resize(num_constraints); cs.b.resize(num_constraints); cs.c.resize(num_constraints);
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    std::vector<Fr> z = {Fr::one(), fr_from_u64(next() >> 8), fr_from_u64(next() >> 8), fr_from_u64(next() >> 8)};
+    if (terms == 0) terms = 1;
+    for (size_t i = 0; i < num_constraints; i++) {
+        Fr dot[2] = {Fr::zero(), Fr::zero()};
+        for (int side = 0; side < 2; side++) {
+            SparseRow& row = side ? cs.b[i] : cs.a[i];
+            for (uint64_t t = 0; t < terms; t++) {
+                const uint32_t col = (uint32_t)(next() % z.size());
+                Fr coef = fr_from_u64((next() >> 40) + 1);
+                if (next() & 1) coef = coef.neg();
+                row.e.push_back({coef, col});
+                dot[side] = dot[side] + coef * z[col];
+            }
+        }
+        cs.c[i].e = {{Fr::one(), (uint32_t)z.size()}};
+        z.push_back(dot[0] * dot[1]);
+    }
+    cs.instance.assign(z.begin(), z.begin() + 4);
+    cs.witness.assign(z.begin() + 4, z.end());
+    cs.has_assignment = true;
+    return cs;
+}
+
 }  // namespace marlin
 }  // namespace swb
 

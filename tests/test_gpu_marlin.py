@@ -149,3 +149,25 @@ def test_tuned_srs_gives_the_same_proofs(gpu):
         out.append((proof, gpu.serialize_verifying_key(vk)))
     assert out[0] == out[1]
     assert hashlib.sha256(out[1][0]).hexdigest() == case["proof_sha256"]
+
+
+@pytest.mark.parametrize("size,terms", [(300, 5), (5000, 3), (70000, 4)])
+def test_general_shape_circuit_gpu_equals_cpu(gpu, size, terms):
+    """Multi-term rows with repeated columns and three public inputs: the device-resident CSR products
+    (k_csr_spmv) and the index must give the CPU arm's bytes."""
+    from simpleworks_b200.binding import ConstraintSystem, Rng
+    bounds = (2 * size, 2 * size, 2 * terms * size + 2 * size)
+    rng = Rng()
+    srs = gpu.generate_universal_srs(*bounds, rng)
+    cs = ConstraintSystem.builtin("random-sparse", size, terms, 77)
+    assert cs.is_satisfied()
+    pk, vk = gpu.generate_proving_and_verifying_keys(srs, cs)
+    proof = gpu.generate_proof(cs, pk, rng)
+    pub = O.fr_mont(CPU.random_sparse_public_inputs(77))
+    assert gpu.verify_proof(vk, pub, proof)
+    crng = CPU.Rng()
+    csrs = CPU.universal_setup(*bounds, crng)
+    ccs = CPU.R1cs("random_sparse", size=size, v0=terms, v1=77)
+    cpk, cvk = CPU.index(csrs, ccs)
+    assert CPU.prove(cpk, ccs, crng) == proof
+    assert gpu.serialize_verifying_key(vk) == CPU.vk_serialize(cvk)

@@ -155,3 +155,20 @@ def test_proof_and_vk_bytes_match_committed_fixtures(golden_dir):
         assert len(proof) == case["proof_len"], tag
         assert hashlib.sha256(proof).hexdigest() == case["proof_sha256"], tag
         assert hashlib.sha256(M.vk_serialize(vk)).hexdigest() == case["vk_sha256"], tag
+
+
+def test_general_shape_circuit_prove_verify():
+    """Rows with several terms, repeated columns and three public inputs (the shape gadget synthesis
+    produces; the toy circuits above have one term per row)."""
+    rng = M.Rng()
+    srs = M.universal_setup(600, 600, 6000, rng)
+    cs = M.R1cs("random_sparse", size=300, v0=5, v1=77)
+    assert cs.is_satisfied()
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, rng)
+    pub = M.random_sparse_public_inputs(77)
+    assert M.verify(vk, O.fr_mont(pub), proof)
+    assert not M.verify(vk, O.fr_mont([pub[0], pub[1], pub[2] + 1]), proof)
+    # the SWBR1CS1 round trip keeps it provable
+    cs2 = M.R1cs.from_bytes(cs.to_bytes())
+    assert M.prove(pk, cs2, M.Rng()) == M.prove(pk, cs, M.Rng())
