@@ -122,6 +122,7 @@ struct MarlinApi {
             auto* p = new PkHandle<Engine>();
             auto* v = new VkHandle();
             marlin::index(eng, *srs->srs, cs->cs, &p->pk, &v->vk);
+            host_profile().report("index");
             *pk = p;
             *vk = v;
             return 0;

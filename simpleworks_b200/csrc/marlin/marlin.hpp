@@ -389,12 +389,15 @@ std::unique_ptr<UniversalSrs<Engine>> universal_setup(Engine& eng, size_t num_co
 
 template <class Engine>
 void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Engine>* pk, VerifyingKey* vk) {
+    ScopedPhase ph_total("total");
+    std::unique_ptr<ScopedPhase> ph(new ScopedPhase("i0_pad"));
     cs.pad_instance();
     cs.make_square();
     const size_t nvar = cs.num_variables();
     pk->dom_h = Domain(cs.num_constraints());
     pk->dom_x = Domain(cs.num_instance);
     const Domain& H = pk->dom_h;
+    ph.reset(); ph.reset(new ScopedPhase("i1_merge_rows"));
     // joint sparsity pattern, row by row, columns in increasing order; rows are independent, so
     // they are merged in parallel: pass 1 counts the distinct columns of each row, pass 2 fills
     struct Ent { uint32_t col; uint8_t which; Fr coef; };
@@ -443,6 +446,7 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     const Domain& K = pk->dom_k;
     if (ahp_max_degree(pk->info.num_constraints, nvar, nnz) > srs.max_degree)
         throw MarlinError("index: circuit exceeds the universal SRS bound");
+    ph.reset(); ph.reset(new ScopedPhase("i2_arith"));
     const std::vector<Fr> h_el = H.elements();
     // For entry k = (r, c): row_k = H[pos(c)] (the variable side, summed against z), col_k = H[r]
     // (the constraint side, paired with r(alpha, .)).  val_M(k) = M[r][c] / u_H(row_k, row_k) with
@@ -450,22 +454,30 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     //    sum_j z(j) t(j) = sum_r r(alpha, H[r]) (M z)(r)   for   t(X) = sum_k val(k) u_H(X,row_k) u_H(alpha,col_k).
     pk->ent_row.resize(nnz);
     pk->ent_col.resize(nnz);
-    std::vector<Fr> row(K.n, h_el[0]), col(K.n, h_el[0]), vala(K.n, Fr::zero()), valb(K.n, Fr::zero()), valc(K.n, Fr::zero()),
-        rowcol(K.n);
+    // six |K|-long evaluation vectors, filled in parallel (entries past nnz: row = col = H[0], val = 0);
+    // raw buffers, because std::vector would first value-initialise 0.8 GB on one core
+    std::unique_ptr<Fr[]> row(new Fr[K.n]), col(new Fr[K.n]), vala(new Fr[K.n]), valb(new Fr[K.n]), valc(new Fr[K.n]),
+        rowcol(new Fr[K.n]);
 #pragma omp parallel for schedule(static)
-    for (size_t k = 0; k < nnz; k++) {
-        const size_t pos = H.reindex_by_subdomain(pk->dom_x, ec[k]);
-        pk->ent_row[k] = er[k];
-        pk->ent_col[k] = (uint32_t)pos;
-        row[k] = h_el[pos];
-        col[k] = h_el[er[k]];
-        const Fr scale = row[k] * H.size_inv;
-        vala[k] = va[k] * scale; valb[k] = vb[k] * scale; valc[k] = vc[k] * scale;
+    for (size_t k = 0; k < K.n; k++) {
+        if (k >= nnz) {
+            row[k] = h_el[0]; col[k] = h_el[0];
+            vala[k] = Fr::zero(); valb[k] = Fr::zero(); valc[k] = Fr::zero();
+        } else {
+            const size_t pos = H.reindex_by_subdomain(pk->dom_x, ec[k]);
+            pk->ent_row[k] = er[k];
+            pk->ent_col[k] = (uint32_t)pos;
+            row[k] = h_el[pos];
+            col[k] = h_el[er[k]];
+            const Fr scale = row[k] * H.size_inv;
+            vala[k] = va[k] * scale; valb[k] = vb[k] * scale; valc[k] = vc[k] * scale;
+        }
+        rowcol[k] = row[k] * col[k];
     }
-#pragma omp parallel for schedule(static)
-    for (size_t k = 0; k < K.n; k++) rowcol[k] = row[k] * col[k];
-    pk->row_evals = eng.vfrom(row); pk->col_evals = eng.vfrom(col);
-    pk->val_a_evals = eng.vfrom(vala); pk->val_b_evals = eng.vfrom(valb); pk->val_c_evals = eng.vfrom(valc);
+    pk->row_evals = eng.vfrom_ptr(row.get(), K.n); pk->col_evals = eng.vfrom_ptr(col.get(), K.n);
+    pk->val_a_evals = eng.vfrom_ptr(vala.get(), K.n); pk->val_b_evals = eng.vfrom_ptr(valb.get(), K.n);
+    pk->val_c_evals = eng.vfrom_ptr(valc.get(), K.n);
+    ph.reset(); ph.reset(new ScopedPhase("i3_transpose"));
     {
         std::vector<uint32_t> pos_of(nvar), cnt(H.n + 1, 0);
         for (size_t v = 0; v < nvar; v++) pos_of[v] = (uint32_t)H.reindex_by_subdomain(pk->dom_x, v);
@@ -485,6 +497,7 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
                     pk->t_row[at] = (uint32_t)r; pk->t_mat[at] = (uint8_t)m; pk->t_coef[at] = e.first;
                 }
     }
+    ph.reset(); ph.reset(new ScopedPhase("i4_upload"));
     pk->a = std::move(cs.a); pk->b = std::move(cs.b); pk->c = std::move(cs.c);   // cs is this function's own copy
     {
         pk->eng = srs.eng;          // lives as long as the SRS, which the key references anyway (ck.srs)
@@ -503,8 +516,9 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
         pk->m_c = upload_rows(pk->c);
         pk->m_t = eng.csr_upload(pk->t_start, pk->t_row, pk->t_coef, &pk->t_mat);
     }
+    ph.reset(); ph.reset(new ScopedPhase("i5_polys_commit"));
     const char* names[6] = {"row", "col", "a_val", "b_val", "c_val", "row_col"};
-    typename Engine::Vec rowcol_v = eng.vfrom(rowcol);
+    typename Engine::Vec rowcol_v = eng.vfrom_ptr(rowcol.get(), K.n);
     const typename Engine::Vec* evs[6] = {&pk->row_evals, &pk->col_evals, &pk->val_a_evals, &pk->val_b_evals, &pk->val_c_evals, &rowcol_v};
     pk->index_polys.clear();
     for (int i = 0; i < 6; i++) {

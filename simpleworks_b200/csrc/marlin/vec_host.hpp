@@ -13,6 +13,7 @@ struct HostVecOps {
     using Vec = std::vector<Fr>;
     Vec vzeros(size_t n) { return Vec(n, Fr::zero()); }
     Vec vfrom(const std::vector<Fr>& h) { return h; }
+    Vec vfrom_ptr(const Fr* p, size_t n) { return Vec(p, p + n); }
     std::vector<Fr> vhost(const Vec& v) { return v; }
     Vec vclone(const Vec& v) { return v; }
     void vresize(Vec& v, size_t n) { v.resize(n, Fr::zero()); }

@@ -92,6 +92,15 @@ struct GpuEngine {
         }
         return v;
     }
+    Vec vfrom_ptr(const Fr* h, size_t n) {
+        OpTimer ot_(c, "vfrom");
+        Vec v = alloc(n);
+        if (n) {
+            cu(cudaMemcpyAsync(v.p, h, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream), "H2D");
+            cu(cudaStreamSynchronize(c->stream), "sync");     // the caller may free h
+        }
+        return v;
+    }
     std::vector<Fr> vhost(const Vec& v) {
         OpTimer ot_(c, "vhost");
         std::vector<Fr> h(v.n);
