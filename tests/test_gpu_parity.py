@@ -298,6 +298,66 @@ def test_msm_repeated_negated_and_infinite_bases(be, srs_points, tables):
         bases.free()
 
 
+def test_msm_randomised_shapes_vs_oracle(be, srs_points):
+    """40 seeded random cases: size, offset, forced window width, window tables or not, and a mix of scalar
+    kinds (0, 1, r - 1, small, top-heavy, uniform) -- each against the oracle's Pippenger."""
+    rs = np.random.RandomState(20261017)
+    special = [0, 1, 2, G.R_MOD - 1, G.R_MOD - 2, (G.R_MOD - 1) // 2, (G.R_MOD + 1) // 2, (1 << 252), (1 << 252) - 1, 1 << 128]
+    for case in range(40):
+        n = int(rs.choice([1, 2, 3, 5, 16, 17, 100, 255, 256, 257, 1000, 4095, 4096, 4097, 9000]))
+        off = int(rs.randint(0, 200))
+        scalars = _rand_fr(n, 5000 + case)
+        kind = rs.randint(0, 6, size=n)
+        scalars[kind == 0] = 0
+        for i in np.nonzero(kind == 1)[0]:
+            scalars[i] = O.ints_to_limbs([special[int(rs.randint(len(special)))]], 4)[0]
+        scalars[kind == 2, 1:] = 0                                   # 64-bit scalars
+        scalars[kind == 3, :3] = 0                                   # only the top limb
+        pts = np.ascontiguousarray(srs_points[off:off + n])
+        want = O.g1_to_affine(O.msm_variable_base(pts, scalars))
+        tables = bool(rs.randint(2))
+        bases = be.load_bases(srs_points[:off + n + 7])
+        try:
+            if tables:
+                bases.precompute(int(rs.choice([0, 8, 9, 11, 13])))
+            else:
+                be.set_msm_window_bits(int(rs.choice([0, 2, 3, 5, 8, 11, 14])))
+            got = O.g1_to_affine(be.msm(bases, scalars, offset=off))
+            assert np.array_equal(got, want), (case, n, off, tables)
+        finally:
+            be.set_msm_window_bits(0)
+            bases.free()
+
+
+def test_ntt_randomised_round_trips_and_linearity(be):
+    """Seeded random sizes and modes: inverse(forward(x)) == x in all four (inverse, coset) pairings,
+    forward is linear, and a random subset of outputs equals the direct evaluation x(w^i) / x(g w^i)."""
+    import torch
+    rs = np.random.RandomState(7)
+    for case in range(12):
+        log_n = int(rs.randint(1, 21))
+        n = 1 << log_n
+        x = _rand_fr(n, 9000 + case)
+        dx = be.to_device(x)
+        coset = bool(rs.randint(2))
+        y = be.ntt_(dx.clone(), log_n, coset=coset)
+        assert torch.equal(be.ntt_(y.clone(), log_n, inverse=True, coset=coset), dx), (log_n, coset)
+        x2 = _rand_fr(n, 9100 + case)
+        lhs = be.ntt_(be.fr_add(dx, be.to_device(x2)), log_n, coset=coset)
+        assert torch.equal(lhs, be.fr_add(y, be.ntt_(be.to_device(x2), log_n, coset=coset)))
+        if log_n <= 12:                                             # direct evaluation with python ints
+            w = G.domain_gen(log_n)
+            xs = O.fr_unmont(x)
+            ys = O.fr_unmont(be.to_host(y))
+            shift = G.FR_GENERATOR if coset else 1
+            for i in rs.choice(n, min(n, 4), replace=False):
+                pt = shift * pow(w, int(i), G.R_MOD) % G.R_MOD
+                acc = 0
+                for c in reversed(xs):
+                    acc = (acc * pt + c) % G.R_MOD
+                assert ys[int(i)] == acc, (log_n, coset, i)
+
+
 def test_fixed_base_powers_vs_oracle(be):
     g = O.g1_mul(O.g1_generator(), 5)
     beta = O.fr_mont([0xDEADBEEFCAFEBABE1234])
