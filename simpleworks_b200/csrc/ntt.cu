@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
                                                            const Fr* __restrict__ tw_coset) {
     extern __shared__ uint4 smem[];
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t, tile = R * T;
-    // final mode keeps the tile row-major [t][j] with rows padded by one element: the transposing
-    // store walks t fastest, and a stride of (R+1) 16-byte words spreads it over the banks
-    const uint32_t row = p.mode == 0 ? 0u : R + 1u;
-    const uint32_t planes = p.mode == 0 ? tile : row * T;
+    // the tile is [j][t] in both modes (t fastest: butterflies and stores touch consecutive words).
+    // Final mode loads rows of consecutive j, i.e. it writes the tile with stride Tp between lanes:
+    // Tp = T + 1 is odd in 16-byte words, which spreads those stores over the banks.
+    const uint32_t Tp = p.mode == 0 ? T : T + 1u;
+    const uint32_t planes = R * Tp;
     Tile tl{smem, smem + planes};
     const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
     Fr* out = p.out + (size_t)blockIdx.y * p.batch_stride;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
     for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
         uint32_t j, t, e;
         if (p.mode == 0) { t = idx & (T - 1); j = idx >> p.log_t; e = idx; }
-        else { j = idx & (R - 1); t = idx >> p.log_r; e = t * row + j; }  // final mode tile is [t][j], padded rows
+        else { j = idx & (R - 1); t = idx >> p.log_r; e = j * Tp + t; }   // global runs along j, tile along t
         const size_t gi = in_base + (size_t)j * in_j_stride + (size_t)t * in_t_stride;
         Fr v = ld_fr(in + gi);
         if (p.pre_coset) v = v * tw_lookup(tw_coset, (uint32_t)gi);
@@ -132,15 +133,15 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
     __syncthreads();
 
     // ---- R-point DIF network along j ----------------------------------------------------------
-    // element (j,t) sits at j*T+t (column mode) or t*R+j (final mode)
-    const uint32_t js = p.mode == 0 ? T : 1u, ts = p.mode == 0 ? 1u : row;
+    // element (j,t) sits at j*Tp + t
+    const uint32_t js = Tp, ts = 1u;
     const uint32_t nbf = tile >> 1;
     for (uint32_t s = 0; s < p.log_r; s++) {
         const uint32_t log_half = p.log_r - 1 - s, half = 1u << log_half;
         for (uint32_t idx = tid; idx < nbf; idx += NTT_THREADS) {
             uint32_t b, t;
-            if (p.mode == 0) { t = idx & (T - 1); b = idx >> p.log_t; }
-            else { b = idx & ((R >> 1) - 1); t = idx >> (p.log_r - 1); }
+            t = idx & (T - 1);
+            b = idx >> p.log_t;
             const uint32_t pos = b & (half - 1), grp = b >> log_half;
             const uint32_t j0 = (grp << (log_half + 1)) + pos;
             const uint32_t e0 = j0 * js + t * ts, e1 = e0 + half * js;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
     } else {
         for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
             const uint32_t t = idx & (T - 1), k = idx >> p.log_t;
-            Fr v = tl.get(t * row + bitrev(k, p.log_r));
+            Fr v = tl.get(bitrev(k, p.log_r) * Tp + t);
             const size_t go = out_base + (size_t)k * out_k_stride + (size_t)t * out_t_stride;
             if (p.post_coset) v = v * tw_lookup(tw_coset, (uint32_t)go);
             if (p.post_scale) v = v * p.scale;
@@ -296,7 +297,8 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
             blocks = n >> (dig[s] + log_t);
         }
         p.log_t = log_t;
-        const size_t smem = (((size_t)32) << (dig[s] + log_t)) + (last ? ((size_t)32 << log_t) : 0);   // + padded rows
+        const size_t smem = last ? ((size_t)32 << dig[s]) * (((size_t)1 << log_t) + 1)          // [R][T + 1] elements
+                                 : ((size_t)32) << (dig[s] + log_t);
         const Fr* coset_tab = inverse ? c->tw_geninv : c->tw_gen;
         dim3 grid((unsigned)blocks, (unsigned)batch);
         k_ntt_pass<<<grid, NTT_THREADS, smem, c->stream>>>(p, c->tw_root, coset_tab);
