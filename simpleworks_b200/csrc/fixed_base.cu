@@ -7,7 +7,7 @@
 // points per table for the (100000, 25000, 300000) bound every non-toy example uses).
 //
 // Device schedule: a 32 x 256 table of d * 2^(8o) * g (8-bit windows, affine), then one thread
-// per power: beta^i by square-and-multiply, 32 mixed additions, one Fermat inversion to affine.
+// per group of 8 consecutive powers: 32 mixed additions each, one shared inversion to affine.
 // Affine results are unique, so they equal arkworks' bit for bit.
 #define SWB_FP_NOINLINE_MUL
 #include "ctx.hpp"
@@ -46,31 +46,62 @@ __global__ void __launch_bounds__(128) k_fb_table(G1Aff* __restrict__ table, con
     table[e] = xyzz_to_affine(acc);
 }
 
-// RECORD = 104: ABI GroupAffine records (x | y | infinity flag); RECORD = 96: resident base layout
+// RECORD = 104: ABI GroupAffine records (x | y | infinity flag); RECORD = 96: resident base layout.
+// A thread produces `group` consecutive powers (beta^(i+1) = beta^i * beta) and normalises them with
+// ONE inversion (Montgomery's trick over zz * zzz): the Fermat inversion is 565 Fq products, more than
+// the 32 mixed additions of a power, so sharing it more than halves the work.
+constexpr int FB_GROUP = 8;
 template <int RECORD>
-__global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, const G1Aff* __restrict__ table, Fr beta, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Fr s = beta.pow_u64((uint64_t)i).to_canonical();
-    G1Xyzz acc = G1Xyzz::identity();
-    for (int o = 0; o < FB_OUTER; o++) {
-        const uint32_t d = (s.l[o >> 2] >> ((o & 3) * 8)) & 255u;
-        if (d) {
-            G1Aff p = table[o * 256 + d];
-            if (!p.is_identity()) acc.add_affine(p.x, p.y);
+__global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, const G1Aff* __restrict__ table, Fr beta, size_t n,
+                                                    int group) {
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)group;
+    if (i0 >= n) return;
+    const int cnt = i0 + group <= n ? group : (int)(n - i0);
+    Fr bp = beta.pow_u64((uint64_t)i0);
+    Fq zz[FB_GROUP], zzz[FB_GROUP], pre[FB_GROUP];
+    Fq run = Fq::one();
+    for (int g = 0; g < cnt; g++) {
+        const Fr s = bp.to_canonical();
+        bp = bp * beta;
+        G1Xyzz acc = G1Xyzz::identity();
+        for (int o = 0; o < FB_OUTER; o++) {
+            const uint32_t d = (s.l[o >> 2] >> ((o & 3) * 8)) & 255u;
+            if (d) {
+                G1Aff p = table[o * 256 + d];
+                if (!p.is_identity()) acc.add_affine(p.x, p.y);
+            }
         }
+        const bool inf = acc.is_identity();
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + (i0 + g) * RECORD);      // X | Y for now
+#pragma unroll
+        for (int k = 0; k < 12; k++) dst[k] = inf ? 0u : acc.x.l[k];
+#pragma unroll
+        for (int k = 0; k < 12; k++) dst[12 + k] = inf ? 0u : acc.y.l[k];
+        if (RECORD == 104) {
+            dst[24] = inf ? 1u : 0u;
+            dst[25] = 0u;
+        }
+        zz[g] = inf ? Fq::one() : acc.zz;
+        zzz[g] = inf ? Fq::one() : acc.zzz;
+        pre[g] = run;
+        run = run * (zz[g] * zzz[g]);
     }
-    const G1Aff a = xyzz_to_affine(acc);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(out + i * RECORD);
+    Fq inv = run.inverse();
+    for (int g = cnt; g-- > 0;) {
+        const Fq tinv = inv * pre[g];            // (zz_g * zzz_g)^-1
+        inv = inv * (zz[g] * zzz[g]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + (i0 + g) * RECORD);
+        Fq x, y;
 #pragma unroll
-    for (int k = 0; k < 12; k++) dst[k] = a.x.l[k];
+        for (int k = 0; k < 12; k++) { x.l[k] = dst[k]; y.l[k] = dst[12 + k]; }
+        x = x * (tinv * zzz[g]);                 // x = X / zz
+        y = y * (tinv * zz[g]);                  // y = Y / zzz
 #pragma unroll
-    for (int k = 0; k < 12; k++) dst[12 + k] = a.y.l[k];
-    if (RECORD == 104) {
-        dst[24] = a.is_identity() ? 1u : 0u;
-        dst[25] = 0u;
+        for (int k = 0; k < 12; k++) { dst[k] = x.l[k]; dst[12 + k] = y.l[k]; }
     }
 }
+// enough threads to fill the GPU first, then groups that share an inversion
+static inline int fb_group(size_t n) { return n >= ((size_t)1 << 18) ? FB_GROUP : 1; }
 
 // resident 96-byte records -> 104-byte ABI records
 __global__ void k_bases_export(uint8_t* __restrict__ out, const Fq* __restrict__ xy, size_t n) {
@@ -178,7 +209,11 @@ extern "C" int swb_fixed_base_powers(swb_ctx* c, const swb_g1_jacobian* g_host, 
     if (rc != SWB_OK) return rc;
     uint8_t* d_out = (uint8_t*)get_scratch(c, "fb_out", n * 104);
     if (!d_out) return SWB_ENOMEM;
-    k_fb_powers<104><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_out, d_table, beta, n);
+    {
+        const int grp = fb_group(n);
+        const size_t threads = (n + grp - 1) / grp;
+        k_fb_powers<104><<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(d_out, d_table, beta, n, grp);
+    }
     SWB_LAUNCH_CHECK(c, "k_fb_powers");
     SWB_CUDA(c, cudaMemcpyAsync(out_host, d_out, n * 104, cudaMemcpyDeviceToHost, c->stream));
     SWB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -202,7 +237,9 @@ extern "C" int swb_bases_from_powers(swb_ctx* c, const swb_g1_jacobian* g_host, 
         return set_err(c, SWB_ENOMEM, "bases_from_powers: cudaMalloc(%zu) failed: %s", n * 96, cudaGetErrorString(e));
     }
     if (n) {
-        k_fb_powers<96><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((uint8_t*)b->xy, d_table, beta, n);
+        const int grp = fb_group(n);
+        const size_t threads = (n + grp - 1) / grp;
+        k_fb_powers<96><<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>((uint8_t*)b->xy, d_table, beta, n, grp);
         c->launches++;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
