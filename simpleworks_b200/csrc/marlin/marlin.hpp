@@ -245,7 +245,6 @@ template <class Engine>
 struct ProvingKey {
     IndexInfo info;
     Domain dom_h, dom_k, dom_x;
-    std::vector<SparseRow> a, b, c;                 // padded, squared matrices
     // joint arithmetisation: entry k of K is (constraint r_k, variable c_k)
     std::vector<uint32_t> ent_row, ent_col;         // r_k, position of c_k in H (reindexed)
     std::vector<LabeledPoly<Engine>> index_polys;   // row, col, a_val, b_val, c_val, row_col (resident)
@@ -388,25 +387,34 @@ std::unique_ptr<UniversalSrs<Engine>> universal_setup(Engine& eng, size_t num_co
 }
 
 template <class Engine>
-void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Engine>* pk, VerifyingKey* vk) {
+void index(Engine& eng, const UniversalSrs<Engine>& srs, const R1cs& cs, ProvingKey<Engine>* pk, VerifyingKey* vk) {
     ScopedPhase ph_total("total");
     std::unique_ptr<ScopedPhase> ph(new ScopedPhase("i0_pad"));
-    cs.pad_instance();
-    cs.make_square();
-    const size_t nvar = cs.num_variables();
-    pk->dom_h = Domain(cs.num_constraints());
-    pk->dom_x = Domain(cs.num_instance);
+    // pad_input_for_indexer_and_prover + make_matrices_square without copying the matrices: the instance
+    // count goes up to a power of two (witness columns shift by `shift`), then either empty constraints
+    // or dummy witnesses make the system square
+    size_t ninst = 1;
+    while (ninst < cs.num_instance) ninst <<= 1;
+    const uint32_t shift = (uint32_t)(ninst - cs.num_instance);
+    const size_t orig_inst = cs.num_instance;
+    auto col_of = [&](uint32_t c) { return c >= orig_inst ? c + shift : c; };
+    const size_t nrows_real = cs.a.size();
+    const size_t nvar = std::max(ninst + cs.num_witness, nrows_real), ncons = nvar;
+    static const SparseRow empty_row;
+    auto row_of = [&](const std::vector<SparseRow>& m, size_t r) -> const SparseRow& { return r < nrows_real ? m[r] : empty_row; };
+    pk->dom_h = Domain(ncons);
+    pk->dom_x = Domain(ninst);
     const Domain& H = pk->dom_h;
     ph.reset(); ph.reset(new ScopedPhase("i1_merge_rows"));
     // joint sparsity pattern, row by row, columns in increasing order; rows are independent, so
     // they are merged in parallel: pass 1 counts the distinct columns of each row, pass 2 fills
     struct Ent { uint32_t col; uint8_t which; Fr coef; };
-    const size_t nrows = cs.a.size();
+    const size_t nrows = ncons;
     auto merged_row = [&](size_t r, std::vector<Ent>& tmp) {
         tmp.clear();
-        const SparseRow* rows[3] = {&cs.a[r], &cs.b[r], &cs.c[r]};
+        const SparseRow* rows[3] = {&row_of(cs.a, r), &row_of(cs.b, r), &row_of(cs.c, r)};
         for (uint8_t w = 0; w < 3; w++)
-            for (auto& e : rows[w]->e) tmp.push_back(Ent{e.second, w, e.first});
+            for (auto& e : rows[w]->e) tmp.push_back(Ent{col_of(e.second), w, e.first});
         std::stable_sort(tmp.begin(), tmp.end(), [](const Ent& x, const Ent& y) { return x.col < y.col; });
     };
     std::vector<size_t> row_off(nrows + 1, 0);
@@ -441,7 +449,7 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
             }
         }
     }
-    pk->info = IndexInfo{nvar, cs.num_constraints(), nnz, cs.num_instance};
+    pk->info = IndexInfo{nvar, ncons, nnz, ninst};
     pk->dom_k = Domain(nnz);
     const Domain& K = pk->dom_k;
     if (ahp_max_degree(pk->info.num_constraints, nvar, nnz) > srs.max_degree)
@@ -479,41 +487,59 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, R1cs cs, ProvingKey<Eng
     pk->val_c_evals = eng.vfrom_ptr(valc.get(), K.n);
     ph.reset(); ph.reset(new ScopedPhase("i3_transpose"));
     {
+        // counting sort of all matrix entries by the H position of their column; the order inside one
+        // position is irrelevant (the entries are summed in exact field arithmetic), so both passes run
+        // in parallel with atomic cursors
         std::vector<uint32_t> pos_of(nvar), cnt(H.n + 1, 0);
+#pragma omp parallel for schedule(static)
         for (size_t v = 0; v < nvar; v++) pos_of[v] = (uint32_t)H.reindex_by_subdomain(pk->dom_x, v);
         const std::vector<SparseRow>* ms[3] = {&cs.a, &cs.b, &cs.c};
-        for (int m = 0; m < 3; m++)
-            for (auto& row : *ms[m])
-                for (auto& e : row.e) cnt[pos_of[e.second] + 1]++;
+        for (int m = 0; m < 3; m++) {
+            const std::vector<SparseRow>& mat = *ms[m];
+#pragma omp parallel for schedule(static)
+            for (size_t r = 0; r < mat.size(); r++)
+                for (auto& e : mat[r].e) {
+                    uint32_t& slot = cnt[pos_of[col_of(e.second)] + 1];
+#pragma omp atomic
+                    slot++;
+                }
+        }
         for (size_t i = 0; i < H.n; i++) cnt[i + 1] += cnt[i];
         pk->t_start = cnt;
         const size_t tot = cnt[H.n];
         pk->t_row.resize(tot); pk->t_mat.resize(tot); pk->t_coef.resize(tot);
         std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
-        for (int m = 0; m < 3; m++)
-            for (size_t r = 0; r < ms[m]->size(); r++)
-                for (auto& e : (*ms[m])[r].e) {
-                    const uint32_t at = cur[pos_of[e.second]]++;
+        for (int m = 0; m < 3; m++) {
+            const std::vector<SparseRow>& mat = *ms[m];
+#pragma omp parallel for schedule(static)
+            for (size_t r = 0; r < mat.size(); r++)
+                for (auto& e : mat[r].e) {
+                    uint32_t at;
+                    uint32_t& slot = cur[pos_of[col_of(e.second)]];
+#pragma omp atomic capture
+                    at = slot++;
                     pk->t_row[at] = (uint32_t)r; pk->t_mat[at] = (uint8_t)m; pk->t_coef[at] = e.first;
                 }
+        }
     }
     ph.reset(); ph.reset(new ScopedPhase("i4_upload"));
-    pk->a = std::move(cs.a); pk->b = std::move(cs.b); pk->c = std::move(cs.c);   // cs is this function's own copy
     {
         pk->eng = srs.eng;          // lives as long as the SRS, which the key references anyway (ck.srs)
         auto upload_rows = [&](const std::vector<SparseRow>& m) {
-            std::vector<uint32_t> start(m.size() + 1, 0), col;
-            std::vector<Fr> coef;
-            for (size_t r = 0; r < m.size(); r++) start[r + 1] = start[r] + (uint32_t)m[r].e.size();
-            col.reserve(start.back());
-            coef.reserve(start.back());
-            for (auto& row : m)
-                for (auto& e : row.e) { col.push_back(e.second); coef.push_back(e.first); }
+            std::vector<uint32_t> start(ncons + 1, 0);
+            for (size_t r = 0; r < ncons; r++) start[r + 1] = start[r] + (uint32_t)row_of(m, r).e.size();
+            std::vector<uint32_t> col(start.back());
+            std::vector<Fr> coef(start.back());
+#pragma omp parallel for schedule(static)
+            for (size_t r = 0; r < m.size(); r++) {
+                uint32_t at = start[r];
+                for (auto& e : m[r].e) { col[at] = col_of(e.second); coef[at] = e.first; at++; }
+            }
             return eng.csr_upload(start, col, coef, nullptr);
         };
-        pk->m_a = upload_rows(pk->a);
-        pk->m_b = upload_rows(pk->b);
-        pk->m_c = upload_rows(pk->c);
+        pk->m_a = upload_rows(cs.a);
+        pk->m_b = upload_rows(cs.b);
+        pk->m_c = upload_rows(cs.c);
         pk->m_t = eng.csr_upload(pk->t_start, pk->t_row, pk->t_coef, &pk->t_mat);
     }
     ph.reset(); ph.reset(new ScopedPhase("i5_polys_commit"));
