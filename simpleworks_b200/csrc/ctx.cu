@@ -65,6 +65,15 @@ void vec_free(swb_ctx* c, void* p, size_t granted) {
     if (!p) return;
     c->vec_cache.emplace(granted, p);
     c->vec_cache_bytes += granted;
+    // a prover that keeps changing sizes must not hoard the device: past a third of its memory the cache
+    // is handed back (after the stream has drained, since cached blocks may still be in use on it)
+    if (c->total_mem && c->vec_cache_bytes > c->total_mem / 3) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        for (auto& kv : c->vec_cache) cudaFree(kv.second);
+        c->vec_cache.clear();
+        c->vec_cache_bytes = 0;
+    }
 }
 
 void* get_scratch(swb_ctx* c, const char* tag, size_t bytes) {
