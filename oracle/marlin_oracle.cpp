@@ -56,6 +56,7 @@ struct CpuEngine : HostVecOps {
     }
     void free_bases(void* h) { delete static_cast<CpuBases*>(h); }
     void bases_tune(void*, size_t) {}     // nothing to restructure on the CPU arm
+    size_t msm_submit(void* h, size_t offset, const Vec& scalars, size_t n) { return msm_submit_sync(*this, h, offset, scalars, n); }
     G1Point msm(void* h, size_t offset, const Vec& scalars, size_t n) {
         const Fr* scalars_mont = scalars.data();
         auto* b = static_cast<CpuBases*>(h);

@@ -77,7 +77,7 @@ void vec_free(swb_ctx* c, void* p, size_t granted) {
 }
 
 void* get_scratch(swb_ctx* c, const char* tag, size_t bytes) {
-    auto& s = c->scratch[tag];
+    auto& s = c->scratch_slot ? c->scratch[std::string(tag) + "#" + std::to_string(c->scratch_slot)] : c->scratch[tag];
     if (s.bytes >= bytes && s.p) return s.p;
     if (s.p) {
         cudaStreamSynchronize(c->stream);
@@ -161,6 +161,12 @@ void swb_destroy(swb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->vec_cache) cudaFree(kv.second);
+    for (auto& sl : c->msm_slot) {
+        if (sl.work) { cudaStreamSynchronize(sl.work); cudaStreamDestroy(sl.work); }
+        if (sl.tail) { cudaStreamSynchronize(sl.tail); cudaStreamDestroy(sl.tail); }
+        if (sl.ev) cudaEventDestroy(sl.ev);
+        if (sl.host_wins) cudaFreeHost(sl.host_wins);
+    }
     for (auto& kv : c->scratch)
         if (kv.second.p) cudaFree(kv.second.p);
     if (c->pinned) cudaFreeHost(c->pinned);

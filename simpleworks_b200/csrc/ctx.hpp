@@ -37,6 +37,19 @@ struct swb_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 
+    // MSM slots: slot 0 runs on `stream`; slots 1..MSM_SLOTS-1 have streams of their own (a normal one
+    // for sort + accumulation, a high-priority one for the latency-bound bucket tail) and their own
+    // scratch, so that independent MSMs of one prover round overlap (msm.cu: msm_begin / msm_end)
+    static constexpr int MSM_SLOTS = 3;
+    struct MsmSlot {
+        cudaStream_t work = nullptr, tail = nullptr;
+        cudaEvent_t ev = nullptr;
+        void* host_wins = nullptr;     // pinned, MSM_MAX_WINDOWS XYZZ points
+        int nwin = 0, cb = 0;
+        bool active = false, empty = false;
+    } msm_slot[MSM_SLOTS];
+    int scratch_slot = 0;              // suffix of scratch tags while a slot > 0 is being launched
+
     // cache of freed device blocks for the engine's vectors (vec_alloc / vec_free below), by size
     std::multimap<size_t, void*> vec_cache;
     size_t vec_cache_bytes = 0;
@@ -54,6 +67,12 @@ struct swb_bases {
 namespace swb {
 
 int set_err(swb_ctx* c, int code, const char* fmt, ...);
+// One MSM split in two: msm_begin enqueues everything up to the device->host copy of the bucket-set
+// sums (slot 0: on the context's stream; slot > 0: on the slot's own streams, after the work already
+// queued on the context's stream), msm_end waits for it and finishes on the host.  A slot holds one
+// MSM at a time.
+int msm_begin(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery);
+int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out);
 // Device blocks for short-lived vectors (the prover allocates and frees hundreds per proof).  All work of
 // a context is ordered on one stream, so a freed block can be handed to the next request at once;
 // blocks are rounded to 2 MiB and kept until swb_destroy, which keeps cudaMalloc/cudaFree (and the

@@ -21,6 +21,8 @@
 //     void  export_bases(void* h, size_t offset, size_t n, G1Point* out);
 //     void  free_bases(void* h);
 //     void  bases_tune(void* h, size_t typical_n);   // optional restructuring for MSMs of about typical_n scalars
+//     size_t msm_submit(void* h, size_t offset, const Vec& scalars, size_t n);   // queue an MSM (scalars stay alive)
+//     G1Point msm_result(size_t id);  void msm_drain();
 //     G1Point msm(void* h, size_t offset, const Vec& scalars_mont, size_t n);  // sum s_i * base[offset+i]
 //   };
 //
@@ -119,21 +121,28 @@ inline Poly rand_poly(size_t degree, ChaChaRng& rng) {   // DensePolynomial::ran
     return p;
 }
 
+// queue the MSM of polynomial p against powers_of_g[offset ..]; the result is fetched with
+// srs.eng->msm_result(id).  p must stay alive until then.
 template <class Engine>
-G1Point kzg_msm(const CommitterKey<Engine>& ck, size_t offset, const typename Engine::Vec& p) {
-    const size_t n = ck.srs->eng->vlen(p);
-    if (n == 0) return G1Point::identity();
-    if (offset + n > ck.srs->max_degree + 1) throw MarlinError("polynomial degree exceeds the SRS");
+size_t kzg_msm_submit(const CommitterKey<Engine>& ck, size_t offset, const typename Engine::Vec& p) {
     const UniversalSrs<Engine>& srs = *ck.srs;
+    const size_t n = srs.eng->vlen(p);
+    if (offset + n > srs.max_degree + 1) throw MarlinError("polynomial degree exceeds the SRS");
     if (!srs.tuned && srs.tune_after > 0 && (long)srs.msm_calls >= srs.tune_after) {
         srs.tuned = true;
+        srs.eng->msm_drain();                 // the tables replace the bases other MSMs may still be reading
         ScopedPhase ph("bases_tune");
         srs.eng->bases_tune(srs.powers_of_g, srs.msm_points / srs.msm_calls);
     }
     srs.msm_calls++;
     srs.msm_points += n;
     ScopedPhase ph("msm");
-    return srs.eng->msm(srs.powers_of_g, offset, p, n);
+    return srs.eng->msm_submit(srs.powers_of_g, offset, p, n);
+}
+template <class Engine>
+G1Point kzg_msm_result(const CommitterKey<Engine>& ck, size_t id) {
+    ScopedPhase ph("msm");
+    return ck.srs->eng->msm_result(id);
 }
 inline G1Point gamma_msm(const std::vector<G1Point>& gamma, const Poly& blind) {
     G1Xyzz acc = G1Xyzz::identity();
@@ -149,25 +158,36 @@ inline G1Point gamma_msm(const std::vector<G1Point>& gamma, const Poly& blind) {
 template <class Engine>
 void pc_commit(const CommitterKey<Engine>& ck, const std::vector<LabeledPoly<Engine>>& polys, ChaChaRng* rng,
                std::vector<Commitment>* comms, std::vector<Randomness>* rands) {
+    // all MSMs of the list are queued first (they are independent), blinders are drawn in upstream's
+    // order meanwhile, then the results are collected
+    struct Pending { size_t comm_id = 0, shifted_id = 0; };
+    std::vector<Pending> pend;
+    const size_t first = rands->size();
     for (const auto& lp : polys) {
-        Commitment c;
         Randomness r;
+        Pending pd;
         if (ck.srs->eng->vlen(lp.poly) > ck.supported_degree + 1) throw MarlinError("polynomial " + lp.label + " too large for the committer key");
-        c.comm = kzg_msm(ck, 0, lp.poly);
-        if (lp.hiding) {
-            r.blind = rand_poly(2, *rng);     // hiding_bound + 1 = degree 2
-            c.comm = g1_add(c.comm, gamma_msm(ck.srs->powers_of_gamma_g, r.blind));
+        pd.comm_id = kzg_msm_submit(ck, 0, lp.poly);
+        if (lp.hiding) r.blind = rand_poly(2, *rng);     // hiding_bound + 1 = degree 2
+        if (lp.has_bound) {
+            pd.shifted_id = kzg_msm_submit(ck, ck.srs->max_degree - lp.bound, lp.poly);
+            if (lp.hiding) r.shifted_blind = rand_poly(2, *rng);
         }
+        pend.push_back(pd);
+        rands->push_back(r);
+    }
+    for (size_t i = 0; i < polys.size(); i++) {
+        const auto& lp = polys[i];
+        const Randomness& r = (*rands)[first + i];
+        Commitment c;
+        c.comm = kzg_msm_result(ck, pend[i].comm_id);
+        if (lp.hiding) c.comm = g1_add(c.comm, gamma_msm(ck.srs->powers_of_gamma_g, r.blind));
         if (lp.has_bound) {
             c.has_shifted = true;
-            c.shifted = kzg_msm(ck, ck.srs->max_degree - lp.bound, lp.poly);
-            if (lp.hiding) {
-                r.shifted_blind = rand_poly(2, *rng);
-                c.shifted = g1_add(c.shifted, gamma_msm(ck.srs->powers_of_gamma_g, r.shifted_blind));
-            }
+            c.shifted = kzg_msm_result(ck, pend[i].shifted_id);
+            if (lp.hiding) c.shifted = g1_add(c.shifted, gamma_msm(ck.srs->powers_of_gamma_g, r.shifted_blind));
         }
         comms->push_back(c);
-        rands->push_back(r);
     }
 }
 
@@ -213,7 +233,10 @@ PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledP
     }
     PcProof pr;
     Vec witness = eng.vdiv_linear(p, point);
-    G1Xyzz w = to_xyzz(kzg_msm(ck, 0, witness));
+    const size_t wit_id = kzg_msm_submit(ck, 0, witness);
+    std::vector<size_t> shifted_ids;
+    for (auto& kv : shifted_by_offset) shifted_ids.push_back(kzg_msm_submit(ck, kv.first, kv.second));
+    G1Xyzz w = to_xyzz(kzg_msm_result(ck, wit_id));
     if (hiding) {
         Poly rwit = poly_divide_by_linear(r, point);
         G1Point t = gamma_msm(ck.srs->powers_of_gamma_g, rwit);
@@ -221,8 +244,8 @@ PcProof pc_open(const CommitterKey<Engine>& ck, const std::vector<const LabeledP
         pr.has_random_v = true;
         pr.random_v = poly_eval(r, point);
     }
-    for (auto& kv : shifted_by_offset) {
-        G1Point t = kzg_msm(ck, kv.first, kv.second);
+    for (size_t id : shifted_ids) {
+        G1Point t = kzg_msm_result(ck, id);
         if (!t.infinity) w.add_affine(t.x, t.y);
     }
     if (!shifted_r_witness.empty()) {

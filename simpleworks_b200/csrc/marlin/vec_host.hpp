@@ -5,6 +5,7 @@
 #pragma once
 #include "poly.hpp"
 #include "rng.hpp"
+#include "curve_host.hpp"
 
 namespace swb {
 namespace marlin {
@@ -48,6 +49,21 @@ struct HostVecOps {
     void vbatch_inverse(Vec& v) { batch_inverse(v); }
     Vec vshift_down(const Vec& p, size_t k) { return k < p.size() ? Vec(p.begin() + k, p.end()) : Vec(); }
     Vec vdomain(uint32_t log_n) { return Domain((size_t)1 << log_n).elements(); }
+    // submit / collect interface of the MSM (asynchronous on the CUDA engine): here the derived engine's
+    // msm() runs at submission
+    std::vector<G1Point> msm_results;     // results of ids msm_base .. ; old ones are dropped in blocks
+    size_t msm_base = 0;
+    template <class Derived>
+    size_t msm_submit_sync(Derived& self, void* h, size_t offset, const Vec& scalars, size_t n) {
+        if (msm_results.size() >= 128) {
+            msm_results.erase(msm_results.begin(), msm_results.begin() + 64);
+            msm_base += 64;
+        }
+        msm_results.push_back(n ? self.msm(h, offset, scalars, n) : G1Point::identity());
+        return msm_base + msm_results.size() - 1;
+    }
+    G1Point msm_result(size_t id) { return msm_results.at(id - msm_base); }
+    void msm_drain() {}
     // n consecutive Fr::rand draws (DensePolynomial::rand)
     Vec vrand(ChaChaRng& rng, size_t n) {
         Vec v(n);

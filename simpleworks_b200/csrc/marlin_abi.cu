@@ -319,6 +319,61 @@ struct GpuEngine {
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || swb_bases_len(b) * W * 96 > free_b / 2) return;
         if (swb_bases_precompute(c, b, best) != SWB_OK) cudaGetLastError();   // keep going on the plain path
     }
+    // Independent MSMs (the commitments of a round, the parts of an opening) are submitted first and
+    // collected later: two of them are in flight on the library's MSM slots, so the latency-bound
+    // bucket tail of one runs under the accumulation of the next.  The scalars must stay alive until the
+    // result has been collected.
+    struct Ticket { int slot; bool done; G1Point value; };
+    std::vector<Ticket> tickets;                           // ids ticket_base .. ; finished old ones are dropped in blocks
+    size_t ticket_base = 0;
+    long slot_owner[swb_ctx::MSM_SLOTS] = {-1, -1, -1};    // ticket id occupying each slot
+    int next_slot = 1;
+    static G1Point from_jacobian(const swb_g1_jacobian& out) {
+        G1Point p = G1Point::identity();
+        Fq z;
+        memcpy(z.l, out.z.l, 48);
+        if (!z.is_zero()) {                 // the library returns Z = 1
+            p.infinity = false;
+            memcpy(p.x.l, out.x.l, 48);
+            memcpy(p.y.l, out.y.l, 48);
+        }
+        return p;
+    }
+    void collect(size_t id) {
+        Ticket& t = tickets.at(id - ticket_base);
+        if (t.done) return;
+        swb_g1_jacobian out;
+        ck(msm_end(c, t.slot, &out), "msm");
+        slot_owner[t.slot] = -1;
+        t.value = from_jacobian(out);
+        t.done = true;
+    }
+    size_t msm_submit(void* h, size_t offset, const Vec& scalars, size_t n) {
+        OpTimer ot_(c, "msm_submit");
+        const int slot = next_slot;
+        next_slot = next_slot == 1 ? 2 : 1;
+        if (slot_owner[slot] >= 0) collect((size_t)slot_owner[slot]);
+        if (tickets.size() >= 128) {                       // batches are a handful of MSMs: these are long finished
+            for (size_t i = 0; i < 64; i++) collect(ticket_base + i);
+            tickets.erase(tickets.begin(), tickets.begin() + 64);
+            ticket_base += 64;
+        }
+        ck(msm_begin(c, slot, static_cast<swb_bases*>(h), offset, scalars.p, n, 1), "msm");
+        tickets.push_back(Ticket{slot, false, G1Point::identity()});
+        slot_owner[slot] = (long)(ticket_base + tickets.size() - 1);
+        return ticket_base + tickets.size() - 1;
+    }
+    G1Point msm_result(size_t id) {
+        OpTimer ot_(c, "msm_result");
+        collect(id);
+        return tickets.at(id - ticket_base).value;
+    }
+    void msm_drain() {
+        for (size_t i = 0; i < tickets.size(); i++) collect(ticket_base + i);
+    }
+    ~GpuEngine() {
+        try { msm_drain(); } catch (...) {}
+    }
     G1Point msm(void* h, size_t offset, const Vec& scalars, size_t n) {
         OpTimer ot_(c, "msm");
         swb_g1_jacobian out;

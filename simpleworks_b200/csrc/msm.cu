@@ -21,6 +21,8 @@
 //
 // The result is the affine value (as a Z = 1 Jacobian), which is unique, hence bit-identical to
 // what arkworks' callers see after into_affine().
+#include <memory>
+
 #include "msm_common.cuh"
 
 namespace swb {
@@ -62,18 +64,86 @@ static int pick_window(swb_ctx* c, size_t n) {
     return lg <= 26 ? best[lg] : 20;
 }
 
-static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery,
-                   swb_g1_jacobian* out) {
-    SWB_REQUIRE(c, bases && out, "msm: NULL argument");
+// streams, event and pinned result buffer of a slot, created on first use
+static int slot_prepare(swb_ctx* c, int slot) {
+    swb_ctx::MsmSlot& sl = c->msm_slot[slot];
+    if (!sl.host_wins) SWB_CUDA(c, cudaMallocHost(&sl.host_wins, sizeof(G1Xyzz) * MSM_MAX_WINDOWS));
+    if (slot > 0 && !sl.work) {
+        int lo = 0, hi = 0;
+        SWB_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi is the numerically smaller value
+        SWB_CUDA(c, cudaStreamCreateWithPriority(&sl.work, cudaStreamNonBlocking, lo));
+        SWB_CUDA(c, cudaStreamCreateWithPriority(&sl.tail, cudaStreamNonBlocking, hi));
+        SWB_CUDA(c, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    }
+    return SWB_OK;
+}
+
+static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery);
+
+int msm_begin(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery) {
+    SWB_REQUIRE(c, slot >= 0 && slot < swb_ctx::MSM_SLOTS, "msm: bad slot");
+    SWB_REQUIRE(c, !c->msm_slot[slot].active, "msm: slot already holds an MSM");
+    SWB_REQUIRE(c, bases != nullptr, "msm: NULL argument");
     SWB_REQUIRE(c, bases->ctx == c, "msm: bases belong to another context");
     SWB_REQUIRE(c, offset <= bases->n && n <= bases->n - offset, "msm: offset + n exceeds the loaded bases");
     SWB_REQUIRE(c, n < ((size_t)1 << 31), "msm: n must be < 2^31");
+    SWB_REQUIRE(c, n == 0 || scalars_dev != nullptr, "msm: NULL scalars");
+    SWB_CUDA(c, cudaSetDevice(c->device));
+    int rc = slot_prepare(c, slot);
+    if (rc != SWB_OK) return rc;
+    swb_ctx::MsmSlot& sl = c->msm_slot[slot];
+    sl.empty = n == 0;
     if (n == 0) {
+        sl.active = true;
+        return SWB_OK;
+    }
+    cudaStream_t main_stream = c->stream;
+    if (slot > 0) {
+        // inputs (scalars, bases) are produced on the context's stream: the slot starts after them
+        SWB_CUDA(c, cudaEventRecord(sl.ev, main_stream));
+        SWB_CUDA(c, cudaStreamWaitEvent(sl.work, sl.ev, 0));
+        c->stream = sl.work;
+        c->scratch_slot = slot;
+    }
+    rc = msm_enqueue(c, slot, bases, offset, scalars_dev, n, montgomery);
+    c->stream = main_stream;
+    c->scratch_slot = 0;
+    if (rc == SWB_OK) sl.active = true;
+    return rc;
+}
+
+int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out) {
+    SWB_REQUIRE(c, slot >= 0 && slot < swb_ctx::MSM_SLOTS && out, "msm: bad slot");
+    swb_ctx::MsmSlot& sl = c->msm_slot[slot];
+    SWB_REQUIRE(c, sl.active, "msm: slot holds no MSM");
+    sl.active = false;
+    if (sl.empty) {
         xyzz_to_out(G1Xyzz::identity(), out);
         return SWB_OK;
     }
-    SWB_REQUIRE(c, scalars_dev != nullptr, "msm: NULL scalars");
     SWB_CUDA(c, cudaSetDevice(c->device));
+    SWB_CUDA(c, cudaStreamSynchronize(slot > 0 ? sl.tail : c->stream));
+    const G1Xyzz* hw = static_cast<const G1Xyzz*>(sl.host_wins);
+    // Horner over the bucket sets, most significant first
+    G1Xyzz acc = hw[sl.nwin - 1];
+    for (int w = sl.nwin - 2; w >= 0; w--) {
+        for (int k = 0; k < sl.cb; k++) acc = acc.dbl();
+        acc.add(hw[w]);
+    }
+    xyzz_to_out(acc, out);
+    return SWB_OK;
+}
+
+static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery,
+                   swb_g1_jacobian* out) {
+    SWB_REQUIRE(c, out != nullptr, "msm: NULL argument");
+    int rc = msm_begin(c, 0, bases, offset, scalars_dev, n, montgomery);
+    if (rc != SWB_OK) return rc;
+    return msm_end(c, 0, out);
+}
+
+static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery) {
+    swb_ctx::MsmSlot& sl = c->msm_slot[slot];
     // window tables are worth it once the shared buckets hold a few points each
     const bool tables = bases->tab_w > 0 && !c->msm_window_override &&
                         n * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1));
@@ -120,13 +190,21 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
         !bf.buckets || !bf.seg || !bf.seg2 || !bf.wins)
         return SWB_ENOMEM;
     const uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;
-    StageTimer tm(c, "msm");
+    std::unique_ptr<StageTimer> tmp(slot == 0 ? new StageTimer(c, "msm") : nullptr);   // stage timing: slot 0 only
+    struct { StageTimer* t; void mark(const char* n) { if (t) t->mark(n); } } tm{tmp.get()};
     int rc = msm_launch_digits_sort(c, pl, bf, scalars_dev, montgomery, &sorted_keys, &sorted_vals);
     if (rc != SWB_OK) return rc;
     tm.mark("digits+sort+count");
     rc = msm_launch_accumulate(c, pl, bf, sorted_keys, sorted_vals, bases->xy + 2 * offset);
     if (rc != SWB_OK) return rc;
     tm.mark("accumulate");
+    if (slot > 0) {
+        // the bucket tail is latency-bound and small: on the slot's high-priority stream its blocks get
+        // the SM slots that another MSM's accumulation frees, instead of queueing behind it
+        SWB_CUDA(c, cudaEventRecord(sl.ev, sl.work));
+        SWB_CUDA(c, cudaStreamWaitEvent(sl.tail, sl.ev, 0));
+        c->stream = sl.tail;
+    }
     rc = msm_launch_gather(c, pl, bf);
     if (rc != SWB_OK) return rc;
     tm.mark("gather");
@@ -142,16 +220,9 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
                 cb, nwin, pl.nb, pl.range_len, pl.nranges, np, nheavy);
     }
 
-    G1Xyzz hw[MSM_MAX_WINDOWS];
-    SWB_CUDA(c, cudaMemcpyAsync(hw, bf.wins, sizeof(G1Xyzz) * nwin, cudaMemcpyDeviceToHost, c->stream));
-    SWB_CUDA(c, cudaStreamSynchronize(c->stream));
-    // Horner over windows, most significant first
-    G1Xyzz acc = hw[nwin - 1];
-    for (int w = nwin - 2; w >= 0; w--) {
-        for (int k = 0; k < cb; k++) acc = acc.dbl();
-        acc.add(hw[w]);
-    }
-    xyzz_to_out(acc, out);
+    sl.nwin = nwin;
+    sl.cb = cb;
+    SWB_CUDA(c, cudaMemcpyAsync(sl.host_wins, bf.wins, sizeof(G1Xyzz) * nwin, cudaMemcpyDeviceToHost, c->stream));
     return SWB_OK;
 }
 
