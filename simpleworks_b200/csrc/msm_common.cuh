@@ -6,7 +6,10 @@
 namespace swb {
 
 constexpr int MSM_MAX_WINDOWS = 128;
-constexpr int MSM_RED_THREADS = 256;   // block size of the heavy-bucket gather
+// block size of the bucket-tail kernels (gather, heavy gather, segments, bit sums): small enough (64 x <= 170
+// registers) to fit beside two resident blocks of another MSM's accumulation kernel, so the tail of one
+// MSM really runs under the accumulation of the next
+constexpr int MSM_TAIL_THREADS = 64;
 constexpr int MSM_SEG_LEN = 32;        // longest segment of the bucket reduction's running-sum level
 constexpr int MSM_GATHER_INLINE = 32;  // buckets with more partial sums than this go to the block-wide path
 

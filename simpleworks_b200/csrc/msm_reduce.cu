@@ -21,7 +21,7 @@ __global__ void k_msm_partial_bounds(uint32_t* __restrict__ pstart, const uint32
 
 // one thread per bucket: add its partial sums; buckets with many of them are queued for the
 // block-wide kernel instead
-__global__ void __launch_bounds__(128) k_msm_gather(G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ partial,
+__global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_gather(G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ partial,
                                                      const uint32_t* __restrict__ pstart, uint32_t nb,
                                                      uint32_t* __restrict__ heavy) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) k_msm_gather(G1Xyzz* __restrict__ buckets
 }
 
 // heavy buckets: one block per bucket, strided sums then a shared-memory tree
-__global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_gather_heavy(G1Xyzz* __restrict__ buckets,
+__global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_gather_heavy(G1Xyzz* __restrict__ buckets,
                                                                        const G1Xyzz* __restrict__ partial,
                                                                        const uint32_t* __restrict__ pstart,
                                                                        const uint32_t* __restrict__ heavy) {
@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_gather_heavy(G1Xyzz* __
         const uint32_t b = heavy[1 + h];
         const uint32_t p0 = pstart[b], p1 = pstart[b + 1];
         G1Xyzz acc = G1Xyzz::identity();
-        for (uint32_t p = p0 + t; p < p1; p += MSM_RED_THREADS) acc.add(partial[p]);
+        for (uint32_t p = p0 + t; p < p1; p += MSM_TAIL_THREADS) acc.add(partial[p]);
         buf[t] = acc;
         __syncthreads();
-        for (uint32_t d = MSM_RED_THREADS >> 1; d > 0; d >>= 1) {
+        for (uint32_t d = MSM_TAIL_THREADS >> 1; d > 0; d >>= 1) {
             if (t < d) {
                 G1Xyzz a = buf[t];
                 a.add(buf[t + d]);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_gather_heavy(G1Xyzz* __
 // levels of running sums cost 2-3 ms whatever the size).  k_msm_bit_sums: job 0 = sum W_s, job 1 + b =
 // T_b, a few blocks per job; k_msm_bit_tree: the blocks' partial results of one job, then 2^b L by
 // doublings; k_msm_bit_final: the jobs of one set.
-__global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_w, G1Xyzz* __restrict__ seg_p,
+__global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_segments(G1Xyzz* __restrict__ seg_w, G1Xyzz* __restrict__ seg_p,
                                                        const G1Xyzz* __restrict__ buckets, uint32_t L, uint32_t nseg_total) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // global segment id (set-major); B is a multiple of L
     if (g >= nseg_total) return;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) k_msm_segments(G1Xyzz* __restrict__ seg_w
     seg_w[g] = acc;
 }
 
-__global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_bit_sums(G1Xyzz* __restrict__ out, const G1Xyzz* __restrict__ seg_w,
+__global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_bit_sums(G1Xyzz* __restrict__ out, const G1Xyzz* __restrict__ seg_w,
                                                                    const G1Xyzz* __restrict__ seg_p, uint32_t m, uint32_t per) {
     extern __shared__ unsigned char smem_raw[];
     G1Xyzz* buf = reinterpret_cast<G1Xyzz*>(smem_raw);
@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_bit_sums(G1Xyzz* __rest
     const uint32_t lo = blk * per, hi = lo + per < m ? lo + per : m;
     const G1Xyzz* src = (job == 0 ? seg_w : seg_p) + (size_t)w * m;
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t s = lo + t; s < hi; s += MSM_RED_THREADS)
+    for (uint32_t s = lo + t; s < hi; s += MSM_TAIL_THREADS)
         if (job == 0 || ((s >> (job - 1)) & 1u)) acc.add(src[s]);
     buf[t] = acc;
     __syncthreads();
-    for (uint32_t d = MSM_RED_THREADS >> 1; d > 0; d >>= 1) {
+    for (uint32_t d = MSM_TAIL_THREADS >> 1; d > 0; d >>= 1) {
         if (t < d) {
             G1Xyzz a = buf[t];
             a.add(buf[t + d]);
@@ -154,11 +154,10 @@ __global__ void __launch_bounds__(32) k_msm_bit_final(G1Xyzz* __restrict__ wins,
 int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     k_msm_partial_bounds<<<(pl.nb + 1 + 255) / 256, 256, 0, c->stream>>>(bf.pstart, bf.pkey, bf.range_off + pl.nranges, pl.nb, bf.heavy);
     SWB_LAUNCH_CHECK(c, "k_msm_partial_bounds");
-    k_msm_gather<<<(pl.nb + 127) / 128, 128, 0, c->stream>>>(bf.buckets, bf.partial, bf.pstart, pl.nb, bf.heavy);
+    k_msm_gather<<<(pl.nb + MSM_TAIL_THREADS - 1) / MSM_TAIL_THREADS, MSM_TAIL_THREADS, 0, c->stream>>>(bf.buckets, bf.partial, bf.pstart, pl.nb, bf.heavy);
     SWB_LAUNCH_CHECK(c, "k_msm_gather");
-    const size_t smem = MSM_RED_THREADS * sizeof(G1Xyzz);
-    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_gather_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_msm_gather_heavy<<<c->sm_count, MSM_RED_THREADS, smem, c->stream>>>(bf.buckets, bf.partial, bf.pstart, bf.heavy);
+    const size_t smem = MSM_TAIL_THREADS * sizeof(G1Xyzz);
+    k_msm_gather_heavy<<<c->sm_count * 4, MSM_TAIL_THREADS, smem, c->stream>>>(bf.buckets, bf.partial, bf.pstart, bf.heavy);
     SWB_LAUNCH_CHECK(c, "k_msm_gather_heavy");
     return SWB_OK;
 }
@@ -173,17 +172,16 @@ int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     while ((1u << nbits) < m) nbits++;
     const uint32_t njobs = 1 + nbits;                     // <= 1 + 22
     G1Xyzz *seg_w = bf.seg, *seg_p = bf.seg + (size_t)nwin * m;
-    k_msm_segments<<<(nwin * m + 127) / 128, 128, 0, c->stream>>>(seg_w, seg_p, bf.buckets, L, nwin * m);
+    k_msm_segments<<<(nwin * m + MSM_TAIL_THREADS - 1) / MSM_TAIL_THREADS, MSM_TAIL_THREADS, 0, c->stream>>>(seg_w, seg_p, bf.buckets, L, nwin * m);
     SWB_LAUNCH_CHECK(c, "k_msm_segments");
     // a few blocks per job so that no thread adds more than ~8 segments serially
     uint32_t bpj = 1;
-    while (bpj < 32 && (size_t)bpj * MSM_RED_THREADS * 8 < m) bpj <<= 1;
+    while (bpj < 32 && (size_t)bpj * MSM_TAIL_THREADS * 8 < m) bpj <<= 1;
     const uint32_t per = (m + bpj - 1) / bpj;
     G1Xyzz* part = bf.seg2;                               // [nwin][njobs][bpj], then [nwin][njobs] values
     G1Xyzz* val = part + (size_t)nwin * njobs * bpj;
-    const size_t smem = MSM_RED_THREADS * sizeof(G1Xyzz);
-    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_bit_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_msm_bit_sums<<<dim3(bpj, njobs, nwin), MSM_RED_THREADS, smem, c->stream>>>(part, seg_w, seg_p, m, per);
+    const size_t smem = MSM_TAIL_THREADS * sizeof(G1Xyzz);
+    k_msm_bit_sums<<<dim3(bpj, njobs, nwin), MSM_TAIL_THREADS, smem, c->stream>>>(part, seg_w, seg_p, m, per);
     SWB_LAUNCH_CHECK(c, "k_msm_bit_sums");
     k_msm_bit_tree<<<dim3(njobs, nwin), 32, 0, c->stream>>>(val, part, bpj, log_L);
     SWB_LAUNCH_CHECK(c, "k_msm_bit_tree");
