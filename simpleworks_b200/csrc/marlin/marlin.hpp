@@ -77,13 +77,13 @@ struct UniversalSrs {
     // may restructure the bases for them (window tables on the CUDA engine), see kzg_msm
     mutable size_t msm_calls = 0, msm_points = 0;
     mutable bool tuned = false;
-    // number of MSMs after which the engine tunes the bases (0 = never).  Default 24 = one index + one
-    // proof: a one-shot setup/index/prove never pays for it, a prover that keeps going gets the faster
-    // path from its second proof on.  SWB_MARLIN_TABLES overrides the default, swb_srs_set_tune_after
-    // one SRS.
+    // number of MSMs after which the engine tunes the bases (0 = never).  Building the window tables
+    // costs about as much as 4 proofs and saves ~13 % of each later one, so the default (400 MSMs, some
+    // twenty proofs) leaves one-shot and short-lived provers alone and lets a proving service reach the
+    // faster path by itself.  SWB_MARLIN_TABLES overrides the default, swb_srs_set_tune_after one SRS.
     long tune_after = [] {
         const char* e = getenv("SWB_MARLIN_TABLES");
-        return e ? atol(e) : 24L;
+        return e ? atol(e) : 400L;
     }();
     ~UniversalSrs() {
         if (eng && powers_of_g) eng->free_bases(powers_of_g);
