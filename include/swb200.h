@@ -131,6 +131,13 @@ int  swb_msm_g1_fr_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* 
 /* the same with host-resident Montgomery scalars (what a polynomial's coefficient vector is) */
 int  swb_msm_g1_fr(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scalars_host, size_t n,
                    swb_g1_jacobian* out_host);
+/* n_msms independent MSMs over the same bases (the commitments of one prover round: ark-poly-commit's
+ * `commit` loops over its polynomials): MSM i takes ns[i] device-resident scalars scalars_dev[i]
+ * (canonical integers, or Montgomery values when montgomery != 0) against bases[offsets[i] ..] and writes
+ * outs[i].  Two MSMs are in flight at a time on streams of their own, which hides the latency-bound
+ * bucket reduction of one under the accumulation of the next; results equal n_msms single calls. */
+int  swb_msm_g1_batch_dev(swb_ctx*, const swb_bases*, const size_t* offsets, const void* const* scalars_dev, const size_t* ns,
+                          size_t n_msms, int montgomery, swb_g1_jacobian* outs);
 /* the signed-digit window width c and window count ceil(254/c) an n-point MSM will use */
 int  swb_msm_plan(swb_ctx*, size_t n, int* window_bits, int* windows);
 /* window width override for tuning/tests (0 = automatic) */

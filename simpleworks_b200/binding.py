@@ -223,6 +223,18 @@ class Backend:
         self._check(self._lib.swb_msm_plan(self._h, n, ctypes.byref(c), ctypes.byref(w)))
         return c.value, w.value
 
+    def msm_batch(self, bases: Bases, scalar_tensors, offsets=None, montgomery: bool = False) -> np.ndarray:
+        """Several MSMs over the same bases (device tensors of shape (n_i, 4) int64/uint64), overlapped on the
+        library's MSM slots; returns (k, 18) Jacobian results."""
+        k = len(scalar_tensors)
+        offsets = list(offsets) if offsets is not None else [0] * k
+        ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in scalar_tensors])
+        ns = (ctypes.c_size_t * k)(*[t.shape[0] for t in scalar_tensors])
+        offs = (ctypes.c_size_t * k)(*offsets)
+        out = np.zeros((k, 18), dtype=np.uint64)
+        self._check(self._lib.swb_msm_g1_batch_dev(self._h, bases._h, offs, ptrs, ns, k, int(montgomery), _np_ptr(out)))
+        return out
+
     def set_msm_window_bits(self, c: int):
         self._check(self._lib.swb_msm_set_window_bits(self._h, c))
 

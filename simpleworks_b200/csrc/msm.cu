@@ -319,6 +319,32 @@ int swb_msm_g1_fr_dev(swb_ctx* c, const swb_bases* b, size_t offset, const swb_f
     return msm_run(c, b, offset, scalars_dev, n, 1, out);
 }
 
+int swb_msm_g1_batch_dev(swb_ctx* c, const swb_bases* b, const size_t* offsets, const void* const* scalars_dev, const size_t* ns,
+                         size_t n_msms, int montgomery, swb_g1_jacobian* outs) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, n_msms == 0 || (offsets && scalars_dev && ns && outs), "msm_batch: NULL argument");
+    // two MSMs in flight on slots 1 and 2: the bucket tail of one runs under the accumulation of the next
+    int rc = SWB_OK;
+    size_t pending[swb_ctx::MSM_SLOTS] = {0, 0, 0};
+    bool busy[swb_ctx::MSM_SLOTS] = {false, false, false};
+    for (size_t i = 0; i < n_msms && rc == SWB_OK; i++) {
+        const int slot = 1 + (int)(i & 1);
+        if (busy[slot]) {
+            rc = msm_end(c, slot, &outs[pending[slot]]);
+            busy[slot] = false;
+            if (rc != SWB_OK) break;
+        }
+        rc = msm_begin(c, slot, b, offsets[i], scalars_dev[i], ns[i], montgomery);
+        if (rc == SWB_OK) { busy[slot] = true; pending[slot] = i; }
+    }
+    for (int slot = 1; slot < swb_ctx::MSM_SLOTS; slot++)
+        if (busy[slot]) {
+            const int r2 = msm_end(c, slot, &outs[pending[slot]]);    // always drain, keep the first error
+            if (rc == SWB_OK) rc = r2;
+        }
+    return rc;
+}
+
 int swb_msm_g1(swb_ctx* c, const swb_bases* b, size_t offset, const swb_bigint256* scalars_host, size_t n,
                swb_g1_jacobian* out) {
     if (!c) return SWB_EARG;

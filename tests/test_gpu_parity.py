@@ -298,6 +298,30 @@ def test_msm_repeated_negated_and_infinite_bases(be, srs_points, tables):
         bases.free()
 
 
+@pytest.mark.parametrize("tables", [False, True])
+def test_msm_batch_equals_single_calls(be, srs_points, tables):
+    """swb_msm_g1_batch_dev: MSMs overlapped on the two slots give the results of single calls, for mixed
+    sizes (including empty), offsets and both scalar forms."""
+    bases = be.load_bases(srs_points[:20000])
+    if tables:
+        bases.precompute(10)
+    try:
+        sizes = [5000, 0, 1, 16384, 777, 12000, 3]
+        offs = [0, 5, 100, 1000, 19000, 8000, 19997]
+        host = [_rand_fr(n, 3100 + i) for i, n in enumerate(sizes)]
+        dev = [be.to_device(h) for h in host]
+        got = be.msm_batch(bases, dev, offs)
+        for i, (h, o) in enumerate(zip(host, offs)):
+            single = be.msm(bases, h, offset=o)
+            assert np.array_equal(got[i:i + 1], single), i
+        mont = [be.to_device(O.fr_mont(O.limbs_to_ints(h))) if len(h) else be.to_device(h) for h in host]
+        assert np.array_equal(be.msm_batch(bases, mont, offs, montgomery=True), got)
+        want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[1000:1000 + 16384]), host[3]))
+        assert np.array_equal(O.g1_to_affine(got[3:4]), want)
+    finally:
+        bases.free()
+
+
 def test_msm_randomised_shapes_vs_oracle(be, srs_points):
     """40 seeded random cases: size, offset, forced window width, window tables or not, and a mix of scalar
     kinds (0, 1, r - 1, small, top-heavy, uniform) -- each against the oracle's Pippenger."""
