@@ -367,6 +367,23 @@ def main():
         w = float(worst.item())
         marlin_replicas = {"log_constraints": args.marlin_log_n, "provers": world, "prove_s_max_over_ranks": w,
                            "proofs_per_s": world / w if w < float("inf") else 0.0, "rank0": r, "error": err}
+        # one proof on all N GPUs: every rank runs the prover, its commit / open MSMs are sharded by index
+        # range and the 144-byte partial results all-gathered over NCCL (swb_set_msm_shard)
+        r2, mine2, err2 = None, float("inf"), None
+        try:
+            be.set_msm_shard(rank, world, dev)
+            r2, _ = marlin_gpu_run(be, args.marlin_log_n, 2)
+            mine2 = r2["prove_s"]
+        except Exception as e:
+            err2 = repr(e)
+        finally:
+            be.set_msm_shard(0, 1)
+        worst2 = torch.tensor([mine2], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst2, op=dist.ReduceOp.MAX)
+        w2 = float(worst2.item())
+        marlin_replicas["one_proof_on_all_gpus"] = {
+            "prove_s_max_over_ranks": w2, "speedup_vs_one_gpu": (w / w2) if w2 < float("inf") and w < float("inf") else 0.0,
+            "rank0": r2, "error": err2, "how": "MSMs sharded by index range, partial sums all-gathered (NCCL); proof bytes as on one GPU"}
 
     if rank != 0:
         if world > 1:

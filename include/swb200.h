@@ -131,6 +131,16 @@ int  swb_msm_g1_fr_dev(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* 
 /* the same with host-resident Montgomery scalars (what a polynomial's coefficient vector is) */
 int  swb_msm_g1_fr(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scalars_host, size_t n,
                    swb_g1_jacobian* out_host);
+/* Multi-GPU proving.  One process per GPU runs the same prover on the same inputs (the protocol is
+ * deterministic, so every rank holds every polynomial); after this call each commit / open MSM of
+ * swb_marlin_index and swb_marlin_prove on this context only covers the rank's contiguous share of
+ * the (base, scalar) index range and `combine` is called with the 144-byte partial result: it must
+ * return the sum over all ranks (an all-gather of world x 144 bytes followed by swb_g1_sum_jacobian --
+ * simpleworks_b200/binding.py does it with torch.distributed over NCCL).  Every rank then continues
+ * with identical commitments, so the proof bytes are those of a single GPU.  world <= 1 or a NULL
+ * callback switch it off.  The callback returns 0 on success. */
+typedef int (*swb_combine_fn)(void* user, const swb_g1_jacobian* mine, swb_g1_jacobian* sum);
+int  swb_set_msm_shard(swb_ctx*, int rank, int world, swb_combine_fn combine, void* user);
 /* n_msms independent MSMs over the same bases (the commitments of one prover round: ark-poly-commit's
  * `commit` loops over its polynomials): MSM i takes ns[i] device-resident scalars scalars_dev[i]
  * (canonical integers, or Montgomery values when montgomery != 0) against bases[offsets[i] ..] and writes

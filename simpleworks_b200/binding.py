@@ -235,6 +235,28 @@ class Backend:
         self._check(self._lib.swb_msm_g1_batch_dev(self._h, bases._h, offs, ptrs, ns, k, int(montgomery), _np_ptr(out)))
         return out
 
+    def set_msm_shard(self, rank: int, world: int, device=None):
+        """Multi-GPU proving (swb_set_msm_shard): every commit / open MSM of the Marlin entry points on this
+        backend covers this rank's share only; the partial results are all-gathered with torch.distributed
+        (NCCL on `device`, gloo when device is None) and summed, so all ranks continue with the same
+        commitments.  world <= 1 switches it off."""
+        if world <= 1:
+            self._check(self._lib.swb_set_msm_shard(self._h, 0, 1, None, None))
+            self._combine_cb = None
+            return
+        cb_t = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+        def combine(_user, mine, out):
+            try:
+                part = np.ctypeslib.as_array(ctypes.cast(mine, ctypes.POINTER(ctypes.c_uint64)), shape=(1, 18)).copy()
+                total = combine_partials(part, world, device)
+                ctypes.memmove(out, total.ctypes.data, 144)
+                return 0
+            except Exception:      # never let an exception cross the C boundary
+                return 1
+        self._combine_cb = cb_t(combine)        # keep the trampoline alive
+        self._check(self._lib.swb_set_msm_shard(self._h, rank, world, ctypes.cast(self._combine_cb, ctypes.c_void_p), None))
+
     def set_msm_window_bits(self, c: int):
         self._check(self._lib.swb_msm_set_window_bits(self._h, c))
 

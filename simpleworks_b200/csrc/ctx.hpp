@@ -49,6 +49,10 @@ struct swb_ctx {
         bool active = false, empty = false;
     } msm_slot[MSM_SLOTS];
     int scratch_slot = 0;              // suffix of scratch tags while a slot > 0 is being launched
+    // multi-GPU proving (swb_set_msm_shard): this rank's share of every prover MSM, and who adds them up
+    int shard_rank = 0, shard_world = 1;
+    int (*shard_combine)(void*, const swb_g1_jacobian*, swb_g1_jacobian*) = nullptr;
+    void* shard_user = nullptr;
 
     // cache of freed device blocks for the engine's vectors (vec_alloc / vec_free below), by size
     std::multimap<size_t, void*> vec_cache;

@@ -323,7 +323,7 @@ struct GpuEngine {
     // collected later: two of them are in flight on the library's MSM slots, so the latency-bound
     // bucket tail of one runs under the accumulation of the next.  The scalars must stay alive until the
     // result has been collected.
-    struct Ticket { int slot; bool done; G1Point value; };
+    struct Ticket { int slot; bool done; G1Point value; bool sharded; };
     std::vector<Ticket> tickets;                           // ids ticket_base .. ; finished old ones are dropped in blocks
     size_t ticket_base = 0;
     long slot_owner[swb_ctx::MSM_SLOTS] = {-1, -1, -1};    // ticket id occupying each slot
@@ -345,6 +345,11 @@ struct GpuEngine {
         swb_g1_jacobian out;
         ck(msm_end(c, t.slot, &out), "msm");
         slot_owner[t.slot] = -1;
+        if (t.sharded) {                                   // this rank's share -> the sum over all ranks
+            swb_g1_jacobian sum;
+            if (c->shard_combine(c->shard_user, &out, &sum) != 0) throw MarlinError("msm: combining the ranks' partial results failed");
+            out = sum;
+        }
         t.value = from_jacobian(out);
         t.done = true;
     }
@@ -358,8 +363,16 @@ struct GpuEngine {
             tickets.erase(tickets.begin(), tickets.begin() + 64);
             ticket_base += 64;
         }
-        ck(msm_begin(c, slot, static_cast<swb_bases*>(h), offset, scalars.p, n, 1), "msm");
-        tickets.push_back(Ticket{slot, false, G1Point::identity()});
+        // multi-GPU proving: only this rank's contiguous share of the index range (remainder to the first ranks)
+        const bool sharded = c->shard_world > 1 && c->shard_combine;
+        size_t lo = 0, cnt = n;
+        if (sharded) {
+            const size_t base = n / (size_t)c->shard_world, rem = n % (size_t)c->shard_world, r = (size_t)c->shard_rank;
+            lo = r * base + (r < rem ? r : rem);
+            cnt = base + (r < rem ? 1 : 0);
+        }
+        ck(msm_begin(c, slot, static_cast<swb_bases*>(h), offset + lo, scalars.p + lo, cnt, 1), "msm");
+        tickets.push_back(Ticket{slot, false, G1Point::identity(), sharded});
         slot_owner[slot] = (long)(ticket_base + tickets.size() - 1);
         return ticket_base + tickets.size() - 1;
     }

@@ -300,6 +300,17 @@ int swb_msm_plan(swb_ctx* c, size_t n, int* window_bits, int* windows) {
     return SWB_OK;
 }
 
+int swb_set_msm_shard(swb_ctx* c, int rank, int world, swb_combine_fn combine, void* user) {
+    if (!c) return SWB_EARG;
+    if (world <= 1 || !combine) {
+        c->shard_rank = 0; c->shard_world = 1; c->shard_combine = nullptr; c->shard_user = nullptr;
+        return SWB_OK;
+    }
+    SWB_REQUIRE(c, rank >= 0 && rank < world, "set_msm_shard: rank out of range");
+    c->shard_rank = rank; c->shard_world = world; c->shard_combine = combine; c->shard_user = user;
+    return SWB_OK;
+}
+
 int swb_msm_set_window_bits(swb_ctx* c, int cb) {
     if (!c) return SWB_EARG;
     SWB_REQUIRE(c, cb == 0 || (cb >= 2 && cb <= 22), "msm_set_window_bits: c must be 0 or in [2,22]");

@@ -171,3 +171,20 @@ def test_general_shape_circuit_gpu_equals_cpu(gpu, size, terms):
     cpk, cvk = CPU.index(csrs, ccs)
     assert CPU.prove(cpk, ccs, crng) == proof
     assert gpu.serialize_verifying_key(vk) == CPU.vk_serialize(cvk)
+
+
+def test_sharded_proving_two_gpus():
+    """Multi-GPU proving (swb_set_msm_shard): two ranks, MSMs sharded, NCCL all-gather of the partial results --
+    same proof bytes as one GPU.  Needs two visible GPUs (skipped on a single-GPU box)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = os.path.join(os.path.dirname(__file__), "dist_marlin_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", script, "14"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1])["ok"]
