@@ -14,10 +14,15 @@
 //                           sum per run of equal bucket ids -- work per thread is bounded whatever
 //                           the scalar distribution
 //   5. k_msm_gather(_heavy) partial sums of one bucket -> the bucket
-//   6. k_msm_segments / k_msm_reduce_level
-//                           sum_k k * B_k per window: per-segment (count, weighted) pairs,
-//                           combined level by level
-//   7. host                 Horner over the W window sums (c doublings each) and normalisation
+//   6. k_msm_segments / k_msm_bit_sums / k_msm_bit_tree / k_msm_bit_final
+//                           sum_k k * B_k per bucket set: running sums per segment, then plain sums
+//                           selected by the bits of the segment index, reduced as trees
+//   7. host                 Horner over the bucket-set sums (c doublings each) and normalisation
+//
+// With window tables (swb_bases_precompute, fixed_base.cu) digit j of a scalar selects the precomputed
+// point 2^(c*j) * P, so all digits share ONE bucket set: steps 2-6 run on a single segment of n * W
+// pairs and step 7 has nothing to fold.  msm_begin / msm_end split a call so that independent MSMs
+// overlap on slots with streams and scratch of their own.
 //
 // The result is the affine value (as a Z = 1 Jacobian), which is unique, hence bit-identical to
 // what arkworks' callers see after into_affine().
