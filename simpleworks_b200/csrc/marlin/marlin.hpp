@@ -135,7 +135,7 @@ size_t kzg_msm_submit(const CommitterKey<Engine>& ck, size_t offset, const typen
         srs.eng->bases_tune(srs.powers_of_g, srs.msm_points / srs.msm_calls);
     }
     srs.msm_calls++;
-    srs.msm_points += n;
+    srs.msm_points += srs.eng->msm_local_count(n);     // what this engine will really process (a share, when sharded)
     ScopedPhase ph("msm");
     return srs.eng->msm_submit(srs.powers_of_g, offset, p, n);
 }

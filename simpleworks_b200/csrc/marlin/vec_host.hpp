@@ -63,6 +63,7 @@ struct HostVecOps {
         return msm_base + msm_results.size() - 1;
     }
     G1Point msm_result(size_t id) { return msm_results.at(id - msm_base); }
+    size_t msm_local_count(size_t n) { return n; }
     void msm_drain() {}
     // n consecutive Fr::rand draws (DensePolynomial::rand)
     Vec vrand(ChaChaRng& rng, size_t n) {

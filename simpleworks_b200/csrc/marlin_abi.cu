@@ -353,6 +353,12 @@ struct GpuEngine {
         t.value = from_jacobian(out);
         t.done = true;
     }
+    // scalars of an n-point prover MSM that this rank processes (swb_set_msm_shard)
+    size_t msm_local_count(size_t n) {
+        if (!(c->shard_world > 1 && c->shard_combine)) return n;
+        const size_t base = n / (size_t)c->shard_world, rem = n % (size_t)c->shard_world;
+        return base + ((size_t)c->shard_rank < rem ? 1 : 0);
+    }
     size_t msm_submit(void* h, size_t offset, const Vec& scalars, size_t n) {
         OpTimer ot_(c, "msm_submit");
         const int slot = next_slot;
