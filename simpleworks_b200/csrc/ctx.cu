@@ -31,6 +31,15 @@ int cuda_fail(swb_ctx* c, cudaError_t e, const char* what) {
     return set_err(c, SWB_ECUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
 }
 
+void sync_all_streams(swb_ctx* c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& sl : c->msm_slot) {
+        if (sl.work) cudaStreamSynchronize(sl.work);
+        if (sl.tail) cudaStreamSynchronize(sl.tail);
+    }
+}
+
 void* vec_alloc(swb_ctx* c, size_t bytes, size_t* granted) {
     const size_t unit = (size_t)2 << 20;
     const size_t want = bytes ? (bytes + unit - 1) / unit * unit : unit;

@@ -71,6 +71,9 @@ struct swb_bases {
 namespace swb {
 
 int set_err(swb_ctx* c, int code, const char* fmt, ...);
+// wait for the context's stream and for the MSM slots' own streams (before device memory they may be
+// reading is released)
+void sync_all_streams(swb_ctx* c);
 // One MSM split in two: msm_begin enqueues everything up to the device->host copy of the bucket-set
 // sums (slot 0: on the context's stream; slot > 0: on the slot's own streams, after the work already
 // queued on the context's stream), msm_end waits for it and finishes on the host.  A slot holds one

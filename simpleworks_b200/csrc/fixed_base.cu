@@ -311,6 +311,7 @@ extern "C" int swb_bases_precompute(swb_ctx* c, swb_bases* b, int window_bits) {
         cudaFree(tab);
         return cuda_fail(c, e, "k_bases_tables");
     }
+    sync_all_streams(c);                         // an MSM on a slot stream may still be reading the old records
     cudaFree(b->xy);
     b->xy = tab;
     b->tab_c = cb;

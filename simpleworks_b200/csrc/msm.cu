@@ -289,10 +289,7 @@ size_t swb_bases_len(const swb_bases* b) { return b ? b->n : 0; }
 
 void swb_bases_free(swb_bases* b) {
     if (!b) return;
-    if (b->ctx) {
-        cudaSetDevice(b->ctx->device);
-        cudaStreamSynchronize(b->ctx->stream);
-    }
+    if (b->ctx) sync_all_streams(b->ctx);
     if (b->xy) cudaFree(b->xy);
     delete b;
 }
