@@ -19,6 +19,14 @@ using namespace swb::marlin;
 
 namespace {
 
+// multi-process proving on the CPU arm, mirroring swb_set_msm_shard: each process computes its
+// contiguous share of every prover MSM and `combine` returns the sum over all processes
+struct OrcShard {
+    int rank = 0, world = 1;
+    int (*combine)(void*, const g1_jac_t*, g1_jac_t*) = nullptr;
+    void* user = nullptr;
+} g_shard;
+
 struct CpuBases {
     std::vector<g1_affine_t> pts;
 };
@@ -57,14 +65,32 @@ struct CpuEngine : HostVecOps {
     void free_bases(void* h) { delete static_cast<CpuBases*>(h); }
     void bases_tune(void*, size_t) {}     // nothing to restructure on the CPU arm
     size_t msm_submit(void* h, size_t offset, const Vec& scalars, size_t n) { return msm_submit_sync(*this, h, offset, scalars, n); }
-    G1Point msm(void* h, size_t offset, const Vec& scalars, size_t n) {
-        const Fr* scalars_mont = scalars.data();
+    size_t msm_local_count(size_t n) {
+        if (!(g_shard.world > 1 && g_shard.combine)) return n;
+        return n / (size_t)g_shard.world + ((size_t)g_shard.rank < n % (size_t)g_shard.world ? 1 : 0);
+    }
+    G1Point msm(void* h, size_t offset_full, const Vec& scalars, size_t n_full) {
+        // this process's share of the index range (all of it unless orc_set_msm_shard is active)
+        const bool sharded = g_shard.world > 1 && g_shard.combine;
+        size_t lo = 0, n = n_full;
+        if (sharded) {
+            const size_t base = n_full / (size_t)g_shard.world, rem = n_full % (size_t)g_shard.world, r = (size_t)g_shard.rank;
+            lo = r * base + (r < rem ? r : rem);
+            n = base + (r < rem ? 1 : 0);
+        }
+        const size_t offset = offset_full + lo;
+        const Fr* scalars_mont = scalars.data() + lo;
         auto* b = static_cast<CpuBases*>(h);
         std::vector<big256_t> sc(n);
 #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < n; i++) orc_fr_to_canon(&sc[i], reinterpret_cast<const fr_t*>(&scalars_mont[i]));
         g1_jac_t out;
         orc_msm_variable_base(&out, b->pts.data() + offset, sc.data(), n, 0);
+        if (sharded) {
+            g1_jac_t sum;
+            if (g_shard.combine(g_shard.user, &out, &sum) != 0) throw MarlinError("msm: combining the processes' partial results failed");
+            out = sum;
+        }
         g1_affine_t a;
         orc_g1_to_affine(&a, &out);
         G1Point p = G1Point::identity();
@@ -140,6 +166,13 @@ int orc_marlin_index(void* srs, void* cs, void** pk, void** vk) {
 }
 void orc_pk_free(void* pk) { delete static_cast<PkHandle<CpuEngine>*>(pk); }
 void orc_vk_free(void* vk) { delete static_cast<VkHandle*>(vk); }
+int orc_set_msm_shard(int rank, int world, int (*combine)(void*, const g1_jac_t*, g1_jac_t*), void* user) {
+    g_shard.rank = world > 1 ? rank : 0;
+    g_shard.world = world > 1 && combine ? world : 1;
+    g_shard.combine = world > 1 ? combine : nullptr;
+    g_shard.user = user;
+    return 0;
+}
 int orc_marlin_prove(void* pk, void* cs, void* rng, uint8_t** bytes, size_t* len) {
     return Api::prove(g_engine, static_cast<PkHandle<CpuEngine>*>(pk), static_cast<R1csHandle*>(cs), static_cast<RngHandle*>(rng),
                       bytes, len, &g_err);

@@ -157,6 +157,33 @@ def index(srs, cs: R1cs):
     return pk, vk
 
 
+_shard_cb = None
+
+
+def set_msm_shard(rank: int, world: int, combine=None):
+    """CPU-arm mirror of swb_set_msm_shard: every prover MSM only covers this process's share of the index
+    range; combine(partial (1,18) uint64 Jacobian) must return the sum over all processes.  world <= 1 = off."""
+    global _shard_cb
+    L = lib()
+    L.orc_set_msm_shard.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    if world <= 1 or combine is None:
+        L.orc_set_msm_shard(0, 1, None, None)
+        _shard_cb = None
+        return
+    cb_t = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+    def tramp(_user, mine, out):
+        try:
+            part = np.ctypeslib.as_array(ctypes.cast(mine, ctypes.POINTER(ctypes.c_uint64)), shape=(1, 18)).copy()
+            total = np.ascontiguousarray(combine(part), dtype=np.uint64)
+            ctypes.memmove(out, total.ctypes.data, 144)
+            return 0
+        except Exception:
+            return 1
+    _shard_cb = cb_t(tramp)
+    L.orc_set_msm_shard(rank, world, ctypes.cast(_shard_cb, ctypes.c_void_p), None)
+
+
 def prove(pk, cs: R1cs, rng: Rng) -> bytes:
     p = ctypes.POINTER(ctypes.c_uint8)()
     n = ctypes.c_size_t()

@@ -54,6 +54,46 @@ def test_sharded_msm_combine_world2():
     assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == n
 
 
+def _prove_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hashlib
+    from oracle import pymarlin as M
+    from simpleworks_b200 import binding
+    M.set_msm_shard(rank, world, lambda part: binding.combine_partials(part, world))
+    rng = M.Rng()
+    srs = M.universal_setup(100, 25, 300, rng)
+    cs = M.R1cs("chain", size=20, v0=3, v1=5)
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, rng)
+    M.set_msm_shard(0, 1)
+    q.put((rank, hashlib.sha256(proof).hexdigest(), hashlib.sha256(M.vk_serialize(vk)).hexdigest()))
+    dist.destroy_process_group()
+
+
+def test_sharded_proving_world2_gives_the_single_process_proof():
+    """Multi-process proving (the CPU-arm mirror of swb_set_msm_shard): two gloo ranks run the same prover,
+    every commit / open MSM is split by index range and the partial results are all-gathered and summed
+    by libswb200 -- both ranks must produce the committed single-process proof and verifying key."""
+    import json
+    from simpleworks_b200 import build
+    build.build()
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "marlin_proofs.json")))["cases"]["mul_chain_20"]
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_prove_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, ph, vh in res:
+        assert ph == case["proof_sha256"] and vh == case["vk_sha256"]
+
+
 def test_shard_range_covers_everything():
     from simpleworks_b200.binding import shard_range
     for n in (0, 1, 7, 8, 1 << 20):
