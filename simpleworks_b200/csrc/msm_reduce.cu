@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_gather(G1Xyzz* __restr
 }
 
 // heavy buckets: one block per bucket, strided sums then a shared-memory tree
-__global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_gather_heavy(G1Xyzz* __restrict__ buckets,
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_gather_heavy(G1Xyzz* __restrict__ buckets,
                                                                        const G1Xyzz* __restrict__ partial,
                                                                        const uint32_t* __restrict__ pstart,
                                                                        const uint32_t* __restrict__ heavy) {
@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_gather_heavy(G1Xyzz* _
         const uint32_t b = heavy[1 + h];
         const uint32_t p0 = pstart[b], p1 = pstart[b + 1];
         G1Xyzz acc = G1Xyzz::identity();
-        for (uint32_t p = p0 + t; p < p1; p += MSM_TAIL_THREADS) acc.add(partial[p]);
+        for (uint32_t p = p0 + t; p < p1; p += MSM_HEAVY_THREADS) acc.add(partial[p]);
         buf[t] = acc;
         __syncthreads();
-        for (uint32_t d = MSM_TAIL_THREADS >> 1; d > 0; d >>= 1) {
+        for (uint32_t d = MSM_HEAVY_THREADS >> 1; d > 0; d >>= 1) {
             if (t < d) {
                 G1Xyzz a = buf[t];
                 a.add(buf[t + d]);
@@ -156,8 +156,9 @@ int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     SWB_LAUNCH_CHECK(c, "k_msm_partial_bounds");
     k_msm_gather<<<(pl.nb + MSM_TAIL_THREADS - 1) / MSM_TAIL_THREADS, MSM_TAIL_THREADS, 0, c->stream>>>(bf.buckets, bf.partial, bf.pstart, pl.nb, bf.heavy);
     SWB_LAUNCH_CHECK(c, "k_msm_gather");
-    const size_t smem = MSM_TAIL_THREADS * sizeof(G1Xyzz);
-    k_msm_gather_heavy<<<c->sm_count * 4, MSM_TAIL_THREADS, smem, c->stream>>>(bf.buckets, bf.partial, bf.pstart, bf.heavy);
+    const size_t smem = MSM_HEAVY_THREADS * sizeof(G1Xyzz);
+    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_gather_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_msm_gather_heavy<<<c->sm_count, MSM_HEAVY_THREADS, smem, c->stream>>>(bf.buckets, bf.partial, bf.pstart, bf.heavy);
     SWB_LAUNCH_CHECK(c, "k_msm_gather_heavy");
     return SWB_OK;
 }
