@@ -125,9 +125,14 @@ def marlin_gpu_run(be, lg, proofs):
     for _ in range(proofs + 1):
         ta = time.perf_counter(); proof = m.generate_proof(cs, pk, Rng()); ts.append(time.perf_counter() - ta)
     tune_s = ts[0] - min(ts[1:])
+    m.profile(True)                      # one more proof for the per-phase breakdown (host wall-clock per phase)
+    m.generate_proof(cs, pk, Rng())
+    phases = m.last_phases()
+    m.profile(False)
     tv = time.perf_counter(); ok = m.verify_proof(vk, _gen.fr_mont(3), proof); tv = time.perf_counter() - tv
     return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t3 - t2, "prove_s": min(ts[1:]), "prove_s_all": ts[1:],
             "prove_s_plain_msm_path": min(ts_plain), "prove_s_plain_all": ts_plain, "srs_window_tables_build_s": tune_s,
+            "prove_phases_ms": phases,
             "prove_s_note": "prove_s: SRS powers with window tables (swb_srs_set_tune_after; automatic after ~20 proofs), "
                             "prove_s_plain_msm_path: before them",
             "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts[1:]), "proof_bytes": len(proof)}, proof

@@ -206,6 +206,13 @@ int  swb_r1cs_set_assignment(swb_r1cs*, const swb_fr* instance, size_t ni, const
 int  swb_r1cs_is_satisfied(const swb_r1cs*);
 void swb_r1cs_free(swb_r1cs*);
 
+/* Host-side phase times of the protocol calls (process-wide): after swb_marlin_profile_enable(1) every
+ * swb_marlin_index / swb_marlin_prove leaves "<call>: phase=milliseconds ..." (wall-clock time the host
+ * spent in each phase -- msm and ntt are nested inside the round phases; GPU work is asynchronous, so a
+ * phase also pays for what was queued before it) for swb_marlin_last_phases, which copies at most cap
+ * bytes including the terminator and returns the size needed. */
+int    swb_marlin_profile_enable(int enable);
+size_t swb_marlin_last_phases(char* buf, size_t cap);
 int  swb_marlin_universal_setup(swb_ctx*, size_t num_constraints, size_t num_variables, size_t num_non_zero,
                                 swb_rng*, swb_srs** out);
 size_t swb_srs_max_degree(const swb_srs*);

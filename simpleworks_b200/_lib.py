@@ -29,7 +29,7 @@ SYMBOLS = [
     "swb_rng_test_rng", "swb_rng_next_u64", "swb_rng_free",
     "swb_r1cs_new", "swb_r1cs_builtin", "swb_r1cs_add_constraint", "swb_r1cs_set_assignment", "swb_r1cs_is_satisfied",
     "swb_r1cs_free",
-    "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_set_tune_after", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
+    "swb_marlin_profile_enable", "swb_marlin_last_phases", "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_set_tune_after", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
     "swb_marlin_prove", "swb_marlin_verify", "swb_bytes_free",
     "swb_vk_serialize", "swb_vk_deserialize", "swb_r1cs_read", "swb_r1cs_write",
 ]
@@ -75,6 +75,8 @@ def load() -> ctypes.CDLL:
         "swb_bases_load": (i32, [vp, vp, sz, pvp]),
         "swb_bases_load_dev": (i32, [vp, vp, sz, pvp]),
         "swb_srs_set_tune_after": (i32, [vp, ctypes.c_long]),
+        "swb_marlin_profile_enable": (i32, [i32]),
+        "swb_marlin_last_phases": (sz, [ctypes.c_char_p, sz]),
         "swb_bases_precompute": (i32, [vp, vp, i32]),
         "swb_bases_table_info": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
         "swb_bases_len": (sz, [vp]),

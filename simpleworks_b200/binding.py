@@ -410,6 +410,21 @@ class Marlin:
     def srs_max_degree(self, srs) -> int:
         return int(self._lib.swb_srs_max_degree(srs))
 
+    def profile(self, on: bool = True):
+        self._lib.swb_marlin_profile_enable(int(on))
+
+    def last_phases(self) -> dict:
+        """host-side phase times (ms) of the most recent index / prove call, see swb_marlin_last_phases"""
+        buf = ctypes.create_string_buffer(4096)
+        self._lib.swb_marlin_last_phases(buf, 4096)
+        text = buf.value.decode()
+        what, _, rest = text.partition(":")
+        out = {"call": what}
+        for item in rest.split():
+            k, _, v = item.partition("=")
+            out[k] = float(v)
+        return out
+
     def srs_set_tune_after(self, srs, n_msms: int):
         """After n_msms commit/open MSMs the SRS powers get window tables (0 = never, 1 = at once)."""
         self.be._check(self._lib.swb_srs_set_tune_after(srs, n_msms))

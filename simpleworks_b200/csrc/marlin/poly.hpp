@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 
@@ -22,13 +23,20 @@ namespace marlin {
 // SWB_TRACE=1: wall-clock breakdown of the host protocol code by phase (stderr)
 struct HostProfile {
     std::map<std::string, double> acc;
-    bool on = false;
-    HostProfile() { const char* e = getenv("SWB_TRACE"); on = e && atoi(e) > 0; }
+    bool on = false;        // phases are being accumulated
+    bool print = false;     // SWB_TRACE: each report goes to stderr
+    std::string last;       // "<what>: name=ms name=ms ..." of the most recent report
+    HostProfile() { const char* e = getenv("SWB_TRACE"); on = print = e && atoi(e) > 0; }
     void report(const char* what) {
         if (!on) return;
-        fprintf(stderr, "[swb trace] %s host phases:", what);
-        for (auto& kv : acc) fprintf(stderr, " %s=%.1fms", kv.first.c_str(), kv.second * 1e3);
-        fprintf(stderr, "\n");
+        last = what;
+        last += ":";
+        char buf[96];
+        for (auto& kv : acc) {
+            snprintf(buf, sizeof buf, " %s=%.3f", kv.first.c_str(), kv.second * 1e3);
+            last += buf;
+        }
+        if (print) fprintf(stderr, "[swb trace] %s host phases (ms)%s\n", what, last.c_str() + strlen(what) + 1);
         acc.clear();
     }
 };

@@ -450,6 +450,22 @@ void swb_r1cs_free(swb_r1cs* cs) {
     delete cs;
 }
 
+int swb_marlin_profile_enable(int enable) {
+    HostProfile& hp = host_profile();
+    hp.on = enable != 0 || hp.print;
+    if (!hp.on) hp.acc.clear();
+    return SWB_OK;
+}
+size_t swb_marlin_last_phases(char* buf, size_t cap) {
+    const std::string& s = host_profile().last;
+    if (buf && cap) {
+        const size_t k = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return s.size() + 1;
+}
+
 int swb_marlin_universal_setup(swb_ctx* c, size_t nc, size_t nv, size_t nnz, swb_rng* rng, swb_srs** out) {
     if (!c || !rng || !out) return SWB_EARG;
     auto* s = new swb_srs{GpuEngine(c), nullptr};
