@@ -734,14 +734,15 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, const R1cs& cs, ChaChaRng
     // the assignment after pad_input_for_indexer_and_prover + make_matrices_square (the matrices
     // themselves live in the proving key): instance padded with zeros to a power of two, dummy
     // witnesses of value one when there are more constraints than variables
-    std::vector<Fr> instance = cs.instance, witness = cs.witness;
+    std::vector<Fr> instance = cs.instance;                // small; the witness is used where it lies
+    size_t dummy_witnesses = 0;
     {
         size_t target = 1;
         while (target < instance.size()) target <<= 1;
         instance.resize(target, Fr::zero());
-        size_t nv = instance.size() + witness.size(), nc = cs.num_constraints();
+        size_t nv = instance.size() + cs.witness.size(), nc = cs.num_constraints();
         if (nc < nv) nc = nv;
-        else if (nv < nc) { witness.resize(witness.size() + (nc - nv), Fr::one()); nv = nc; }
+        else if (nv < nc) { dummy_witnesses = nc - nv; nv = nc; }
         if (nv != pk.info.num_variables || nc != pk.info.num_constraints || instance.size() != pk.info.num_instance)
             throw MarlinError("prove: constraint system does not match the proving key");
     }
@@ -768,9 +769,15 @@ Proof prove(Engine& eng, const ProvingKey<Engine>& pk, const R1cs& cs, ChaChaRng
     // ---- init: z_A = A z, z_B = B z on the engine (prover_init) ------------------------------------
     Vec z_vec;
     {
-        std::vector<Fr> z = instance;
-        z.insert(z.end(), witness.begin(), witness.end());
-        z_vec = eng.vfrom(z);
+        // z = (instance | witness | dummy witnesses = 1): uploaded part by part, no concatenated host copy
+        const size_t ni = instance.size(), nw = cs.witness.size();
+        z_vec = eng.vzeros(ni + nw + dummy_witnesses);
+        eng.vwrite(z_vec, 0, instance.data(), ni);
+        eng.vwrite(z_vec, ni, cs.witness.data(), nw);
+        if (dummy_witnesses) {
+            const std::vector<Fr> ones(dummy_witnesses, Fr::one());
+            eng.vwrite(z_vec, ni + nw, ones.data(), dummy_witnesses);
+        }
     }
     Vec za_ev = eng.vspmv(pk.m_a, z_vec, nh, nullptr), zb_ev = eng.vspmv(pk.m_b, z_vec, nh, nullptr);
     {

@@ -15,6 +15,7 @@ struct HostVecOps {
     Vec vzeros(size_t n) { return Vec(n, Fr::zero()); }
     Vec vfrom(const std::vector<Fr>& h) { return h; }
     Vec vfrom_ptr(const Fr* p, size_t n) { return Vec(p, p + n); }
+    void vwrite(Vec& v, size_t at, const Fr* p, size_t n) { std::copy(p, p + n, v.begin() + at); }   // v[at .. at+n) = p
     std::vector<Fr> vhost(const Vec& v) { return v; }
     Vec vclone(const Vec& v) { return v; }
     void vresize(Vec& v, size_t n) { v.resize(n, Fr::zero()); }

@@ -101,6 +101,14 @@ struct GpuEngine {
         }
         return v;
     }
+    void vwrite(Vec& v, size_t at, const Fr* h, size_t n) {
+        OpTimer ot_(c, "vwrite");
+        if (at + n > v.n) throw MarlinError("vwrite: range out of bounds");
+        if (n) {
+            cu(cudaMemcpyAsync(v.p + at, h, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream), "H2D");
+            cu(cudaStreamSynchronize(c->stream), "sync");     // h may be a temporary
+        }
+    }
     std::vector<Fr> vhost(const Vec& v) {
         OpTimer ot_(c, "vhost");
         std::vector<Fr> h(v.n);
