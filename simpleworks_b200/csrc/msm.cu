@@ -13,7 +13,8 @@
 //   4. k_msm_accumulate     one thread per range: XYZZ += +-base (mixed additions), one partial
 //                           sum per run of equal bucket ids -- work per thread is bounded whatever
 //                           the scalar distribution
-//   5. k_msm_gather(_heavy) partial sums of one bucket -> the bucket
+//   5. k_msm_gather (+ k_msm_heavy_chunks / k_msm_heavy_finish for buckets with many partial sums)
+//                           partial sums of one bucket -> the bucket
 //   6. k_msm_segments / k_msm_bit_sums / k_msm_bit_tree / k_msm_bit_final
 //                           sum_k k * B_k per bucket set: running sums per segment, then plain sums
 //                           selected by the bits of the segment index, reduced as trees

@@ -9,6 +9,7 @@ constexpr int MSM_MAX_WINDOWS = 128;
 // block size of the heavy-bucket gather: a bucket that holds a large share of all points (scalars equal to
 // one, top window) has one partial sum per range, i.e. up to ~10^5 of them, summed by one block
 constexpr int MSM_HEAVY_THREADS = 256;
+constexpr int MSM_HEAVY_CHUNK = 4096;  // partial sums of a heavy bucket that one block adds up
 // block size of the other bucket-tail kernels (gather, segments, bit sums): small enough (64 x <= 170
 // registers) to fit beside two resident blocks of another MSM's accumulation kernel, so the tail of one
 // MSM really runs under the accumulation of the next

@@ -37,31 +37,66 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_gather(G1Xyzz* __restr
     buckets[b] = acc;
 }
 
-// heavy buckets: one block per bucket, strided sums then a shared-memory tree
-__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_gather_heavy(G1Xyzz* __restrict__ buckets,
+// heavy buckets (more than MSM_GATHER_INLINE partial sums; a bucket that holds a large share of all points
+// has one per range, i.e. up to ~10^5): two stages.  Stage 1 cuts every heavy bucket's partial sums into
+// chunks of MSM_HEAVY_CHUNK, one block per chunk (strided sums, then a shared-memory tree) -> chunk sums;
+// stage 2 adds the chunk sums of a bucket.  Every block walks the (short) heavy list itself to find where a
+// bucket's chunks start, so no scan is needed.
+__device__ __forceinline__ G1Xyzz block_sum(G1Xyzz* buf, const G1Xyzz* __restrict__ src, uint32_t lo, uint32_t hi) {
+    const uint32_t t = threadIdx.x;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t p = lo + t; p < hi; p += MSM_HEAVY_THREADS) acc.add(src[p]);
+    buf[t] = acc;
+    __syncthreads();
+    for (uint32_t d = MSM_HEAVY_THREADS >> 1; d > 0; d >>= 1) {
+        if (t < d) {
+            G1Xyzz a = buf[t];
+            a.add(buf[t + d]);
+            buf[t] = a;
+        }
+        __syncthreads();
+    }
+    const G1Xyzz r = buf[0];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_heavy_chunks(G1Xyzz* __restrict__ chunk_sum,
                                                                        const G1Xyzz* __restrict__ partial,
                                                                        const uint32_t* __restrict__ pstart,
                                                                        const uint32_t* __restrict__ heavy) {
     extern __shared__ unsigned char smem_raw[];
     G1Xyzz* buf = reinterpret_cast<G1Xyzz*>(smem_raw);
-    const uint32_t nheavy = heavy[0], t = threadIdx.x;
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    const uint32_t nheavy = heavy[0];
+    uint32_t first = 0;                                   // index of the bucket's first chunk
+    for (uint32_t h = 0; h < nheavy; h++) {
         const uint32_t b = heavy[1 + h];
         const uint32_t p0 = pstart[b], p1 = pstart[b + 1];
-        G1Xyzz acc = G1Xyzz::identity();
-        for (uint32_t p = p0 + t; p < p1; p += MSM_HEAVY_THREADS) acc.add(partial[p]);
-        buf[t] = acc;
-        __syncthreads();
-        for (uint32_t d = MSM_HEAVY_THREADS >> 1; d > 0; d >>= 1) {
-            if (t < d) {
-                G1Xyzz a = buf[t];
-                a.add(buf[t + d]);
-                buf[t] = a;
-            }
-            __syncthreads();
+        const uint32_t nch = (p1 - p0 + MSM_HEAVY_CHUNK - 1) / MSM_HEAVY_CHUNK;
+        // chunks are dealt round-robin over the grid, continuing across buckets
+        for (uint32_t j = (blockIdx.x + gridDim.x - first % gridDim.x) % gridDim.x; j < nch; j += gridDim.x) {
+            const uint32_t lo = p0 + j * MSM_HEAVY_CHUNK, hi = lo + MSM_HEAVY_CHUNK < p1 ? lo + MSM_HEAVY_CHUNK : p1;
+            const G1Xyzz r = block_sum(buf, partial, lo, hi);
+            if (threadIdx.x == 0) chunk_sum[first + j] = r;
         }
-        if (t == 0) buckets[b] = buf[0];
-        __syncthreads();
+        first += nch;
+    }
+}
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_heavy_finish(G1Xyzz* __restrict__ buckets,
+                                                                       const G1Xyzz* __restrict__ chunk_sum,
+                                                                       const uint32_t* __restrict__ pstart,
+                                                                       const uint32_t* __restrict__ heavy) {
+    extern __shared__ unsigned char smem_raw[];
+    G1Xyzz* buf = reinterpret_cast<G1Xyzz*>(smem_raw);
+    const uint32_t nheavy = heavy[0];
+    uint32_t first = 0;
+    for (uint32_t h = 0; h < nheavy; h++) {
+        const uint32_t b = heavy[1 + h];
+        const uint32_t nch = (pstart[b + 1] - pstart[b] + MSM_HEAVY_CHUNK - 1) / MSM_HEAVY_CHUNK;
+        if (h % gridDim.x == blockIdx.x) {
+            const G1Xyzz r = block_sum(buf, chunk_sum, first, first + nch);
+            if (threadIdx.x == 0) buckets[b] = r;
+        }
+        first += nch;
     }
 }
 
@@ -156,10 +191,18 @@ int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     SWB_LAUNCH_CHECK(c, "k_msm_partial_bounds");
     k_msm_gather<<<(pl.nb + MSM_TAIL_THREADS - 1) / MSM_TAIL_THREADS, MSM_TAIL_THREADS, 0, c->stream>>>(bf.buckets, bf.partial, bf.pstart, pl.nb, bf.heavy);
     SWB_LAUNCH_CHECK(c, "k_msm_gather");
+    // chunk sums: at most pcap / MSM_HEAVY_CHUNK full chunks plus one partly filled chunk per heavy bucket
+    // (a heavy bucket has > MSM_GATHER_INLINE partial sums, so there are fewer than pcap / MSM_GATHER_INLINE)
+    const size_t max_chunks = (size_t)pl.pcap / MSM_HEAVY_CHUNK + (size_t)pl.pcap / MSM_GATHER_INLINE + 2;
+    G1Xyzz* chunk_sum = (G1Xyzz*)get_scratch(c, "msm_heavy_chunks", max_chunks * sizeof(G1Xyzz));
+    if (!chunk_sum) return SWB_ENOMEM;
     const size_t smem = MSM_HEAVY_THREADS * sizeof(G1Xyzz);
-    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_gather_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_msm_gather_heavy<<<c->sm_count, MSM_HEAVY_THREADS, smem, c->stream>>>(bf.buckets, bf.partial, bf.pstart, bf.heavy);
-    SWB_LAUNCH_CHECK(c, "k_msm_gather_heavy");
+    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_heavy_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SWB_CUDA(c, cudaFuncSetAttribute(k_msm_heavy_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_msm_heavy_chunks<<<c->sm_count * 2, MSM_HEAVY_THREADS, smem, c->stream>>>(chunk_sum, bf.partial, bf.pstart, bf.heavy);
+    SWB_LAUNCH_CHECK(c, "k_msm_heavy_chunks");
+    k_msm_heavy_finish<<<c->sm_count, MSM_HEAVY_THREADS, smem, c->stream>>>(bf.buckets, chunk_sum, bf.pstart, bf.heavy);
+    SWB_LAUNCH_CHECK(c, "k_msm_heavy_finish");
     return SWB_OK;
 }
 
