@@ -66,7 +66,7 @@ static int pick_window(swb_ctx* c, size_t n) {
     while (((size_t)1 << lg) < n) lg++;
     // measured on B200 (tools/msm_sweep.py, profiles/r1_msm_window_sweep.json): best signed-window width
     // per log2(n); small sizes are launch-latency bound and flat in c
-    static const int best[27] = {4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 9, 9, 9, 9, 9, 9, 9, 10, 10, 13, 15, 16, 17, 18, 19, 19, 20};
+    static const int best[27] = {4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 8, 9, 11, 11, 11, 11, 11, 11, 15, 15, 15, 16, 17, 18, 19, 19, 20};
     return lg <= 26 ? best[lg] : 20;
 }
 
