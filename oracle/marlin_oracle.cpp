@@ -218,6 +218,16 @@ int orc_pairing_selftest() {
     if (!(e.pow_words(rw, 8) == Fq12::one())) bad |= 256;
     if (!pairing_product_is_one({{g1_mul_fr(g, a), h}, {g1_neg(g), g2_mul_fr(h, a)}})) bad |= 512;
     if (pairing_product_is_one({{g1_mul_fr(g, a), h}, {g1_neg(g), g2_mul_fr(h, b)}})) bad |= 1024;
+    // Frobenius is the q-th power; the fast final exponentiation is the cube of the plain one
+    uint32_t qw[12];
+    for (int i = 0; i < 12; i++) qw[i] = FqParams::mod(i);
+    if (!(frobenius(a12) == a12.pow_words(qw, 12))) bad |= 2048;
+    if (!(frobenius(a12, 2) == a12.pow_words(qw, 12).pow_words(qw, 12))) bad |= 4096;
+    const Fq12 ml = miller_loop(g1_mul_fr(g, a), h);
+    const Fq12 plain = final_exponentiation_plain(ml);
+    if (!(final_exponentiation(ml) == plain * plain * plain)) bad |= 8192;
+    const Fq12 plain2 = final_exponentiation_plain(a12);
+    if (!(final_exponentiation(a12) == plain2 * plain2 * plain2)) bad |= 16384;
     return bad;
 }
 

@@ -7,8 +7,9 @@
 //   G2   : y^2 = x^3 - u/5 over Fq2 (D-type sextic twist), cofactor derived in tools/gen_constants.py
 // The pairing is the ate pairing f_{x,Q}(P)^((q^12-1)/r), x = 0x8508c00000000001, computed the plain
 // way: Q is mapped to E(Fq12) through the untwisting map (x', y') -> (x' w^2, y' w^3) and the Miller
-// loop runs in affine coordinates over Fq12 with a generic final exponentiation.  That is slow
-// (tens of milliseconds) but has no curve-specific line formulas to get wrong; verification checks
+// loop runs in affine coordinates over Fq12; the final exponentiation uses the BLS12 decomposition
+// (checked against the plain 2009-bit exponentiation).  The affine Miller loop is slow (milliseconds)
+// but has no curve-specific line formulas to get wrong; verification checks
 // pairing *equations*, for which any bilinear non-degenerate pairing gives the same verdict as
 // arkworks' optimised one.  Verify is milliseconds either way and stays off the GPU.
 #pragma once
@@ -37,9 +38,18 @@ struct Fq2 {
     Fq2 operator-(const Fq2& o) const { return {c0 - o.c0, c1 - o.c1}; }
     Fq2 neg() const { return {c0.neg(), c1.neg()}; }
     static Fq mul5(const Fq& a) { Fq t = a.dbl().dbl(); return t + a; }
-    Fq2 operator*(const Fq2& o) const {                     // u^2 = -5
-        Fq a = c0 * o.c0, b = c1 * o.c1;
-        return {a - mul5(b), c0 * o.c1 + c1 * o.c0};
+    Fq2 operator*(const Fq2& o) const {                     // u^2 = -5; Karatsuba: 3 Fq products
+        const Fq a = c0 * o.c0, b = c1 * o.c1;
+        return {a - mul5(b), (c0 + c1) * (o.c0 + o.c1) - a - b};
+    }
+    Fq2 conj() const { return {c0, c1.neg()}; }             // the q-power Frobenius (u^q = -u)
+    Fq2 pow_words(const uint32_t* e, int nwords) const {
+        Fq2 acc = one();
+        for (int i = nwords * 32 - 1; i >= 0; i--) {
+            acc = acc.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1u) acc = acc * (*this);
+        }
+        return acc;
     }
     Fq2 sqr() const { return (*this) * (*this); }
     Fq2 scale(const Fq& s) const { return {c0 * s, c1 * s}; }
@@ -60,13 +70,14 @@ struct Fq6 {
     Fq6 operator+(const Fq6& o) const { return {c0 + o.c0, c1 + o.c1, c2 + o.c2}; }
     Fq6 operator-(const Fq6& o) const { return {c0 - o.c0, c1 - o.c1, c2 - o.c2}; }
     Fq6 neg() const { return {c0.neg(), c1.neg(), c2.neg()}; }
-    Fq6 operator*(const Fq6& o) const {                     // v^3 = u
-        Fq2 t0 = c0 * o.c0, t1 = c1 * o.c1, t2 = c2 * o.c2;
-        Fq2 r0 = t0 + (c1 * o.c2 + c2 * o.c1).mul_by_u();
-        Fq2 r1 = c0 * o.c1 + c1 * o.c0 + t2.mul_by_u();
-        Fq2 r2 = c0 * o.c2 + t1 + c2 * o.c0;
+    Fq6 operator*(const Fq6& o) const {                     // v^3 = u; Karatsuba: 6 Fq2 products
+        const Fq2 t0 = c0 * o.c0, t1 = c1 * o.c1, t2 = c2 * o.c2;
+        const Fq2 r0 = t0 + ((c1 + c2) * (o.c1 + o.c2) - t1 - t2).mul_by_u();
+        const Fq2 r1 = (c0 + c1) * (o.c0 + o.c1) - t0 - t1 + t2.mul_by_u();
+        const Fq2 r2 = (c0 + c2) * (o.c0 + o.c2) - t0 - t2 + t1;
         return {r0, r1, r2};
     }
+    Fq6 scale2(const Fq2& s) const { return {c0 * s, c1 * s, c2 * s}; }
     Fq6 mul_by_v() const { return {c2.mul_by_u(), c0, c1}; }
     Fq6 inverse() const {
         Fq2 t0 = c0.sqr() - (c1 * c2).mul_by_u();
@@ -87,10 +98,11 @@ struct Fq12 {
     bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
     Fq12 operator+(const Fq12& o) const { return {c0 + o.c0, c1 + o.c1}; }
     Fq12 operator-(const Fq12& o) const { return {c0 - o.c0, c1 - o.c1}; }
-    Fq12 operator*(const Fq12& o) const {                   // w^2 = v
-        Fq6 a = c0 * o.c0, b = c1 * o.c1;
-        return {a + b.mul_by_v(), c0 * o.c1 + c1 * o.c0};
+    Fq12 operator*(const Fq12& o) const {                   // w^2 = v; Karatsuba: 3 Fq6 products
+        const Fq6 a = c0 * o.c0, b = c1 * o.c1;
+        return {a + b.mul_by_v(), (c0 + c1) * (o.c0 + o.c1) - a - b};
     }
+    Fq12 conj() const { return {c0, c1.neg()}; }            // the q^6-power Frobenius
     Fq12 sqr() const { return (*this) * (*this); }
     Fq12 inverse() const {
         Fq6 d = (c0 * c0 - (c1 * c1).mul_by_v()).inverse();
@@ -270,12 +282,95 @@ inline Fq12 miller_loop(const G1Point& p, const G2Point& q) {
     }
     return f;
 }
-// f^((q^12 - 1)/r) = (conj(f) / f)^((q^6 + 1)/r): conjugation over Fq6 is the q^6-power Frobenius
-inline Fq12 final_exponentiation(const Fq12& f) {
+// ---- Frobenius on the tower --------------------------------------------------------------------
+// x -> x^q.  On Fq2 it is conjugation; v^q = v * u^((q-1)/3) and w^q = w * u^((q-1)/6), so on Fq6 / Fq12
+// it conjugates the Fq2 coefficients and scales them by powers of those two constants, which are
+// computed once from the modulus.
+struct FrobeniusCtx {
+    Fq2 g1, g2, d;          // u^((q-1)/3), its square, u^((q-1)/6)
+    FrobeniusCtx() {
+        uint32_t qm1[12], e3[12], e6[12];
+        for (int i = 0; i < 12; i++) qm1[i] = FqParams::mod(i);
+        qm1[0] -= 1;
+        div_small(e3, qm1, 3);
+        div_small(e6, qm1, 6);
+        const Fq2 u = {Fq::zero(), Fq::one()};
+        g1 = u.pow_words(e3, 12);
+        g2 = g1 * g1;
+        d = u.pow_words(e6, 12);
+    }
+    static void div_small(uint32_t* out, const uint32_t* in, uint32_t k) {       // exact division of 12 limbs
+        uint64_t rem = 0;
+        for (int i = 11; i >= 0; i--) {
+            const uint64_t cur = (rem << 32) | in[i];
+            out[i] = (uint32_t)(cur / k);
+            rem = cur % k;
+        }
+    }
+};
+inline const FrobeniusCtx& frobenius_ctx() {
+    static const FrobeniusCtx c;
+    return c;
+}
+inline Fq6 frobenius6(const Fq6& a) {
+    const FrobeniusCtx& c = frobenius_ctx();
+    return {a.c0.conj(), a.c1.conj() * c.g1, a.c2.conj() * c.g2};
+}
+inline Fq12 frobenius(const Fq12& a, int power = 1) {
+    Fq12 r = a;
+    for (int k = 0; k < power; k++) r = {frobenius6(r.c0), frobenius6(r.c1).scale2(frobenius_ctx().d)};
+    return r;
+}
+
+// f^((q^12 - 1)/r), the plain way: (conj(f) / f)^((q^6 + 1)/r) -- conjugation over Fq6 is the q^6-power
+// Frobenius.  3000 Fq12 products; kept as the reference the fast version is checked against.
+inline Fq12 final_exponentiation_plain(const Fq12& f) {
     static const uint32_t e[SWB_FINAL_EXP_WORDS] = SWB_FINAL_EXP_INIT;
-    Fq12 conj = {f.c0, f.c1.neg()};
-    Fq12 g = conj * f.inverse();
+    Fq12 g = f.conj() * f.inverse();
     return g.pow_words(e, SWB_FINAL_EXP_WORDS);
+}
+inline Fq12 exp_by_x(const Fq12& f) {                       // f^x, x = 0x8508c00000000001 (positive)
+    const uint64_t x = SWB_BLS_X;
+    Fq12 acc = f;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) {
+        acc = acc.sqr();
+        if ((x >> i) & 1) acc = acc * f;
+    }
+    return acc;
+}
+// The BLS12 decomposition (easy part by Frobenius, hard part as in Fuentes-Castaneda, Knapp, Rodriguez-
+// Henriquez, "Faster hashing to G2", the schedule ark-ec 0.3 bls12/mod.rs uses): five exponentiations by
+// the 64-bit x instead of one by a 2009-bit number.  It returns the CUBE of final_exponentiation_plain
+// (the hard part is raised to 3 (q^4 - q^2 + 1) / r); 3 is prime to r, so "== 1" tests and equalities
+// between values computed this way are unaffected.  orc_pairing_selftest checks exactly that relation.
+inline Fq12 final_exponentiation(const Fq12& f) {
+    Fq12 r = f.conj() * f.inverse();                        // f^(q^6 - 1)
+    r = frobenius(r, 2) * r;                                // ^(q^2 + 1): now in the cyclotomic subgroup, inverse = conj
+    Fq12 y0 = r.sqr().conj();
+    Fq12 y5 = exp_by_x(r);
+    Fq12 y1 = y5.sqr();
+    Fq12 y3 = y0 * y5;
+    y0 = exp_by_x(y3);
+    const Fq12 y2 = exp_by_x(y0);
+    Fq12 y4 = exp_by_x(y2);
+    y4 = y4 * y1;
+    y1 = exp_by_x(y4);
+    y3 = y3.conj();
+    y1 = y1 * y3;
+    y1 = y1 * r;
+    y3 = r.conj();
+    y0 = y0 * r;
+    y0 = frobenius(y0, 3);
+    y4 = y4 * y3;
+    y4 = frobenius(y4, 1);
+    y5 = y5 * y2;
+    y5 = frobenius(y5, 2);
+    y5 = y5 * y0;
+    y5 = y5 * y4;
+    y5 = y5 * y1;
+    return y5;
 }
 inline Fq12 pairing(const G1Point& p, const G2Point& q) { return final_exponentiation(miller_loop(p, q)); }
 // prod_i e(P_i, Q_i) == 1 ?
