@@ -172,3 +172,55 @@ def test_general_shape_circuit_prove_verify():
     # the SWBR1CS1 round trip keeps it provable
     cs2 = M.R1cs.from_bytes(cs.to_bytes())
     assert M.prove(pk, cs2, M.Rng()) == M.prove(pk, cs, M.Rng())
+
+
+def test_corrupted_proofs_and_keys_are_rejected_not_crashed(toy_srs):
+    """Every sampled single-bit flip and every truncation of a valid proof is rejected (never accepted,
+    never a crash); corrupted verifying-key bytes either fail to parse or stop verifying."""
+    srs, rng = toy_srs
+    cs = M.R1cs("manual", v0=1, v1=1)
+    pk, vk = M.index(srs, cs)
+    proof = M.prove(pk, cs, rng)
+    pub = O.fr_mont([1])
+    assert M.verify(vk, pub, proof)
+    rs = np.random.RandomState(11)
+    for pos in rs.choice(len(proof), 40, replace=False):
+        bad = bytearray(proof)
+        bad[int(pos)] ^= 1 << int(rs.randint(8))
+        assert not M.verify(vk, pub, bytes(bad)), int(pos)
+    for cut in (0, 1, 7, 8, 100, len(proof) - 48, len(proof) - 1):
+        assert not M.verify(vk, pub, proof[:cut])
+    assert not M.verify(vk, pub, proof + b"\x00")
+    vkb = M.vk_serialize(vk)
+    for pos in rs.choice(len(vkb), 12, replace=False):
+        bad = bytearray(vkb)
+        bad[int(pos)] ^= 0x04
+        try:
+            vk2 = M.vk_deserialize(bytes(bad))
+        except M.MarlinError:
+            continue
+        assert not M.verify(vk2, pub, proof), int(pos)
+
+
+def test_r1cs_reader_rejects_malformed_input():
+    """SWBR1CS1 (swb_r1cs_read / the CPU arm's reader): truncations, a wrong magic, out-of-range columns and
+    non-canonical field elements are refused instead of read."""
+    cs = M.R1cs("random_sparse", size=12, v0=3, v1=9)
+    good = cs.to_bytes()
+    assert M.R1cs.from_bytes(good).is_satisfied()
+    for cut in list(range(0, 40)) + [len(good) // 2, len(good) - 1]:
+        with pytest.raises(M.MarlinError):
+            M.R1cs.from_bytes(good[:cut])
+    with pytest.raises(M.MarlinError):
+        M.R1cs.from_bytes(b"SWBR1CS2" + good[8:])
+    with pytest.raises(M.MarlinError):
+        M.R1cs.from_bytes(good + b"\x00")
+    bad = bytearray(good)
+    first_entry = 8 + 24 + 8                       # magic, three counts, nnz of the first row
+    bad[first_entry + 32:first_entry + 40] = (10 ** 6).to_bytes(8, "little")   # column out of range
+    with pytest.raises(M.MarlinError):
+        M.R1cs.from_bytes(bytes(bad))
+    bad = bytearray(good)
+    bad[first_entry:first_entry + 32] = b"\xff" * 32                           # coefficient >= r
+    with pytest.raises(M.MarlinError):
+        M.R1cs.from_bytes(bytes(bad))
