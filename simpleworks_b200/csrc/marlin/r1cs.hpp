@@ -210,6 +210,7 @@ inline bool r1cs_read(const uint8_t* p, size_t len, R1cs* cs) {
     uint64_t ni, nw, nc;
     if (!get_u64(p, end, &ni) || !get_u64(p, end, &nw) || !get_u64(p, end, &nc) || ni == 0) return false;
     if (nc > ((uint64_t)1 << 32) || ni + nw > ((uint64_t)1 << 32)) return false;
+    if (nc > len / 24) return false;          // every constraint needs at least three 8-byte row lengths
     *cs = R1cs();
     cs->num_instance = (size_t)ni;
     cs->num_witness = (size_t)nw;

@@ -215,6 +215,10 @@ def test_r1cs_reader_rejects_malformed_input():
         M.R1cs.from_bytes(b"SWBR1CS2" + good[8:])
     with pytest.raises(M.MarlinError):
         M.R1cs.from_bytes(good + b"\x00")
+    huge = bytearray(good)
+    huge[24:32] = (1 << 31).to_bytes(8, "little")  # a constraint count the data cannot possibly hold
+    with pytest.raises(M.MarlinError):
+        M.R1cs.from_bytes(bytes(huge))
     bad = bytearray(good)
     first_entry = 8 + 24 + 8                       # magic, three counts, nnz of the first row
     bad[first_entry + 32:first_entry + 40] = (10 ** 6).to_bytes(8, "little")   # column out of range
