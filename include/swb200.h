@@ -152,6 +152,10 @@ int  swb_msm_g1_batch_dev(swb_ctx*, const swb_bases*, const size_t* offsets, con
 int  swb_msm_plan(swb_ctx*, size_t n, int* window_bits, int* windows);
 /* window width override for tuning/tests (0 = automatic) */
 int  swb_msm_set_window_bits(swb_ctx*, int c);
+/* which path MSMs over bases with window tables take: 0 = automatic (the rule above), 1 = the table
+ * path whatever n is, -1 = the plain path on level 0.  Results are identical; tests and bench.py use it
+ * to compare the two paths on the same input. */
+int  swb_msm_set_table_policy(swb_ctx*, int policy);
 /* sum of n Jacobian points on the host side of the ABI (combining per-GPU partial MSMs); pure
  * host arithmetic, ctx may be NULL */
 int  swb_g1_sum_jacobian(swb_ctx*, const swb_g1_jacobian* pts_host, size_t n, swb_g1_jacobian* out_host);

@@ -110,6 +110,29 @@ class R1cs:
         k = {"manual": 0, "uint8_eq": 1, "chain": 2, "random_sparse": 3}[kind]
         self.h = ctypes.c_void_p(lib().orc_r1cs_builtin(k, size, v0, v1))
 
+    @classmethod
+    def custom(cls, num_instance: int, num_witness: int, constraints, instance, witness) -> "R1cs":
+        """a constraint system given as python integers: constraints = [(a_row, b_row, c_row)] with rows
+        [(coefficient, column)], assignment values mod r (instance[0] must be 1)"""
+        from oracle import pyoracle as O
+        L = lib()
+        obj = cls.__new__(cls)
+        obj.h = ctypes.c_void_p(L.orc_r1cs_new(num_instance, num_witness))
+
+        def pack(row):
+            coef = O.fr_mont([k for k, _ in row]) if row else np.zeros((0, 4), np.uint64)
+            col = np.ascontiguousarray([j for _, j in row], dtype=np.uint32)
+            return coef, col
+        for ra, rb, rc in constraints:
+            (ac, ai), (bc, bi), (cc, ci) = pack(ra), pack(rb), pack(rc)
+            if L.orc_r1cs_add_constraint(obj.h, ac.ctypes.data, ai.ctypes.data, len(ra), bc.ctypes.data, bi.ctypes.data, len(rb),
+                                         cc.ctypes.data, ci.ctypes.data, len(rc)):
+                raise MarlinError("add_constraint: column out of range")
+        inst, wit = O.fr_mont(list(instance)), O.fr_mont(list(witness))
+        if L.orc_r1cs_set_assignment(obj.h, inst.ctypes.data, len(instance), wit.ctypes.data, len(witness)):
+            raise MarlinError("set_assignment: wrong sizes")
+        return obj
+
     def is_satisfied(self) -> bool:
         return bool(lib().orc_r1cs_is_satisfied(self.h))
 

@@ -260,6 +260,10 @@ class Backend:
     def set_msm_window_bits(self, c: int):
         self._check(self._lib.swb_msm_set_window_bits(self._h, c))
 
+    def set_msm_table_policy(self, policy: int):
+        """0 automatic, 1 always the window-table path when the bases have tables, -1 always the plain path"""
+        self._check(self._lib.swb_msm_set_table_policy(self._h, policy))
+
     def msm(self, bases: Bases, scalars, offset: int = 0, montgomery: bool = False) -> np.ndarray:
         """VariableBaseMSM::multi_scalar_mul(bases[offset..], scalars) -> (1,18) Jacobian with Z=1.
         scalars: (n,4) canonical BigInteger256 as numpy (host path, H2D inside the call) or CUDA

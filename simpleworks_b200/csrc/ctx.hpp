@@ -21,6 +21,7 @@ struct swb_ctx {
     std::string err;
     uint64_t launches = 0;
     int msm_window_override = 0;
+    int msm_table_policy = 0;  // swb_msm_set_table_policy: -1 never, 0 automatic, 1 whenever the bases have tables
     int trace = 0;            // SWB_TRACE=1: per-stage CUDA-event timings on stderr
     int profile = 0;          // swb_profile_enable: keep the last call's stage timings
     std::vector<std::pair<const char*, double>> last_stages;

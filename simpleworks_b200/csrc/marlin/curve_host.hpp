@@ -189,9 +189,10 @@ inline void put_u64(std::vector<uint8_t>& out, uint64_t v) {
     for (int b = 0; b < 8; b++) out.push_back((uint8_t)(v >> (8 * b)));
 }
 // ark_ff::ToBytes for GroupAffine: x || y || infinity  (97 bytes) -- the transcript format
+// (the identity is GroupAffine::zero() = (0, 1, true) in ark-ec 0.3, so its y coordinate is written as one)
 inline void put_g1_uncompressed(std::vector<uint8_t>& out, const G1Point& p) {
     put_fq_canonical(out, p.infinity ? Fq::zero() : p.x);
-    put_fq_canonical(out, p.infinity ? Fq::zero() : p.y);
+    put_fq_canonical(out, p.infinity ? Fq::one() : p.y);
     out.push_back(p.infinity ? 1 : 0);
 }
 // ark_serialize::CanonicalSerialize for GroupAffine: x with SWFlags in the top bits of the last
@@ -228,6 +229,28 @@ inline bool get_fr_canonical(const uint8_t*& p, const uint8_t* end, Fr* out) {
     p += 32;
     return true;
 }
+// 48 little-endian bytes (flag bits already cleared) -> Fq; false when the integer is >= q (ark-serialize
+// refuses non-canonical field elements)
+inline bool fq_from_canonical_bytes(const uint8_t* buf, Fq* out) {
+    Fq c;
+    for (int i = 0; i < 12; i++) c.l[i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) | ((uint32_t)buf[4 * i + 3] << 24);
+    for (int i = 11; i >= 0; i--) {
+        if (c.l[i] != FqParams::mod(i)) {
+            if (c.l[i] > FqParams::mod(i)) return false;
+            break;
+        }
+        if (i == 0) return false;
+    }
+    *out = c.from_canonical();
+    return true;
+}
+// [r]P == O: membership in the prime-order subgroup (GroupAffine::deserialize of ark-ec 0.3 checks
+// is_in_correct_subgroup_assuming_on_curve the same way)
+inline bool g1_in_subgroup(const G1Point& p) {
+    uint32_t r[8];
+    for (int i = 0; i < 8; i++) r[i] = FrParams::mod(i);
+    return g1_mul_words(p, r, 8).is_identity();
+}
 inline bool get_g1_compressed(const uint8_t*& p, const uint8_t* end, G1Point* out) {
     if (end - p < 48) return false;
     uint8_t buf[48];
@@ -235,10 +258,17 @@ inline bool get_g1_compressed(const uint8_t*& p, const uint8_t* end, G1Point* ou
     const uint8_t flags = buf[47] & 0xC0;
     buf[47] &= 0x3F;
     p += 48;
-    if (flags & 0x40) { *out = G1Point::identity(); return true; }
-    Fq c;
-    for (int i = 0; i < 12; i++) c.l[i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) | ((uint32_t)buf[4 * i + 3] << 24);
-    return g1_point_from_x(c.from_canonical(), (flags & 0x80) != 0, out);
+    if (flags & 0x40) {
+        // the identity has one encoding: x = 0, no sign bit (stricter than upstream, which ignores x here)
+        if (flags & 0x80) return false;
+        for (int i = 0; i < 48; i++)
+            if (buf[i]) return false;
+        *out = G1Point::identity();
+        return true;
+    }
+    Fq x;
+    if (!fq_from_canonical_bytes(buf, &x)) return false;
+    return g1_point_from_x(x, (flags & 0x80) != 0, out) && g1_in_subgroup(*out);
 }
 
 }  // namespace marlin

@@ -30,6 +30,7 @@
 // opening equations are folded with a verifier-side random scalar into one pairing-product test
 // e(sum r_i (C_i - v_i g - v'_i gamma_g + z_i W_i), h) * e(-sum r_i W_i, beta h) == 1.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <map>
 #include <memory>
@@ -590,7 +591,11 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, const R1cs& cs, Proving
     vk->beta_h = srs.beta_h;
     vk->max_degree = srs.max_degree;
     vk->shift_powers.clear();
-    for (size_t bound : {H.n - 2, K.n - 2}) {            // get_degree_bounds: |H| - 2, |K| - 2
+    // get_degree_bounds: |H| - 2, |K| - 2; marlin_pc::trim sorts and dedups the enforced bounds
+    std::vector<size_t> bounds = {H.n - 2, K.n - 2};
+    std::sort(bounds.begin(), bounds.end());
+    bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+    for (size_t bound : bounds) {
         G1Point sp;
         eng.export_bases(srs.powers_of_g, srs.max_degree - bound, 1, &sp);
         vk->shift_powers.push_back({bound, sp});

@@ -219,22 +219,25 @@ inline bool get_g2_compressed(const uint8_t*& p, const uint8_t* end, G2Point* ou
     const uint8_t flags = buf[95] & 0xC0;
     buf[95] &= 0x3F;
     p += 96;
-    if (flags & 0x40) { *out = G2Point::identity(); return true; }
-    Fq c[2];
-    for (int k = 0; k < 2; k++) {
-        Fq t;
-        for (int i = 0; i < 12; i++) {
-            const uint8_t* b = buf + 48 * k + 4 * i;
-            t.l[i] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
-        }
-        c[k] = t.from_canonical();
+    if (flags & 0x40) {
+        if (flags & 0x80) return false;
+        for (int i = 0; i < 96; i++)
+            if (buf[i]) return false;
+        *out = G2Point::identity();
+        return true;
     }
+    Fq c[2];
+    for (int k = 0; k < 2; k++)
+        if (!fq_from_canonical_bytes(buf + 48 * k, &c[k])) return false;      // refuses coordinates >= q
     Fq2 x = {c[0], c[1]}, y;
     if (!fq2_sqrt(x.sqr() * x + g2_coeff_b(), &y)) return false;
     const Fq2 negy = y.neg();
     const bool want_larger = (flags & 0x80) != 0;
     *out = {x, (fq2_gt(y, negy) == want_larger) ? y : negy, false};
-    return true;
+    // prime-order subgroup: [r]Q == O (a small-order point in a verifying key would otherwise reach the Miller loop)
+    uint32_t r[8];
+    for (int i = 0; i < 8; i++) r[i] = FrParams::mod(i);
+    return g2_mul_words(*out, r, 8).infinity;
 }
 
 // ---- ate pairing --------------------------------------------------------------------------------

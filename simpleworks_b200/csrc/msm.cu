@@ -151,8 +151,8 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
 static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery) {
     swb_ctx::MsmSlot& sl = c->msm_slot[slot];
     // window tables are worth it once the shared buckets hold a few points each
-    const bool tables = bases->tab_w > 0 && !c->msm_window_override &&
-                        n * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1));
+    const bool tables = bases->tab_w > 0 && !c->msm_window_override && c->msm_table_policy >= 0 &&
+                        (c->msm_table_policy > 0 || n * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1)));
     const int cb = tables ? bases->tab_c : pick_window(c, n);
     const int ndig = tables ? bases->tab_w : (254 + cb - 1) / cb;
     const int nwin = tables ? 1 : ndig;
@@ -316,8 +316,15 @@ int swb_set_msm_shard(swb_ctx* c, int rank, int world, swb_combine_fn combine, v
 
 int swb_msm_set_window_bits(swb_ctx* c, int cb) {
     if (!c) return SWB_EARG;
-    SWB_REQUIRE(c, cb == 0 || (cb >= 2 && cb <= 22), "msm_set_window_bits: c must be 0 or in [2,22]");
+    SWB_REQUIRE(c, cb == 0 || (cb >= 2 && cb <= 24), "msm_set_window_bits: c must be 0 or in [2,24]");
     c->msm_window_override = cb;
+    return SWB_OK;
+}
+
+int swb_msm_set_table_policy(swb_ctx* c, int policy) {
+    if (!c) return SWB_EARG;
+    SWB_REQUIRE(c, policy >= -1 && policy <= 1, "msm_set_table_policy: -1 (never), 0 (automatic) or 1 (always)");
+    c->msm_table_policy = policy;
     return SWB_OK;
 }
 

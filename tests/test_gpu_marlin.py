@@ -109,24 +109,45 @@ def test_vk_bytes_and_r1cs_interchange(gpu):
     assert CPU.vk_serialize(cvk) == gpu.serialize_verifying_key(vk)
 
 
+def _gpu_circuit(case):
+    """the fixture's instance through the C ABI: built-ins where they can express the values, swb_r1cs_new /
+    add_constraint / set_assignment otherwise (examples/manual-constraints.rs passes the raw Montgomery word 1)"""
+    from oracle import golden_marlin as PM
+    from simpleworks_b200.binding import ConstraintSystem
+    names = {"manual": "manual-constraints", "uint8_eq": "test-circuit", "chain": "mul-chain"}
+    a = case["args"]
+    if max(a["v0"], a["v1"]) < 1 << 64:
+        return ConstraintSystem.builtin(names[case["kind"]], a.get("size", 0), a["v0"], a["v1"])
+    assert case["kind"] == "manual"
+    pc = PM.circuit_manual_constraints(a["v0"], a["v1"])
+    cs = ConstraintSystem.new(pc.num_instance, pc.num_witness)
+    lc = lambda row: [(O.fr_mont([k])[0], j) for k, j in row]
+    for ra, rb, rc in zip(pc.a, pc.b, pc.c):
+        cs.enforce_constraint(lc(ra), lc(rb), lc(rc))
+    cs.assign(O.fr_mont(pc.instance), O.fr_mont(pc.witness))
+    return cs
+
+
 def test_gpu_proofs_match_committed_fixtures(gpu):
-    """The GPU engine reproduces tests/golden/marlin_proofs.json (proof and verifying-key bytes of the toy
-    circuits under the fixed test_rng() seed) without the CPU arm in the loop."""
+    """The GPU engine reproduces tests/golden/marlin_proofs.json -- proof and verifying-key bytes of the reference's
+    toy circuits under the fixed test_rng() seed, computed by the independent python restatement
+    oracle/golden_marlin.py -- without the CPU arm in the loop."""
     import hashlib
     import json
     import os
-    from simpleworks_b200.binding import ConstraintSystem, Rng
-    names = {"manual": "manual-constraints", "uint8_eq": "test-circuit", "chain": "mul-chain"}
+    from simpleworks_b200.binding import Rng
     g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "marlin_proofs.json")))["cases"]
+    assert len(g) >= 6
     for tag, case in g.items():
         rng = Rng()
         srs = gpu.generate_universal_srs(*case["bounds"], rng)
-        a = case["args"]
-        cs = ConstraintSystem.builtin(names[case["kind"]], a.get("size", 0), a["v0"], a["v1"])
+        cs = _gpu_circuit(case)
         pk, vk = gpu.generate_proving_and_verifying_keys(srs, cs)
         proof = gpu.generate_proof(cs, pk, rng)
         assert hashlib.sha256(proof).hexdigest() == case["proof_sha256"], tag
         assert hashlib.sha256(gpu.serialize_verifying_key(vk)).hexdigest() == case["vk_sha256"], tag
+        if "proof_hex" in case:
+            assert proof.hex() == case["proof_hex"] and gpu.serialize_verifying_key(vk).hex() == case["vk_hex"], tag
 
 
 def test_tuned_srs_gives_the_same_proofs(gpu):

@@ -415,3 +415,107 @@ def test_msm_large_properties(be):
     assert np.array_equal(be.msm(bases, ints2), be.g1_sum(np.concatenate([full, full])))
     assert np.array_equal(O.g1_to_affine(full), O.g1_to_affine(O.msm_variable_base(pts, scalars)))
     bases.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# the configurations bench.py times: wide windows (three radix-sort passes from c = 21 on), one shared
+# bucket set with W = 11 / 13 table levels, and NTTs beyond 2^24
+# ---------------------------------------------------------------------------------------------
+def _uniform_mod_r(n, seed):
+    """canonical scalars uniform in [0, r): 253-bit draws, rejected when >= r (SURVEY 8d distribution U)"""
+    rs = np.random.Generator(np.random.PCG64(seed))
+    a = rs.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    r_limbs = O.ints_to_limbs([G.R_MOD], 4)[0]
+    while True:
+        ge = np.ones(n, dtype=bool)                      # lexicographic compare from the top limb down
+        decided = np.zeros(n, dtype=bool)
+        for j in (3, 2, 1, 0):
+            lt = ~decided & (a[:, j] < r_limbs[j])
+            gt = ~decided & (a[:, j] > r_limbs[j])
+            ge[lt] = False
+            decided |= lt | gt
+        bad = np.nonzero(ge)[0]
+        if len(bad) == 0:
+            return a
+        a[bad] = rs.integers(0, 2 ** 64, size=(len(bad), 4), dtype=np.uint64)
+        a[bad, 3] &= np.uint64((1 << 61) - 1)
+
+
+@pytest.mark.parametrize("c", [21, 23])
+def test_msm_wide_window_tables_vs_oracle(be, c):
+    """The headline path of bench.py: window tables with c = 23 (W = 11) -- and c = 21 (W = 13), what four
+    GPUs use -- one shared bucket set, three-pass radix sort; 2^22 points against the oracle's Pippenger,
+    uniform scalars mod r plus the edge values, on the table path and (same handle) forced onto the plain one."""
+    n = 1 << 22
+    g = O.g1_mul(O.g1_generator(), 1)
+    beta = O.fr_mont([0x5357423230300001])
+    bases = be.bases_from_powers(g, beta, n)
+    try:
+        host = be.export_bases(bases, 0, n)
+        scalars = _uniform_mod_r(n, 2300 + c)
+        for i, v in enumerate([0, 1, G.R_MOD - 1, (G.R_MOD - 1) // 2, (G.R_MOD + 1) // 2, (1 << 252) - 1, 1 << 252]):
+            scalars[i] = O.ints_to_limbs([v], 4)[0]
+        scalars[100:164, 1:] = 0
+        want = O.g1_to_affine(O.msm_variable_base(host, scalars))
+        bases.precompute(c)
+        assert bases.table_info() == (c, -(-253 // c))
+        dev = be.to_device(scalars)
+        be.profile(True)
+        got = be.msm(bases, dev)
+        assert "accumulate" in be.last_stages()
+        assert np.array_equal(O.g1_to_affine(got), want)
+        assert np.array_equal(be.msm(bases, scalars), got)                       # host-buffer entry point
+        be.set_msm_table_policy(-1)
+        assert np.array_equal(be.msm(bases, dev), got)                          # plain path, automatic width
+        be.set_msm_window_bits(c)
+        assert np.array_equal(be.msm(bases, dev), got)                          # plain path at the same width (3-pass sort per window)
+        be.set_msm_window_bits(0)
+        # a sub-range that the automatic rule would send down the plain path, forced through the tables
+        m = 1 << 16
+        be.set_msm_table_policy(1)
+        sub = be.msm(bases, np.ascontiguousarray(scalars[:m]), offset=12345)
+        be.set_msm_table_policy(0)
+        want_sub = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(host[12345:12345 + m]), np.ascontiguousarray(scalars[:m])))
+        assert np.array_equal(O.g1_to_affine(sub), want_sub)
+    finally:
+        be.set_msm_window_bits(0)
+        be.set_msm_table_policy(0)
+        be.profile(False)
+        bases.free()
+
+
+@pytest.mark.parametrize("log_n", [25, 26])
+def test_ntt_four_pass_sizes(be, log_n):
+    """log n >= 25 (more passes than anything the oracle comparison reaches): inverse(forward(x)) == x with and
+    without the coset shift, and outputs of a 64-sparse input against direct evaluation with python integers."""
+    import torch
+    n = 1 << log_n
+    rs = np.random.RandomState(log_n)
+    x = torch.randint(-2 ** 63, 2 ** 63 - 1, (n, 4), dtype=torch.int64, device=f"cuda:{be.device}")
+    x[:, 3] &= 0x0FFFFFFFFFFFFFFF
+    y = be.ntt_(x.clone(), log_n)
+    assert not torch.equal(y, x)
+    assert torch.equal(be.ntt_(y, log_n, inverse=True), x)
+    del y
+    yc = be.ntt_(x.clone(), log_n, coset=True)
+    assert torch.equal(be.ntt_(yc, log_n, inverse=True, coset=True), x)
+    del yc
+    pos = rs.choice(n, 64, replace=False)
+    vals_m = _rand_fr(64, 31 + log_n)
+    sparse = torch.zeros_like(x)
+    sparse[torch.from_numpy(pos).to(sparse.device)] = be.to_device(vals_m)
+    vals = O.fr_unmont(vals_m)
+    w = G.domain_gen(log_n)
+    idx = [0, 1, 2, 3, n // 2, n // 2 + 1, n - 1, 123457, (1 << 24) + 5, n - (1 << 17) - 3] + [int(i) for i in rs.choice(n, 6)]
+    for coset in (False, True):
+        ys = be.ntt_(sparse.clone(), log_n, coset=coset)
+        got = O.fr_unmont(be.to_host(ys[torch.tensor(idx, device=ys.device)]))
+        for i, gv in zip(idx, got):
+            if coset:
+                want = sum(v * pow(G.FR_GENERATOR, int(p), G.R_MOD) * pow(w, (i * int(p)) % n, G.R_MOD) for v, p in zip(vals, pos)) % G.R_MOD
+            else:
+                want = sum(v * pow(w, (i * int(p)) % n, G.R_MOD) for v, p in zip(vals, pos)) % G.R_MOD
+            assert gv == want, (log_n, coset, i)
+        # and back: the inverse restores the sparse input
+        assert torch.equal(be.ntt_(ys, log_n, inverse=True, coset=coset), sparse)
