@@ -194,6 +194,12 @@ typedef struct swb_pk swb_pk;
 typedef struct swb_vk swb_vk;
 
 swb_rng* swb_rng_test_rng(void);
+/* rand::rngs::StdRng::from_seed (ChaCha12 keyed with 32 bytes) and StdRng::from_entropy (seeded from the
+ * operating system; NULL when no entropy source is available).  test_rng() is a PUBLIC fixed seed: it makes
+ * setup's trapdoor, the prover's blinders and the verifier's batching scalar predictable, so outside tests use
+ * one of these. */
+swb_rng* swb_rng_from_seed(const uint8_t seed[32]);
+swb_rng* swb_rng_from_entropy(void);
 uint64_t swb_rng_next_u64(swb_rng*);
 void swb_rng_free(swb_rng*);
 
@@ -226,14 +232,18 @@ size_t swb_srs_max_degree(const swb_srs*);
  * proofs).  Default 400, i.e. some twenty proofs (SWB_MARLIN_TABLES overrides), 0 = never, 1 = at the
  * first commitment.  Proof bytes do not depend on it. */
 int  swb_srs_set_tune_after(swb_srs*, long n_msms);
+/* Handle lifetimes: a proving key keeps its SRS alive (reference counted), so swb_srs_free and swb_pk_free
+ * may come in either order; every SRS, proving key and bases handle must be freed BEFORE swb_destroy of the
+ * context it was created on, and is only valid on that context (other contexts are refused with SWB_EARG). */
 void swb_srs_free(swb_srs*);
 int  swb_marlin_index(swb_ctx*, const swb_srs*, const swb_r1cs*, swb_pk** pk, swb_vk** vk);
 void swb_pk_free(swb_pk*);
 void swb_vk_free(swb_vk*);
 int  swb_marlin_prove(swb_ctx*, const swb_pk*, const swb_r1cs* cs_with_assignment, swb_rng*, uint8_t** proof, size_t* len);
 /* rng supplies the scalar that folds the two opening equations into one pairing product (the
- * reference passes its StdRng, mod.rs:79-86); NULL uses a fresh test_rng().  ctx may be NULL:
- * verification is host arithmetic (BLS12-377 pairing), no GPU involved. */
+ * reference passes its StdRng, mod.rs:79-86).  The scalar must be unpredictable to the prover -- the
+ * opening proofs are not bound by the transcript -- so NULL draws it from OS entropy, never from a fixed
+ * seed.  ctx may be NULL: verification is host arithmetic (BLS12-377 pairing), no GPU involved. */
 int  swb_marlin_verify(swb_ctx*, const swb_vk*, const swb_fr* public_inputs, size_t n, const uint8_t* proof, size_t len,
                        swb_rng*, int* ok);
 void swb_bytes_free(uint8_t*);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_g1_fr", "swb_msm_g1_batch_dev", "swb_set_msm_shard", "swb_msm_plan", "swb_msm_set_window_bits", "swb_msm_set_table_policy", "swb_g1_sum_jacobian",
     "swb_fixed_base_powers",
     "swb_ntt_fr", "swb_ntt_fr_dev", "swb_ntt_fr_batch_dev",
-    "swb_rng_test_rng", "swb_rng_next_u64", "swb_rng_free",
+    "swb_rng_test_rng", "swb_rng_from_seed", "swb_rng_from_entropy", "swb_rng_next_u64", "swb_rng_free",
     "swb_r1cs_new", "swb_r1cs_builtin", "swb_r1cs_add_constraint", "swb_r1cs_set_assignment", "swb_r1cs_is_satisfied",
     "swb_r1cs_free",
     "swb_marlin_profile_enable", "swb_marlin_last_phases", "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_set_tune_after", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
@@ -88,6 +88,8 @@ def load() -> ctypes.CDLL:
         "swb_msm_g1_fr_dev": (i32, [vp, vp, sz, vp, sz, vp]),
         "swb_msm_g1_fr": (i32, [vp, vp, sz, vp, sz, vp]),
         "swb_rng_test_rng": (vp, []),
+        "swb_rng_from_seed": (vp, [ctypes.c_char_p]),
+        "swb_rng_from_entropy": (vp, []),
         "swb_rng_next_u64": (ctypes.c_uint64, [vp]),
         "swb_rng_free": (None, [vp]),
         "swb_r1cs_new": (vp, [sz, sz]),

@@ -15,6 +15,7 @@ torch.distributed); every computation happens in libswb200.
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -70,6 +71,7 @@ class Bases:
         self._b = backend
         self._h = handle
         self.n = n
+        backend._children.add(self)        # freed with the backend at the latest (handles die before their context)
 
     def precompute(self, window_bits: int = 0) -> "Bases":
         """Build the window tables 2^(c*j) * P_i (swb_bases_precompute): later MSMs over these bases use
@@ -86,6 +88,8 @@ class Bases:
         if self._h:
             self._b._lib.swb_bases_free(self._h)
             self._h = None
+
+    close = free
 
     def __del__(self):
         try:
@@ -104,6 +108,7 @@ class Backend:
             raise SwbError(f"swb_init({device}) failed [{rc}]: {msg.decode() if msg else ''}")
         self._h = h
         self.device = device
+        self._children = weakref.WeakSet()     # bases / SRS / key handles living on this context
         # tensors handed to the *_dev entry points are produced and consumed on torch's current
         # stream, so run there by default (ordering + torch.cuda.Event timing)
         self.use_torch_stream()
@@ -115,7 +120,11 @@ class Backend:
             raise SwbError(f"libswb200 error {rc}: {msg.decode() if msg else ''}")
 
     def close(self):
+        """frees every handle that still lives on this context (proving keys before their SRS), then the context"""
         if self._h:
+            kids = sorted(list(self._children), key=lambda k: getattr(k, "_order", 0))
+            for k in kids:
+                k.close()
             self._lib.swb_destroy(self._h)
             self._h = None
 
@@ -314,11 +323,27 @@ class Backend:
 # protocol level: simpleworks::marlin (reference src/marlin/mod.rs:33-94)
 # ------------------------------------------------------------------------------------------------
 class Rng:
-    """generate_rand(): ark_std::test_rng() (reference src/marlin/mod.rs:33-35)."""
+    """generate_rand(): ark_std::test_rng() (reference src/marlin/mod.rs:33-35) by default -- a public fixed
+    seed, for tests and reproducible fixtures; Rng(seed=32 bytes) is StdRng::from_seed, Rng.from_entropy() is
+    StdRng::from_entropy()."""
 
-    def __init__(self):
+    def __init__(self, seed: bytes | None = None, _handle=None):
         self._lib = _lib.load()
-        self._h = ctypes.c_void_p(self._lib.swb_rng_test_rng())
+        if _handle is not None:
+            self._h = _handle
+        elif seed is None:
+            self._h = ctypes.c_void_p(self._lib.swb_rng_test_rng())
+        else:
+            if len(seed) != 32:
+                raise ValueError("StdRng seeds are 32 bytes")
+            self._h = ctypes.c_void_p(self._lib.swb_rng_from_seed(bytes(seed)))
+
+    @classmethod
+    def from_entropy(cls) -> "Rng":
+        h = _lib.load().swb_rng_from_entropy()
+        if not h:
+            raise SwbError("no OS entropy source")
+        return cls(_handle=ctypes.c_void_p(h))
 
     def next_u64(self) -> int:
         return int(self._lib.swb_rng_next_u64(self._h))
@@ -397,19 +422,52 @@ class ConstraintSystem:
             pass
 
 
+class _Handle(ctypes.c_void_p):
+    """An owned library handle: freed when the last python reference goes, after the objects that depend on
+    it (a proving key keeps its SRS, every handle keeps the Backend whose context it lives on).  It is a
+    c_void_p, so it is passed to the library as is."""
+
+    def bind(self, free_fn, *keep, order: int = 0):
+        self._free, self._keep, self._order = free_fn, keep, order
+        for k in keep:
+            if isinstance(k, Backend):
+                k._children.add(self)
+        return self
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    def close(self):
+        if getattr(self, "_free", None) is not None and self.value:
+            self._free(self)
+            self.value = None
+        self._free = None
+        self._keep = ()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Marlin:
     """generate_universal_srs / generate_proving_and_verifying_keys / generate_proof / verify_proof
-    (reference src/marlin/mod.rs:45-94) on one GPU."""
+    (reference src/marlin/mod.rs:45-94) on one GPU.  The returned SRS / key objects own their library handles
+    (freed with the object, in dependency order; .close() frees early)."""
 
     def __init__(self, backend: Backend):
         self.be = backend
         self._lib = backend._lib
 
     def generate_universal_srs(self, num_constraints: int, num_variables: int, num_non_zero: int, rng: Rng):
-        srs = ctypes.c_void_p()
+        srs = _Handle()
         self.be._check(self._lib.swb_marlin_universal_setup(self.be._h, num_constraints, num_variables, num_non_zero, rng._h,
                                                             ctypes.byref(srs)))
-        return srs
+        return srs.bind(self._lib.swb_srs_free, self.be, order=1)
 
     def srs_max_degree(self, srs) -> int:
         return int(self._lib.swb_srs_max_degree(srs))
@@ -434,9 +492,9 @@ class Marlin:
         self.be._check(self._lib.swb_srs_set_tune_after(srs, n_msms))
 
     def generate_proving_and_verifying_keys(self, srs, cs: ConstraintSystem):
-        pk, vk = ctypes.c_void_p(), ctypes.c_void_p()
+        pk, vk = _Handle(), _Handle()
         self.be._check(self._lib.swb_marlin_index(self.be._h, srs, cs._h, ctypes.byref(pk), ctypes.byref(vk)))
-        return pk, vk
+        return pk.bind(self._lib.swb_pk_free, srs, self.be), vk.bind(self._lib.swb_vk_free)
 
     def generate_proof(self, cs: ConstraintSystem, pk, rng: Rng) -> bytes:
         """returns serialize_proof(generate_proof(...)) (src/marlin/serialization.rs:5)"""
@@ -459,10 +517,11 @@ class Marlin:
         h = self._lib.swb_vk_deserialize(data, len(data))
         if not h:
             raise SwbError("malformed verifying key")
-        return ctypes.c_void_p(h)
+        return _Handle(h).bind(self._lib.swb_vk_free)
 
     def verify_proof(self, vk, public_inputs: np.ndarray, proof: bytes, rng: "Rng | None" = None) -> bool:
-        """verify_proof(deserialize_proof(bytes)): pairing check on the host"""
+        """verify_proof(deserialize_proof(bytes)): pairing check on the host.  rng=None lets the library draw the
+        batching scalar from OS entropy (it must be unpredictable to the prover)."""
         ok = ctypes.c_int()
         pi = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
         self.be._check(self._lib.swb_marlin_verify(self.be._h, vk, pi.ctypes.data, pi.shape[0], proof, len(proof),

@@ -2,8 +2,10 @@
 // instantiates it with the CUDA engine (marlin_abi.cu -> swb_marlin_*), the oracle build with the
 // CPU engine (oracle/marlin_oracle.cpp -> orc_marlin_*).
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <random>
 #include <string>
 
 #include "marlin.hpp"
@@ -28,6 +30,39 @@ struct PkHandle {
 struct VkHandle {
     VerifyingKey vk;
 };
+
+// StdRng::from_entropy(): 32 seed bytes from the operating system (/dev/urandom, std::random_device as a
+// second source); false when neither is available
+inline bool os_entropy(uint8_t seed[32]) {
+    bool ok = false;
+    if (FILE* f = fopen("/dev/urandom", "rb")) {
+        ok = fread(seed, 1, 32, f) == 32;
+        fclose(f);
+    }
+    if (!ok) {
+        try {
+            std::random_device rd;
+            for (int i = 0; i < 8; i++) {
+                const uint32_t w = rd();
+                memcpy(seed + 4 * i, &w, 4);
+            }
+            ok = true;
+        } catch (...) {
+            ok = false;
+        }
+    }
+    return ok;
+}
+inline RngHandle* rng_from_seed(const uint8_t seed[32]) {          // StdRng::from_seed = ChaCha12
+    auto* h = new RngHandle();
+    h->rng = ChaChaRng(seed, 12);
+    return h;
+}
+inline RngHandle* rng_from_entropy() {
+    uint8_t seed[32];
+    if (!os_entropy(seed)) return nullptr;
+    return rng_from_seed(seed);
+}
 
 inline Fr fr_from_abi(const uint64_t l[4]) {
     Fr r;
@@ -86,10 +121,17 @@ inline uint8_t* bytes_out(const std::vector<uint8_t>& b, size_t* len) {
     *len = b.size();
     return p;
 }
+// the parsers never let an exception (std::bad_alloc on hostile sizes included) cross the C boundary
 inline R1csHandle* r1cs_from_bytes(const uint8_t* p, size_t len) {
-    auto* h = new R1csHandle();
-    if (!r1cs_read(p, len, &h->cs)) { delete h; return nullptr; }
-    return h;
+    R1csHandle* h = nullptr;
+    try {
+        h = new R1csHandle();
+        if (!r1cs_read(p, len, &h->cs)) { delete h; return nullptr; }
+        return h;
+    } catch (...) {
+        delete h;
+        return nullptr;
+    }
 }
 inline uint8_t* r1cs_to_bytes(const R1csHandle* h, size_t* len) {
     std::vector<uint8_t> b;
@@ -98,9 +140,15 @@ inline uint8_t* r1cs_to_bytes(const R1csHandle* h, size_t* len) {
 }
 inline uint8_t* vk_to_bytes(const VkHandle* vk, size_t* len) { return bytes_out(vk->vk.serialize(), len); }
 inline VkHandle* vk_from_bytes(const uint8_t* p, size_t len) {
-    auto* h = new VkHandle();
-    if (!VerifyingKey::deserialize(p, len, &h->vk)) { delete h; return nullptr; }
-    return h;
+    VkHandle* h = nullptr;
+    try {
+        h = new VkHandle();
+        if (!VerifyingKey::deserialize(p, len, &h->vk)) { delete h; return nullptr; }
+        return h;
+    } catch (...) {
+        delete h;
+        return nullptr;
+    }
 }
 
 template <class Engine>
@@ -146,7 +194,10 @@ struct MarlinApi {
             return 4;
         }
     }
-    // rng may be null: a fresh test_rng() then supplies the batching scalar (any value is sound to test with)
+    // rng supplies the scalar that folds the two opening equations into one pairing product.  It MUST be
+    // unpredictable to the prover: the opening proofs are not part of the transcript, so with a known scalar
+    // two wrong equations can be made to cancel.  A null rng therefore draws from OS entropy (never from a
+    // fixed seed); callers that want reproducible verification pass their own.
     static int verify(const VkHandle* vk, const uint64_t* public_inputs, size_t n, const uint8_t* proof, size_t len, RngHandle* rng,
                       int* ok, std::string* err) {
         try {
@@ -155,7 +206,12 @@ struct MarlinApi {
             if (!Proof::deserialize(proof, len, &pr)) return 0;      // malformed proof: rejected, not an error
             std::vector<Fr> pi(n);
             for (size_t i = 0; i < n; i++) pi[i] = fr_from_abi(public_inputs + 4 * i);
-            ChaChaRng local = test_rng();
+            ChaChaRng local;
+            if (!rng) {
+                uint8_t seed[32];
+                if (!os_entropy(seed)) { *err = "verify: no rng given and no OS entropy source available"; return 4; }
+                local = ChaChaRng(seed, 12);
+            }
             *ok = marlin::verify(vk->vk, pi, pr, rng ? rng->rng : local) ? 1 : 0;
             return 0;
         } catch (const std::exception& e) {

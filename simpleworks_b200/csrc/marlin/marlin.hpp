@@ -353,6 +353,10 @@ inline bool VerifyingKey::deserialize(const uint8_t* p, size_t len, VerifyingKey
     uint64_t v[4], n;
     for (int i = 0; i < 4; i++)
         if (!get_u64(p, end, &v[i])) return false;
+    // sizes a verifier would turn into evaluation domains: refuse what no radix-2 domain of Fr can hold
+    for (int i = 0; i < 4; i++)
+        if (v[i] > ((uint64_t)1 << SWB_FR_TWO_ADICITY)) return false;
+    if (v[3] == 0 || v[3] > v[0]) return false;
     out->info = IndexInfo{(size_t)v[0], (size_t)v[1], (size_t)v[2], (size_t)v[3]};
     if (!get_u64(p, end, &n) || n > 64) return false;
     out->index_comms.resize(n);

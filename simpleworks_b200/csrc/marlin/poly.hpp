@@ -5,6 +5,7 @@
 // crate's EvaluationDomainExt bivariate helper.  The transforms themselves are
 // delegated to the Engine (GPU in the product, CPU in the oracle build).
 #pragma once
+#include <stdexcept>
 #include <algorithm>
 #include <vector>
 
@@ -148,7 +149,9 @@ struct Domain {
     size_t n = 1;
     Fr gen, gen_inv, size_inv, size_fr;
     Domain() : Domain(1) {}
+    // Radix2EvaluationDomain::new returns None beyond the field's two-adicity (2^47); here: throws
     explicit Domain(size_t min_size) {
+        if (min_size > ((size_t)1 << SWB_FR_TWO_ADICITY)) throw std::length_error("evaluation domain larger than 2^47");
         log_n = 0;
         while (((size_t)1 << log_n) < min_size) log_n++;
         n = (size_t)1 << log_n;

@@ -219,7 +219,9 @@ inline bool r1cs_read(const uint8_t* p, size_t len, R1cs* cs) {
         ms[m]->resize((size_t)nc);
         for (auto& row : *ms[m]) {
             uint64_t k;
-            if (!get_u64(p, end, &k) || k > ni + nw) return false;
+            // a row may repeat columns (r1cs_write and gadget synthesis both can), so k is bounded by the bytes
+            // that are left, not by the variable count: every entry takes 40 bytes
+            if (!get_u64(p, end, &k) || k > (uint64_t)(end - p) / 40) return false;
             row.e.resize((size_t)k);
             for (auto& e : row.e) {
                 uint64_t col;
@@ -231,6 +233,7 @@ inline bool r1cs_read(const uint8_t* p, size_t len, R1cs* cs) {
     if (p >= end) return false;
     cs->has_assignment = *p++ != 0;
     if (cs->has_assignment) {
+        if (ni + nw > (uint64_t)(end - p) / 32) return false;      // 32 bytes per value must still be there
         cs->instance.resize((size_t)ni);
         cs->witness.resize((size_t)nw);
         for (auto& x : cs->instance)

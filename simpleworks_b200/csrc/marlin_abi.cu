@@ -422,8 +422,15 @@ using Api = MarlinApi<GpuEngine>;
 
 struct swb_rng { RngHandle h; };
 struct swb_r1cs { R1csHandle* h; };
-struct swb_srs { GpuEngine eng; SrsHandle<GpuEngine>* h; };
-struct swb_pk { PkHandle<GpuEngine>* h; };
+// A proving key points into the SRS it was indexed from (committer key, engine), so the SRS is reference
+// counted: swb_srs_free only drops the caller's reference and the last proving key releases the rest.
+struct swb_srs { GpuEngine eng; SrsHandle<GpuEngine>* h; swb_ctx* ctx; int refs; };
+struct swb_pk { PkHandle<GpuEngine>* h; swb_srs* srs; };
+static void srs_release(swb_srs* s) {
+    if (!s || --s->refs > 0) return;
+    delete s->h;
+    delete s;
+}
 struct swb_vk { VkHandle* h; };
 
 extern "C" {
@@ -432,6 +439,17 @@ swb_rng* swb_rng_test_rng(void) {
     auto* r = new swb_rng();
     r->h.rng = test_rng();
     return r;
+}
+swb_rng* swb_rng_from_seed(const uint8_t seed[32]) {
+    if (!seed) return nullptr;
+    auto* r = new swb_rng();
+    r->h.rng = ChaChaRng(seed, 12);
+    return r;
+}
+swb_rng* swb_rng_from_entropy(void) {
+    uint8_t seed[32];
+    if (!os_entropy(seed)) return nullptr;
+    return swb_rng_from_seed(seed);
 }
 uint64_t swb_rng_next_u64(swb_rng* r) { return r->h.rng.next_u64(); }
 void swb_rng_free(swb_rng* r) { delete r; }
@@ -476,7 +494,7 @@ size_t swb_marlin_last_phases(char* buf, size_t cap) {
 
 int swb_marlin_universal_setup(swb_ctx* c, size_t nc, size_t nv, size_t nnz, swb_rng* rng, swb_srs** out) {
     if (!c || !rng || !out) return SWB_EARG;
-    auto* s = new swb_srs{GpuEngine(c), nullptr};
+    auto* s = new swb_srs{GpuEngine(c), nullptr, c, 1};
     std::string err;
     int rc = Api::setup(s->eng, nc, nv, nnz, &rng->h, &s->h, &err);
     if (rc) {
@@ -492,15 +510,12 @@ int swb_srs_set_tune_after(swb_srs* s, long n_msms) {
     s->h->srs->tune_after = n_msms;
     return SWB_OK;
 }
-void swb_srs_free(swb_srs* s) {
-    if (!s) return;
-    delete s->h;
-    delete s;
-}
+void swb_srs_free(swb_srs* s) { srs_release(s); }
 int swb_marlin_index(swb_ctx* c, const swb_srs* srs, const swb_r1cs* cs, swb_pk** pk, swb_vk** vk) {
     if (!c || !srs || !cs || !pk || !vk) return SWB_EARG;
+    if (srs->ctx != c) return swb::set_err(c, SWB_EARG, "%s", "index: the SRS was built on another context");
     std::string err;
-    auto* p = new swb_pk{nullptr};
+    auto* p = new swb_pk{nullptr, nullptr};
     auto* v = new swb_vk{nullptr};
     GpuEngine eng(c);
     int rc = Api::index(eng, srs->h, cs->h, &p->h, &v->h, &err);
@@ -509,13 +524,16 @@ int swb_marlin_index(swb_ctx* c, const swb_srs* srs, const swb_r1cs* cs, swb_pk*
         delete v;
         return swb::set_err(c, SWB_EINTERNAL, "index: %s", err.c_str());
     }
+    p->srs = const_cast<swb_srs*>(srs);
+    p->srs->refs++;
     *pk = p;
     *vk = v;
     return SWB_OK;
 }
 void swb_pk_free(swb_pk* p) {
     if (!p) return;
-    delete p->h;
+    delete p->h;                 // releases the device-resident matrices through the SRS's engine ...
+    srs_release(p->srs);         // ... which therefore goes last
     delete p;
 }
 void swb_vk_free(swb_vk* v) {
@@ -525,6 +543,7 @@ void swb_vk_free(swb_vk* v) {
 }
 int swb_marlin_prove(swb_ctx* c, const swb_pk* pk, const swb_r1cs* cs, swb_rng* rng, uint8_t** proof, size_t* len) {
     if (!c || !pk || !cs || !rng || !proof || !len) return SWB_EARG;
+    if (pk->srs && pk->srs->ctx != c) return swb::set_err(c, SWB_EARG, "%s", "prove: the proving key belongs to another context");
     std::string err;
     GpuEngine eng(c);
     int rc = Api::prove(eng, pk->h, cs->h, &rng->h, proof, len, &err);
