@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Headline benchmark of the Marlin-prover hot path on B200: BLS12-377 G1 variable-base MSM.
+"""Headline benchmark of the Marlin-prover hot path on B200: BLS12-377 G1 variable-base MSM, with the
+NTT and the whole Marlin prover (setup / index / prove / verify) measured beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 26] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
@@ -8,9 +9,7 @@
 One "step" = one multi-scalar multiplication sum_i s_i * P_i over 2^log_n synthetic (scalar, SRS
 power) pairs -- the operation kzg10::commit / open spends its time in under simpleworks'
 generate_proof (reference src/marlin/mod.rs:70-77) -- BASELINE.json configs[4] at its largest
-single-GPU size.  configs[1..3] (the example circuits) need ark-r1cs-std synthesis, which cannot
-run without a Rust toolchain; the full-proof metric follows once the host prover
-lands.
+single-GPU size.  Scalars are uniform in [0, r).
 
   value        points/s, whole job, scalars already resident in HBM, CUDA events, max over ranks
   e2e          the same through the host-buffer ABI call swb_msm_g1 (pinned host scalars -> H2D ->
@@ -22,6 +21,15 @@ lands.
                sanity counter BASELINE.md asks for)
   cpu_baseline the C restatement of arkworks' VariableBaseMSM (oracle/, OpenMP over windows like
                rayon) on a bounded sample, host cores of this box            [N = 1, rank 0 only]
+  extra.checks parity of exactly what was timed: the window-table result on the full input equals the
+               plain-path result, a sample forced through the table path equals the CPU oracle
+  extra.ntt_fr NTT at 2^20 / 2^24 / 2^26 with the fraction of the integer roof
+  extra.marlin the prover end to end at 2^20 constraints on the GPU and on the CPU arm (same proof
+               bytes), and the reference's own bound universal_setup(100000, 25000, 300000) with
+               setup + index + prove + verify timed as one unit (what its tests pay per call)
+
+--impl reference: the CPU arm alone (arkworks-equivalent C port on all host cores; under torchrun
+rank 0 runs it, the other ranks exit) on the same config and metric.
 
 N > 1 (strong scaling): the same 2^log_n problem, bases and scalars sharded by contiguous index
 range across ranks, one NCCL all-gather of the 144-byte partial results, final sum on every rank.
@@ -37,7 +45,23 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank unless the variable is already set; the CPU arm and the
+# host-side OpenMP loops of the library must not silently run on one core because of that.  libgomp reads
+# the variable when it is loaded, which has not happened yet.  SWB_BENCH_THREADS overrides.
+def _host_threads() -> int:
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    if os.environ.get("SWB_BENCH_THREADS"):
+        return max(1, int(os.environ["SWB_BENCH_THREADS"]))
+    cores = os.cpu_count() or 1
+    if "--impl" in sys.argv and "reference" in sys.argv:
+        return cores                       # rank 0 works alone
+    return max(1, cores // world)
+
+
+if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(_host_threads())
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -98,12 +122,38 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+R_MOD = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
+
+
 def synth_scalars_host(n: int, seed: int) -> np.ndarray:
-    """uniform canonical scalars below 2^252 (< r), (n,4) uint64"""
+    """canonical scalars uniform in [0, r) (SURVEY 8d distribution U): 253-bit draws, redrawn while >= r;
+    (n,4) uint64"""
     rs = np.random.Generator(np.random.PCG64(seed))
-    a = rs.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
-    a[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
-    return a
+    r_limbs = [(R_MOD >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
+
+    def draw(m):
+        a = rs.integers(0, 2 ** 64, size=(m, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 61) - 1)
+        return a
+    a = draw(n)
+    while True:
+        ge = np.ones(n, dtype=bool)
+        decided = np.zeros(n, dtype=bool)
+        for j in (3, 2, 1, 0):
+            lt = ~decided & (a[:, j] < np.uint64(r_limbs[j]))
+            gt = ~decided & (a[:, j] > np.uint64(r_limbs[j]))
+            ge[lt] = False
+            decided |= lt | gt
+        bad = np.nonzero(ge)[0]
+        if len(bad) == 0:
+            return a
+        a[bad] = draw(len(bad))
+
+
+def workload_config(log_n: int) -> dict:
+    """the part of the JSON line's config both arms (libswb200 and --impl reference) share"""
+    return {"workload": f"bls12-377 G1 variable-base MSM 2^{log_n}", "scalars": "uniform in [0, r)",
+            "bases": "SRS powers beta^i*G"}
 
 
 def marlin_gpu_run(be, lg, proofs):
@@ -138,32 +188,109 @@ def marlin_gpu_run(be, lg, proofs):
             "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts[1:]), "proof_bytes": len(proof)}, proof
 
 
-def marlin_extra(be, args) -> dict:
-    """End-to-end Marlin (BASELINE configs[3]): synthetic mul-chain R1CS, setup / index / prove /
-    verify through the protocol-level C ABI on this GPU; the CPU arm (same protocol source on the
-    oracle's CPU operators) proves a bounded smaller instance and the byte-identical proof check is
-    repeated on it."""
+def example_bound_gpu(be, seed: int = 2026):
+    """The reference's only non-toy configuration: every Marlin test and example calls
+    universal_setup(100000, 25000, 300000) and then index + prove + verify in the same call
+    (simple_merkle_tree.rs:39,83,119,148; examples/merkle-tree/main.rs:212; examples/schnorr-signature/main.rs:191,233;
+    examples/simple-payments/transaction.rs:89-139), so the whole sequence is what a user pays.  The Merkle / Schnorr
+    R1CS themselves need ark-r1cs-std; the stand-in has the shape that bound admits: 100 000 constraints, about three
+    non-zero entries per row (|H| = 2^17, |K| = 2^19), three public inputs."""
     from oracle import pymarlin as C
-    from simpleworks_b200 import _gen
+    from oracle import pyoracle as O
     from simpleworks_b200.binding import ConstraintSystem, Marlin, Rng
-    out = {"circuit": "mul-chain x_i*x_{i+1}=x_{i+2}, 1 public input", "verifier": "pairing check on the host (BLS12-377 ate pairing)"}
+    m = Marlin(be)
+    cs = ConstraintSystem.builtin("random-sparse", 100000, 1, seed)
+    pub = O.fr_mont(C.random_sparse_public_inputs(seed))
+    runs = []
+    for _ in range(2):                       # the second run is the steady state (scratch arenas grown)
+        rng = Rng()
+        t0 = time.perf_counter(); srs = m.generate_universal_srs(100000, 25000, 300000, rng)
+        t1 = time.perf_counter(); pk, vk = m.generate_proving_and_verifying_keys(srs, cs)
+        t2 = time.perf_counter(); proof = m.generate_proof(cs, pk, rng)
+        t3 = time.perf_counter(); ok = m.verify_proof(vk, pub, proof, rng)
+        t4 = time.perf_counter()
+        runs.append({"setup_s": t1 - t0, "index_s": t2 - t1, "prove_s": t3 - t2, "verify_s": t4 - t3, "total_s": t4 - t0,
+                     "verified": bool(ok)})
+        vkb = m.serialize_verifying_key(vk)
+        pk.close(); vk.close(); srs.close()
+    return {"srs_max_degree": 1572861, "first_call": runs[0], "steady": runs[1]}, proof, vkb
 
-    def gpu_run(lg, proofs):
-        return marlin_gpu_run(be, lg, proofs)
 
-    big, _ = gpu_run(args.marlin_log_n, 3)
-    out["gpu"] = big
-    small, proof_small = gpu_run(args.marlin_cpu_log_n, 3)
-    out["gpu_at_cpu_size"] = small
-    lg = args.marlin_cpu_log_n
+def example_bound_cpu(seed: int = 2026):
+    from oracle import pymarlin as C
+    from oracle import pyoracle as O
+    cs = C.R1cs("random_sparse", size=100000, v0=1, v1=seed)
+    pub = O.fr_mont(C.random_sparse_public_inputs(seed))
+    rng = C.Rng()
+    t0 = time.perf_counter(); srs = C.universal_setup(100000, 25000, 300000, rng)
+    t1 = time.perf_counter(); pk, vk = C.index(srs, cs)
+    t2 = time.perf_counter(); proof = C.prove(pk, cs, rng)
+    t3 = time.perf_counter(); ok = C.verify(vk, pub, proof, rng)
+    t4 = time.perf_counter()
+    return {"setup_s": t1 - t0, "index_s": t2 - t1, "prove_s": t3 - t2, "verify_s": t4 - t3, "total_s": t4 - t0,
+            "verified": bool(ok), "cores": O_threads(), "kind": "port"}, proof, C.vk_serialize(vk)
+
+
+def marlin_cpu_run(lg):
+    """the CPU arm (the same protocol code on the oracle's CPU operators, all host cores) on the 2^lg - 2
+    constraint mul-chain circuit: setup, index, one proof"""
+    from oracle import pymarlin as C
     crng = C.Rng()
     t0 = time.perf_counter(); csrs = C.universal_setup(1 << lg, 1 << lg, 3 << lg, crng); t1 = time.perf_counter()
     ccs = C.R1cs("chain", size=(1 << lg) - 2, v0=3, v1=5)
     cpk, cvk = C.index(csrs, ccs); t2 = time.perf_counter()
     cproof = C.prove(cpk, ccs, C.Rng()); t3 = time.perf_counter()
-    out["cpu_arm"] = {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t2 - t1, "prove_s": t3 - t2,
-                      "cores": O_threads(), "kind": "port", "same_proof_bytes_as_gpu": cproof == proof_small}
-    out["prove_speedup_at_cpu_size"] = (t3 - t2) / small["prove_s"]
+    return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t2 - t1, "prove_s": t3 - t2, "cores": O_threads(),
+            "kind": "port"}, cproof
+
+
+def marlin_extra(be, args, progress) -> dict:
+    """End-to-end Marlin (BASELINE configs[1-3]): setup / index / prove / verify through the protocol-level C ABI
+    on this GPU, and the CPU arm (same protocol source on the oracle's CPU operators, all host cores) beside it:
+      * mul-chain at 2^marlin_log_n constraints on both arms, proof bytes compared -- the north star's
+        "end-to-end 2^20-constraint proving >= 20x the host-CPU baseline".  The CPU run is sized by a probe at
+        2^16 so that it stays within --marlin-cpu-budget-s (about three minutes at 2^20 on 16 cores);
+      * the reference's own bound (100000, 25000, 300000) with the whole sequence as one unit, both arms."""
+    out = {"circuit": "mul-chain x_i*x_{i+1}=x_{i+2}, 1 public input", "verifier": "pairing check on the host (BLS12-377 ate pairing)"}
+    big, proof_big = marlin_gpu_run(be, args.marlin_log_n, 3)
+    out["gpu"] = big
+    progress(f"marlin gpu 2^{args.marlin_log_n} done")
+    ex_gpu, ex_proof, ex_vk = example_bound_gpu(be)
+    progress("marlin example bound (gpu) done")
+    ex_cpu, ex_cproof, ex_cvk = example_bound_cpu()
+    progress(f"marlin example bound (cpu) done: {ex_cpu['total_s']:.1f}s")
+    out["example_bound"] = {
+        "what": "universal_setup(100000, 25000, 300000) + index + prove + verify as ONE unit (what simple_merkle_tree.rs / "
+                "transaction.rs pay per call); stand-in R1CS: 100000 constraints, ~3 non-zeros per row, 3 public inputs",
+        "gpu": ex_gpu, "cpu_arm": ex_cpu, "same_proof_bytes": ex_proof == ex_cproof, "same_vk_bytes": ex_vk == ex_cvk,
+        "speedup_whole_sequence": ex_cpu["total_s"] / ex_gpu["steady"]["total_s"],
+        "speedup_whole_sequence_first_call": ex_cpu["total_s"] / ex_gpu["first_call"]["total_s"]}
+    # CPU arm at the north-star size, bounded: a 2^16 probe predicts the 2^20 time (work grows ~ n log n)
+    probe, proof_probe = marlin_cpu_run(16)
+    small, proof_small = marlin_gpu_run(be, 16, 2)
+    out["gpu_at_2p16"] = small
+    probe["same_proof_bytes_as_gpu"] = proof_probe == proof_small
+    out["cpu_arm_at_2p16"] = probe
+    lg = args.marlin_log_n
+    per = probe["setup_s"] + probe["index_s"] + probe["prove_s"]
+    while lg > 16 and per * (1 << (lg - 16)) * (lg / 16.0) > args.marlin_cpu_budget_s:
+        lg -= 1
+    progress(f"marlin cpu probe 2^16: {per:.1f}s -> cpu arm at 2^{lg}")
+    if lg == args.marlin_log_n:
+        cpu, cproof = marlin_cpu_run(lg)
+        cpu["same_proof_bytes_as_gpu"] = cproof == proof_big
+        gpu_same = big
+    elif lg > 16:
+        cpu, cproof = marlin_cpu_run(lg)
+        gpu_same, gproof = marlin_gpu_run(be, lg, 2)
+        cpu["same_proof_bytes_as_gpu"] = cproof == gproof
+        out[f"gpu_at_2p{lg}"] = gpu_same
+    else:
+        cpu, gpu_same = probe, small
+    out["cpu_arm"] = cpu
+    out[f"prove_speedup_at_2p{lg}"] = cpu["prove_s"] / gpu_same["prove_s"]
+    out[f"index_plus_prove_speedup_at_2p{lg}"] = (cpu["index_s"] + cpu["prove_s"]) / (gpu_same["index_s"] + gpu_same["prove_s"])
+    out["cpu_arm_log_constraints"] = lg
     return out
 
 
@@ -173,34 +300,42 @@ def O_threads() -> int:
 
 
 def run_reference(args):
-    """--impl reference: the CPU path (oracle port of arkworks' VariableBaseMSM, all host threads)."""
+    """--impl reference: the CPU path (oracle port of arkworks' VariableBaseMSM, all host threads -- one task per
+    window like rayon) on the arm's config and metric; each step is a bounded sample of the workload."""
     from oracle import pyoracle as O
     from simpleworks_b200 import _gen
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = _host_threads()
     log_s = min(args.log_n, args.cpu_log_n)
-    n = 1 << log_s
     g = O.g1_mul(O.g1_generator(), 1)
-    bases = O.fixed_base_powers(g, _gen.fr_mont(BETA_SEED), n)
-    scalars = synth_scalars_host(n, 1234)
-    threads = O.num_threads()
+    bases = O.fixed_base_powers(g, _gen.fr_mont(BETA_SEED), 1 << log_s, threads)
+    scalars = synth_scalars_host(1 << log_s, 1234)
+    # size the sample so that the whole run stays within a few minutes on this box
+    t0 = time.perf_counter()
+    O.msm_variable_base(np.ascontiguousarray(bases[:1 << 18]), np.ascontiguousarray(scalars[:1 << 18]), threads)
+    t18 = time.perf_counter() - t0
+    while log_s > 18 and t18 * (1 << (log_s - 18)) * 0.8 * (args.steps + args.warmup) > args.reference_budget_s:
+        log_s -= 1
+    n = 1 << log_s
+    bases, scalars = np.ascontiguousarray(bases[:n]), np.ascontiguousarray(scalars[:n])
     for _ in range(args.warmup):
-        O.msm_variable_base(bases, scalars)
+        O.msm_variable_base(bases, scalars, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.msm_variable_base(bases, scalars)
+        O.msm_variable_base(bases, scalars, threads)
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt
     line = {
         "impl": "reference", "metric": "msm_g1_points_per_sec", "value": val, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32-limbs(Fq 377-bit, Fr 253-bit)",
-        "data": "synthetic",
-        "config": {"workload": f"bls12-377 G1 variable-base MSM 2^{args.log_n}", "sample": f"2^{log_s} points per step"},
+        "data": "synthetic", "config": workload_config(args.log_n),
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"2^{log_s}-point MSM (first 2^{log_s} SRS powers, uniform scalars), "
-                                   "arkworks-equivalent C (not arkworks: no Rust toolchain in this image)"},
+                         "sample": f"2^{log_s}-point MSM per step (first 2^{log_s} SRS powers, scalars uniform in [0, r)), "
+                                   "arkworks-equivalent C (not arkworks: no Rust toolchain in this image); arkworks runs one "
+                                   f"rayon task per window, so at most {-(-253 // (max(3, (log_s * 69) // 100 + 2)))} of the cores work"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -213,9 +348,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="swb200", choices=["swb200", "reference"])
     ap.add_argument("--log-n", type=int, default=int(os.environ.get("SWB_BENCH_LOG_N", "26")))
-    ap.add_argument("--cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_CPU_LOG_N", "20")))
+    ap.add_argument("--cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_CPU_LOG_N", "22")),
+                    help="largest CPU sample (2^k points) of the cpu_baseline leg and of --impl reference")
+    ap.add_argument("--reference-budget-s", type=float, default=float(os.environ.get("SWB_BENCH_REFERENCE_BUDGET_S", "150")),
+                    help="--impl reference shrinks its per-step sample until steps + warmup fit in this many seconds")
     ap.add_argument("--marlin-log-n", type=int, default=int(os.environ.get("SWB_BENCH_MARLIN_LOG_N", "20")))
-    ap.add_argument("--marlin-cpu-log-n", type=int, default=int(os.environ.get("SWB_BENCH_MARLIN_CPU_LOG_N", "16")))
+    ap.add_argument("--marlin-cpu-budget-s", type=float, default=float(os.environ.get("SWB_BENCH_MARLIN_CPU_BUDGET_S", "300")),
+                    help="the CPU arm of the Marlin comparison runs at the largest size <= --marlin-log-n predicted to fit")
     ap.add_argument("--no-tables", action="store_true",
                     help="plain MSM path: no window tables (swb_bases_precompute) over the resident bases")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -301,6 +440,17 @@ def main():
         torch.cuda.synchronize()
 
     progress(f"bases ready ({t_bases:.1f}s + tables {t_tables:.1f}s)")
+    # ---- parity of the path that is about to be timed: the window-table result on the FULL input equals the
+    # plain-path result (same handle, level 0 only, per-window bucket sets) ---------------------------------
+    checks = {}
+    if not args.no_tables:
+        with_tables = combine(be.msm(bases, scalars_dev))
+        be.set_msm_table_policy(-1)
+        plain = combine(be.msm(bases, scalars_dev))
+        be.set_msm_table_policy(0)
+        checks["tables_equal_plain_on_full_input"] = bool(np.array_equal(with_tables, plain))
+        assert checks["tables_equal_plain_on_full_input"], "window-table path and plain path disagree on the full input"
+        progress("table path == plain path on the full input")
     # ---- resident-input timing ("value") ------------------------------------------------------------
     be.profile(True)
     result = None
@@ -363,9 +513,10 @@ def main():
         r, mine, err = None, float("inf"), None
         try:
             bases.free()
-            r, _ = marlin_gpu_run(be, args.marlin_log_n, 2)
+            r, proof_single = marlin_gpu_run(be, args.marlin_log_n, 2)
             mine = r["prove_s"]
         except Exception as e:     # every rank still joins the collective below
+            proof_single = None
             err = repr(e)
         worst = torch.tensor([mine], dtype=torch.float64, device=dev)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
@@ -377,17 +528,22 @@ def main():
         r2, mine2, err2 = None, float("inf"), None
         try:
             be.set_msm_shard(rank, world, dev)
-            r2, _ = marlin_gpu_run(be, args.marlin_log_n, 2)
+            r2, proof_sharded = marlin_gpu_run(be, args.marlin_log_n, 2)
             mine2 = r2["prove_s"]
         except Exception as e:
+            proof_sharded = None
             err2 = repr(e)
         finally:
             be.set_msm_shard(0, 1)
+        # the proof made by all N GPUs together must be, byte for byte, the proof each GPU made alone (every rank checks)
+        same = torch.tensor([1 if (proof_sharded is not None and proof_sharded == proof_single) else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
         worst2 = torch.tensor([mine2], dtype=torch.float64, device=dev)
         dist.all_reduce(worst2, op=dist.ReduceOp.MAX)
         w2 = float(worst2.item())
         marlin_replicas["one_proof_on_all_gpus"] = {
             "prove_s_max_over_ranks": w2, "speedup_vs_one_gpu": (w / w2) if w2 < float("inf") and w < float("inf") else 0.0,
+            "bytes_equal_single_gpu_proof_on_every_rank": bool(same.item()),
             "rank0": r2, "error": err2, "how": "MSMs sharded by index range, partial sums all-gathered (NCCL); proof bytes as on one GPU"}
 
     if rank != 0:
@@ -444,42 +600,56 @@ def main():
         dt = time.perf_counter() - t0
         got = be.msm(bases, hs)
         assert np.array_equal(O.g1_to_affine(got), O.g1_to_affine(ref)), "GPU MSM != CPU oracle on the baseline sample"
+        checks["sample_equals_cpu_oracle"] = True
+        if not args.no_tables:
+            # the automatic rule may send a sample this small down the plain path: force it through the
+            # c-bit / single-bucket-set / multi-pass-sort path that `value` was measured on
+            be.set_msm_table_policy(1)
+            forced = be.msm(bases, hs)
+            be.set_msm_table_policy(0)
+            checks["sample_through_table_path_equals_cpu_oracle"] = bool(np.array_equal(O.g1_to_affine(forced), O.g1_to_affine(ref)))
+            assert checks["sample_through_table_path_equals_cpu_oracle"], "table path != CPU oracle on the baseline sample"
         cpu = {"value": ns / dt, "unit": "points/s", "cores": O.num_threads(), "kind": "port",
                "sample": f"2^{log_s}-point MSM, first 2^{log_s} of the same bases/scalars, {dt:.2f} s; "
-                         "arkworks-equivalent C port (oracle/), result checked equal to the GPU's"}
+                         "arkworks-equivalent C port (oracle/), result checked equal to the GPU's (automatic and forced table path)"}
 
     extra = {}
     if not args.no_extra:
-        # NTT throughput beside the headline (BASELINE.json metric names both)
-        log_ntt = 24
-        x = torch.randint(-2 ** 63, 2 ** 63 - 1, (1 << log_ntt, 4), dtype=torch.int64, device=dev)
-        x[:, 3] &= 0x0FFFFFFFFFFFFFFF
-        for _ in range(3):
-            be.ntt_(x, log_ntt)
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(5):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            be.ntt_(x, log_ntt)
-            e1.record()
+        # NTT throughput beside the headline (BASELINE.json metric names both); the roof is the integer pipe
+        def ntt_line(log_ntt):
+            x = torch.randint(-2 ** 63, 2 ** 63 - 1, (1 << log_ntt, 4), dtype=torch.int64, device=dev)
+            x[:, 3] &= 0x0FFFFFFFFFFFFFFF
+            for _ in range(3):
+                be.ntt_(x, log_ntt)
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sum(ts) / len(ts)
-        nn = 1 << log_ntt
-        extra["ntt_fr"] = {
-            "log_n": log_ntt, "ms": ms, "elems_per_s": nn / ms * 1e3,
-            "hbm_gbs_algorithmic": 64.0 * nn / ms / 1e6, "hbm_frac": 64.0 * nn / ms / 1e6 / hbm_peak,
-            "limb_products_per_s": (nn / 2) * log_ntt * 128 / ms * 1e3,
-            "int_frac": (nn / 2) * log_ntt * 128 / ms * 1e3 / imad_wide, "passes": be.last_stages()}
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                be.ntt_(x, log_ntt)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sum(ts) / len(ts)
+            nn = 1 << log_ntt
+            return {"log_n": log_ntt, "ms": ms, "elems_per_s": nn / ms * 1e3,
+                    "hbm_gbs_algorithmic": 64.0 * nn / ms / 1e6, "hbm_frac": 64.0 * nn / ms / 1e6 / hbm_peak,
+                    "limb_products_per_s": (nn / 2) * log_ntt * 128 / ms * 1e3,
+                    "int_frac": (nn / 2) * log_ntt * 128 / ms * 1e3 / imad_wide, "passes": be.last_stages()}
+        extra["ntt_fr"] = ntt_line(24)
+        extra["ntt_fr_sizes"] = [ntt_line(k) for k in (20, 22, 26)]
         progress("ntt extra done")
         extra["setup_bases_s"] = t_bases
         extra["setup_tables_s"] = t_tables
         extra["stages_ms_avg"] = {k: v / args.steps for k, v in stage_sum.items()}
+        extra["checks"] = checks
         if world == 1:
             try:
-                extra["marlin"] = marlin_extra(be, args)
+                bases.free()
+                del scalars_dev, flush
+                torch.cuda.empty_cache()
+                extra["marlin"] = marlin_extra(be, args, progress)
             except Exception as e:     # the headline must not die with the side measurement
                 extra["marlin"] = {"error": repr(e)}
         elif marlin_replicas is not None:
@@ -489,13 +659,13 @@ def main():
         "metric": "msm_g1_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32-limbs(Fq 377-bit, Fr 253-bit)", "data": "synthetic",
-        "config": {"workload": f"bls12-377 G1 variable-base MSM 2^{args.log_n}", "points_per_gpu": n_local,
-                   "window_bits": c_bits, "windows": n_win, "scalars": "uniform < 2^252",
-                   "bases": "SRS powers beta^i*G generated on device and kept resident" +
-                            ("" if args.no_tables else f", with their {n_win}-level window tables 2^({c_bits}j)*P built once at load "
-                             f"({n_win * n_local * 96 / 2**30:.1f} GiB per GPU; --no-tables = plain path)"),
-                   "bucket_sets": n_sets, "parallelism": f"index-sharded x{world}",
-                   "l2": "256 MiB buffer rewritten between steps; inputs (>= 2 GiB) exceed L2"},
+        "config": workload_config(args.log_n),
+        "plan": {"points_per_gpu": n_local, "window_bits": c_bits, "windows": n_win,
+                 "bases": "generated on device and kept resident" +
+                          ("" if args.no_tables else f", with their {n_win}-level window tables 2^({c_bits}j)*P built once at load "
+                           f"({n_win * n_local * 96 / 2**30:.1f} GiB per GPU; --no-tables = plain path)"),
+                 "bucket_sets": n_sets, "parallelism": f"index-sharded x{world}",
+                 "l2": "256 MiB buffer rewritten between steps; inputs (>= 2 GiB) exceed L2"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_local) * 32 * world,
                 "d2h_bytes_per_step": (144 + n_sets * 192) * world, "ms_per_step": sum(e2e_ms) / len(e2e_ms)},
