@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswb200.so")
+# SWB_LIB points the loader at another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("SWB_LIB") or os.path.join(_HERE, "libswb200.so")
 
 # every symbol include/swb200.h declares; tests/test_abi.py checks the header against this list
 # and that the built library exports each one.

@@ -18,8 +18,19 @@
 namespace swb {
 
 constexpr int NTT_THREADS = 256;
-constexpr int NTT_TILE_LOG = 11;            // R*T = 2048 elements = 64 KB of shared memory
+#ifndef NTT_TILE_LOG_DEF
+#define NTT_TILE_LOG_DEF 11
+#endif
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 1
+#endif
+constexpr int NTT_TILE_LOG = NTT_TILE_LOG_DEF;   // R*T = 2048 elements = 64 KB of shared memory
 constexpr uint32_t NTT_MAX_LOG = 30;
+#ifndef NTT_BF_ILP
+#define NTT_BF_ILP 1                        // butterflies in flight per thread
+#endif
+constexpr int NTT_MAX_DIGIT = NTT_TILE_LOG;           // one column of the tile
+constexpr int NTT_MAX_SMEM = 3 * (1 << NTT_TILE_LOG) * 16;   // final pass with T = 2: [R][T + 1] elements = 96 KB
 
 struct NttPass {
     const Fr* in;
@@ -77,14 +88,14 @@ __device__ __forceinline__ void st_fr(Fr* p, const Fr& v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* __restrict__ tw_root,
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_ntt_pass(NttPass p, const Fr* __restrict__ tw_root,
                                                            const Fr* __restrict__ tw_coset) {
     extern __shared__ uint4 smem[];
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t, tile = R * T;
     // the tile is [j][t] in both modes (t fastest: butterflies and stores touch consecutive words).
     // Final mode loads rows of consecutive j, i.e. it writes the tile with stride Tp between lanes:
     // Tp = T + 1 is odd in 16-byte words, which spreads those stores over the banks.
-    const uint32_t Tp = p.mode == 0 ? T : T + 1u;
+    const uint32_t Tp = (p.mode == 0 || T == 1u) ? T : T + 1u;
     const uint32_t planes = R * Tp;
     Tile tl{smem, smem + planes};
     const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
@@ -138,22 +149,39 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPass p, const Fr* _
     const uint32_t nbf = tile >> 1;
     for (uint32_t s = 0; s < p.log_r; s++) {
         const uint32_t log_half = p.log_r - 1 - s, half = 1u << log_half;
-        for (uint32_t idx = tid; idx < nbf; idx += NTT_THREADS) {
-            uint32_t b, t;
-            t = idx & (T - 1);
-            b = idx >> p.log_t;
-            const uint32_t pos = b & (half - 1), grp = b >> log_half;
-            const uint32_t j0 = (grp << (log_half + 1)) + pos;
-            const uint32_t e0 = j0 * js + t * ts, e1 = e0 + half * js;
-            Fr u = tl.get(e0), v = tl.get(e1);
-            Fr sum = u + v, dif = u - v;
-            if (pos) {
-                uint32_t ex = (pos << s) << (NTT_MAX_LOG - p.log_r);
-                if (p.inverse) ex = ((1u << NTT_MAX_LOG) - ex) & ((1u << NTT_MAX_LOG) - 1u);
-                dif = dif * tw_lookup(tw_root, ex);
+        // two butterflies per iteration, loaded before either is computed: their Montgomery products are
+        // independent dependency chains that the scheduler interleaves (one chain alone leaves the multiplier idle
+        // between dependent instructions)
+        for (uint32_t idx = tid; idx < nbf; idx += NTT_BF_ILP * NTT_THREADS) {
+            uint32_t e0[NTT_BF_ILP], e1[NTT_BF_ILP], ex[NTT_BF_ILP];
+            Fr u[NTT_BF_ILP], v[NTT_BF_ILP];
+            bool on[NTT_BF_ILP];
+#pragma unroll
+            for (int q = 0; q < NTT_BF_ILP; q++) {
+                const uint32_t id = idx + q * NTT_THREADS;
+                on[q] = id < nbf;
+                const uint32_t t = id & (T - 1), b = id >> p.log_t;
+                const uint32_t pos = b & (half - 1), grp = b >> log_half;
+                const uint32_t j0 = (grp << (log_half + 1)) + pos;
+                e0[q] = j0 * js + t * ts;
+                e1[q] = e0[q] + half * js;
+                ex[q] = (pos << s) << (NTT_MAX_LOG - p.log_r);
+                if (p.inverse) ex[q] = ((1u << NTT_MAX_LOG) - ex[q]) & ((1u << NTT_MAX_LOG) - 1u);
+                if (on[q]) { u[q] = tl.get(e0[q]); v[q] = tl.get(e1[q]); }
             }
-            tl.put(e0, sum);
-            tl.put(e1, dif);
+            Fr tw[NTT_BF_ILP];
+#pragma unroll
+            for (int q = 0; q < NTT_BF_ILP; q++)
+                if (on[q] && ex[q]) tw[q] = tw_lookup(tw_root, ex[q]);
+#pragma unroll
+            for (int q = 0; q < NTT_BF_ILP; q++) {
+                if (!on[q]) continue;
+                const Fr sum = u[q] + v[q];
+                Fr dif = u[q] - v[q];
+                if (ex[q]) dif = dif * tw[q];
+                tl.put(e0[q], sum);
+                tl.put(e1[q], dif);
+            }
         }
         __syncthreads();
     }
@@ -197,6 +225,16 @@ __global__ void k_build_pow_table(Fr* __restrict__ tab, Fr b0, Fr b1, Fr b2) {
     tab[i] = base.pow_u64(j);
 }
 
+// widest digit of the automatic plan (SWB_NTT_MAX_DIGIT overrides: tuning aid)
+static uint32_t ntt_max_digit() {
+    static const uint32_t v = [] {
+        const char* e = getenv("SWB_NTT_MAX_DIGIT");
+        const long d = e ? atol(e) : 10;
+        return (uint32_t)(d >= 1 && d <= NTT_MAX_DIGIT ? d : 10);
+    }();
+    return v;
+}
+
 static Fr host_fr_const(const uint32_t (&v)[8]) {
     Fr r;
     for (int i = 0; i < 8; i++) r.l[i] = v[i];
@@ -226,15 +264,34 @@ int ntt_build_tables(swb_ctx* c) {
         k_build_pow_table<<<12, 256, 0, c->stream>>>(tabs[k], bases[k][0], bases[k][1], bases[k][2]);
         SWB_LAUNCH_CHECK(c, "k_build_pow_table");
     }
-    SWB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_TILE_LOG) * 32 + 32 * 256));
+    SWB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_MAX_SMEM));
     SWB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SWB_OK;
 }
 
-// plan: digits of at most 8 bits, as even as possible
+// plan: n = R_1 * ... * R_m.  Every pass costs a trip through HBM and (all but the last) one inter-digit
+// twiddle multiplication per element on top of its butterflies, so fewer, wider passes win as long as the
+// tile keeps a few adjacent columns (T = 2^(11 - digit)) for coalescing: measured on B200 (profiles/
+// r2_ntt_plan_sweep.json).  SWB_NTT_PLAN_<log_n>=a,b,c overrides (tuning aid).
 static int plan_digits(uint32_t log_n, uint32_t* dig) {
     if (log_n == 0) { dig[0] = 0; return 1; }
-    int m = (int)((log_n + 7) / 8);
+    char name[32];
+    snprintf(name, sizeof name, "SWB_NTT_PLAN_%u", log_n);
+    if (const char* e = getenv(name)) {
+        int m = 0;
+        uint32_t sum = 0;
+        while (*e && m < 8) {
+            char* end = nullptr;
+            const unsigned long v = strtoul(e, &end, 10);
+            if (end == e || v == 0 || v > (unsigned long)NTT_MAX_DIGIT) { m = 0; break; }
+            dig[m++] = (uint32_t)v;
+            sum += (uint32_t)v;
+            e = *end == ',' ? end + 1 : end;
+        }
+        if (m > 0 && sum == log_n) return m;
+    }
+    const uint32_t maxd = ntt_max_digit();
+    int m = (int)((log_n + maxd - 1) / maxd);
     for (int s = 0; s < m; s++) dig[s] = log_n / m + ((uint32_t)s < log_n % m ? 1 : 0);
     return m;
 }
@@ -297,8 +354,9 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
             blocks = n >> (dig[s] + log_t);
         }
         p.log_t = log_t;
-        const size_t smem = last ? ((size_t)32 << dig[s]) * (((size_t)1 << log_t) + 1)          // [R][T + 1] elements
-                                 : ((size_t)32) << (dig[s] + log_t);
+        const size_t smem = (last && log_t > 0) ? ((size_t)32 << dig[s]) * (((size_t)1 << log_t) + 1)          // [R][T + 1] elements
+                                                : ((size_t)32) << (dig[s] + log_t);
+        SWB_REQUIRE(c, smem <= (size_t)NTT_MAX_SMEM, "ntt: plan needs more shared memory than the kernel may use");
         const Fr* coset_tab = inverse ? c->tw_geninv : c->tw_gen;
         dim3 grid((unsigned)blocks, (unsigned)batch);
         k_ntt_pass<<<grid, NTT_THREADS, smem, c->stream>>>(p, c->tw_root, coset_tab);
