@@ -357,6 +357,9 @@ def main():
                     help="the CPU arm of the Marlin comparison runs at the largest size <= --marlin-log-n predicted to fit")
     ap.add_argument("--no-tables", action="store_true",
                     help="plain MSM path: no window tables (swb_bases_precompute) over the resident bases")
+    ap.add_argument("--shard", default="bucket", choices=["bucket", "index"],
+                    help="N > 1: 'bucket' = every rank holds all bases (with tables) and fills its interleaved share of the "
+                         "buckets; 'index' = contiguous index ranges (round-1 behaviour; the fallback without tables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -397,42 +400,72 @@ def main():
 
     n_total = 1 << args.log_n
     assert n_total % world == 0
-    n_local = n_total // world
-    lo = rank * n_local
-    c_bits, n_win = be.msm_plan(n_local)
-
-    # ---- synthetic inputs: bases = beta^i * G (the SRS shape), this rank's index slice ---------
-    # slice [lo, lo+n_local) of the powers = powers of beta applied to g' = beta^lo * G
+    bucket_shard = world > 1 and args.shard == "bucket" and not args.no_tables
+    if world > 1:
+        be.comm_init(rank, world)       # the library's own NCCL communicator; only the unique id went through torch
     g = _gen.g1_generator_jacobian()
     beta = _gen.fr_mont(BETA_SEED)
-    if lo:
-        r_mod = _gen.R_MOD
-        shift = pow(BETA_SEED, lo, r_mod)
-        tmp = be.bases_from_powers(g, _gen.fr_mont(shift), 2)          # [G, beta^lo * G]
-        g = np.concatenate([be.export_bases(tmp, 1, 1)[:, :12], _gen.fq_mont(1)], axis=1)
-        tmp.free()
+
+    def load_bases(first, count):
+        """bases[first .. first + count) = beta^i * G on the device: powers of beta applied to beta^first * G"""
+        g0 = g
+        if first:
+            tmp = be.bases_from_powers(g, _gen.fr_mont(pow(BETA_SEED, first, _gen.R_MOD)), 2)          # [G, beta^first * G]
+            g0 = np.concatenate([be.export_bases(tmp, 1, 1)[:, :12], _gen.fq_mont(1)], axis=1)
+            tmp.free()
+        return be.bases_from_powers(g0, beta, count)
+
+    # ---- synthetic inputs: bases = beta^i * G (the SRS shape) ---------------------------------------------------
+    n_local = n_total if bucket_shard else n_total // world      # bases (and scalars) this rank holds
+    lo = 0 if bucket_shard else rank * n_local
+    c_bits, n_win = be.msm_plan(n_local)
     t0 = time.perf_counter()
-    bases = be.bases_from_powers(g, beta, n_local)
+    bases = load_bases(lo, n_local)
     t_bases = time.perf_counter() - t0
     n_sets, t_tables = n_win, 0.0
     if not args.no_tables:
         # the SRS is fixed, so its window tables are built once at load time, like the bases themselves
         t0 = time.perf_counter()
+        ok = 1
         try:
             bases.precompute(0)
             t_tables = time.perf_counter() - t0
+        except Exception as e:     # e.g. not enough free memory for the tables: measure the plain path, say so
+            print(f"[bench] window tables unavailable on rank {rank} ({e})", file=sys.stderr, flush=True)
+            ok = 0
+        if world > 1:              # all ranks must take the same path
+            okt = torch.tensor([ok], dtype=torch.int64, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            ok = int(okt.item())
+        if ok:
             c_bits, n_win = bases.table_info()
             n_sets = 1
-        except Exception as e:     # e.g. not enough free memory for the tables: measure the plain path, say so
-            print(f"[bench] window tables unavailable ({e}); plain path", file=sys.stderr, flush=True)
+        else:
             args.no_tables = True
-    scalars_host = synth_scalars_host(n_local, 1234 + rank)
+            if bucket_shard:       # bucket sharding needs the tables: fall back to index ranges on the plain path
+                bucket_shard = False
+                bases.free()
+                n_local = n_total // world
+                lo = rank * n_local
+                c_bits, n_win = be.msm_plan(n_local)
+                bases = load_bases(lo, n_local)
+                n_sets = n_win
+            else:
+                be.set_msm_table_policy(-1)
+    # scalars: one global array (same on every rank); index sharding keeps this rank's slice of it only
+    all_scalars = synth_scalars_host(n_total, 1234)
+    scalars_host = all_scalars if bucket_shard else np.ascontiguousarray(all_scalars[lo:lo + n_local])
+    del all_scalars
     pinned = torch.from_numpy(scalars_host.view(np.int64)).pin_memory()
     scalars_dev = pinned.to(dev)
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)   # written between steps to flush L2
+    if bucket_shard:
+        be.set_msm_bucket_shard(rank, world)
+    share_adds = float(n_total) * n_win / world if bucket_shard else float(n_local) * n_win    # mixed additions per rank and step
 
     def combine(partial: np.ndarray) -> np.ndarray:
-        return binding.combine_partials(partial, world, dev)
+        """this rank's partial result -> the sum over all ranks, inside the library (swb_comm_sum_g1)"""
+        return partial if world == 1 else be.comm_sum_g1(partial)
 
     def barrier():
         if world > 1:
@@ -451,6 +484,14 @@ def main():
         checks["tables_equal_plain_on_full_input"] = bool(np.array_equal(with_tables, plain))
         assert checks["tables_equal_plain_on_full_input"], "window-table path and plain path disagree on the full input"
         progress("table path == plain path on the full input")
+    if bucket_shard:
+        # every rank holds everything, so every rank can also compute the whole MSM alone: the sum of the N shares
+        # must be that point
+        be.set_msm_bucket_shard(0, 1)
+        alone = be.msm(bases, scalars_dev)
+        be.set_msm_bucket_shard(rank, world)
+        checks["sum_of_bucket_shards_equals_single_gpu_result"] = bool(np.array_equal(alone, combine(be.msm(bases, scalars_dev))))
+        assert checks["sum_of_bucket_shards_equals_single_gpu_result"], "bucket shards do not add up to the single-GPU result"
     # ---- resident-input timing ("value") ------------------------------------------------------------
     be.profile(True)
     result = None
@@ -485,10 +526,25 @@ def main():
     ms_per_step = t_total * 1e3 / args.steps
     value = n_total * args.steps / t_total
 
-    # ---- end-to-end through the host-buffer ABI ----------------------------------------------------
+    # ---- end-to-end: scalars start in pinned HOST memory every step ------------------------------------
+    # one GPU / index sharding: the host-buffer ABI call swb_msm_g1 (H2D inside the call).  Bucket sharding: every
+    # rank needs all scalars, but each uploads only its 1/N slice over its own PCIe link and the slices are
+    # all-gathered over NVLink (NCCL), which is both less PCIe traffic in total and faster than N full uploads.
     host_view = pinned.numpy().view(np.uint64)
+    if bucket_shard:
+        ns = n_total // world
+        my_slice = pinned[rank * ns:(rank + 1) * ns]
+        full_dev = torch.empty_like(scalars_dev)
+
+        def e2e_step():
+            full_dev[rank * ns:(rank + 1) * ns].copy_(my_slice, non_blocking=True)
+            dist.all_gather_into_tensor(full_dev, full_dev[rank * ns:(rank + 1) * ns])
+            return combine(be.msm(bases, full_dev))
+    else:
+        def e2e_step():
+            return combine(be.msm(bases, host_view))
     for _ in range(min(args.warmup, 2)):
-        combine(be.msm(bases, host_view))
+        e2e_step()
     barrier()
     e2e_ms = []
     for _ in range(args.steps):
@@ -496,7 +552,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        result_e2e = combine(be.msm(bases, host_view))
+        result_e2e = e2e_step()
         e1.record()
         barrier()
         e2e_ms.append(e0.elapsed_time(e1))
@@ -512,6 +568,7 @@ def main():
     if world > 1 and not args.no_extra:
         r, mine, err = None, float("inf"), None
         try:
+            be.set_msm_bucket_shard(0, 1)
             bases.free()
             r, proof_single = marlin_gpu_run(be, args.marlin_log_n, 2)
             mine = r["prove_s"]
@@ -527,7 +584,7 @@ def main():
         # range and the 144-byte partial results all-gathered over NCCL (swb_set_msm_shard)
         r2, mine2, err2 = None, float("inf"), None
         try:
-            be.set_msm_shard(rank, world, dev)
+            be.set_msm_shard(rank, world, use_comm=True)      # partial commitments through the library's communicator
             r2, proof_sharded = marlin_gpu_run(be, args.marlin_log_n, 2)
             mine2 = r2["prove_s"]
         except Exception as e:
@@ -544,7 +601,9 @@ def main():
         marlin_replicas["one_proof_on_all_gpus"] = {
             "prove_s_max_over_ranks": w2, "speedup_vs_one_gpu": (w / w2) if w2 < float("inf") and w < float("inf") else 0.0,
             "bytes_equal_single_gpu_proof_on_every_rank": bool(same.item()),
-            "rank0": r2, "error": err2, "how": "MSMs sharded by index range, partial sums all-gathered (NCCL); proof bytes as on one GPU"}
+            "rank0": r2, "error": err2,
+            "how": "MSMs sharded by index range; the partial commitments of a prover round go through ONE ncclAllGather inside "
+                   "libswb200 (swb_comm_init / swb_set_msm_shard with no callback); proof bytes as on one GPU"}
 
     if rank != 0:
         if world > 1:
@@ -558,7 +617,7 @@ def main():
     imad_lo = be.measure_imad_peak("lo", 20000)
     mont = be.measure_mul_peak("fq", 4000)
     acc_avg_s = (sum(acc_ms) / len(acc_ms)) / 1e3
-    alg_lp = float(n_local) * n_win * FQ_MUL_PER_MIXED_ADD * LIMB_PRODUCTS_PER_FQ_MUL
+    alg_lp = share_adds * FQ_MUL_PER_MIXED_ADD * LIMB_PRODUCTS_PER_FQ_MUL
     achieved = alg_lp / acc_avg_s
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -571,7 +630,7 @@ def main():
         traffic = tr.get(f"k_msm_accumulate@2^{args.log_n}/{world}")
     except Exception:
         pass
-    alg_bytes = 128.0 * n_local
+    alg_bytes = 128.0 * n_total / world
     roofline = {
         "kernel": "k_msm_accumulate", "bound": "int32 IMAD pipe (not hbm/tensor: 377-bit modular arithmetic)",
         "achieved": achieved / 1e12, "peak": imad_wide / 1e12, "unit": "T limb-products/s", "frac": achieved / imad_wide,
@@ -579,7 +638,8 @@ def main():
         "frac_of_montgomery_loop_peak": achieved / mont["limb_products_per_s"],
         "imad32_peak_tops": imad_lo / 1e12, "montgomery_loop_peak_tlps": mont["limb_products_per_s"] / 1e12,
         "kernel_ms": acc_avg_s * 1e3, "kernel_share_of_step": acc_avg_s * 1e3 / ms_per_step,
-        "algorithmic_units": f"{n_local} points x {n_win} windows (c={c_bits}) x 10 Fq mul x 288 limb-products",
+        "algorithmic_units": f"{share_adds:.0f} mixed additions per GPU ({n_total} points x {n_win} windows (c={c_bits}) / {world}) "
+                             "x 10 Fq mul x 288 limb-products",
         "traffic": traffic,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (ms_per_step / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak, "peak_source": hbm_src,
@@ -660,14 +720,19 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32-limbs(Fq 377-bit, Fr 253-bit)", "data": "synthetic",
         "config": workload_config(args.log_n),
-        "plan": {"points_per_gpu": n_local, "window_bits": c_bits, "windows": n_win,
+        "plan": {"bases_per_gpu": n_local, "window_bits": c_bits, "windows": n_win,
+                 "sharding": "none" if world == 1 else (
+                     "bucket: every GPU holds all bases with tables and sees all scalars, fills the buckets b = rank (mod N); "
+                     "sort, accumulation and bucket reduction all shrink N-fold at the single-GPU window width" if bucket_shard
+                     else "index: contiguous ranges of (base, scalar) pairs"),
+                 "combine": "none" if world == 1 else "swb_comm_sum_g1: one ncclAllGather of N x 144 bytes inside libswb200, host sum",
                  "bases": "generated on device and kept resident" +
                           ("" if args.no_tables else f", with their {n_win}-level window tables 2^({c_bits}j)*P built once at load "
                            f"({n_win * n_local * 96 / 2**30:.1f} GiB per GPU; --no-tables = plain path)"),
-                 "bucket_sets": n_sets, "parallelism": f"index-sharded x{world}",
+                 "bucket_sets": n_sets,
                  "l2": "256 MiB buffer rewritten between steps; inputs (>= 2 GiB) exceed L2"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_local) * 32 * world,
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(n_total) * 32,
                 "d2h_bytes_per_step": (144 + n_sets * 192) * world, "ms_per_step": sum(e2e_ms) / len(e2e_ms)},
         "gpu_launches": int(launches), "extra": extra,
     }

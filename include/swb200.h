@@ -137,10 +137,22 @@ int  swb_msm_g1_fr(swb_ctx*, const swb_bases*, size_t offset, const swb_fr* scal
  * the (base, scalar) index range and `combine` is called with the 144-byte partial result: it must
  * return the sum over all ranks (an all-gather of world x 144 bytes followed by swb_g1_sum_jacobian --
  * simpleworks_b200/binding.py does it with torch.distributed over NCCL).  Every rank then continues
- * with identical commitments, so the proof bytes are those of a single GPU.  world <= 1 or a NULL
- * callback switch it off.  The callback returns 0 on success. */
+ * with identical commitments, so the proof bytes are those of a single GPU.  world <= 1 switches it off; a NULL
+ * callback uses the context's own communicator (swb_comm_init, below).  The callback returns 0 on success. */
 typedef int (*swb_combine_fn)(void* user, const swb_g1_jacobian* mine, swb_g1_jacobian* sum);
 int  swb_set_msm_shard(swb_ctx*, int rank, int world, swb_combine_fn combine, void* user);
+/* ---- multi-GPU exchange inside the library (one process per GPU; NCCL resolved at run time) ---------------
+ * swb_comm_unique_id: rank 0 obtains the 128-byte ncclUniqueId and hands it to the other ranks out of band
+ * (any channel: a file, MPI, torch.distributed's store); swb_comm_init: every rank joins, on its context's
+ * device; swb_comm_sum_g1: out[k] = sum over all ranks of mine[k] for k < count -- ONE ncclAllGather of
+ * world x count x 144 bytes on the context's stream, then host additions, identical on every rank.  With a
+ * communicator in place swb_set_msm_shard may be called with a NULL callback: the prover's partial commitments
+ * then travel through it, all MSMs of a prover round in one all-gather.  swb_destroy ends the communicator. */
+int  swb_comm_unique_id(uint8_t id[128]);
+int  swb_comm_init(swb_ctx*, const uint8_t id[128], int rank, int world);
+int  swb_comm_info(const swb_ctx*, int* rank, int* world);
+int  swb_comm_sum_g1(swb_ctx*, const swb_g1_jacobian* mine_host, size_t count, swb_g1_jacobian* out_host);
+int  swb_comm_destroy(swb_ctx*);
 /* n_msms independent MSMs over the same bases (the commitments of one prover round: ark-poly-commit's
  * `commit` loops over its polynomials): MSM i takes ns[i] device-resident scalars scalars_dev[i]
  * (canonical integers, or Montgomery values when montgomery != 0) against bases[offsets[i] ..] and writes
@@ -148,6 +160,14 @@ int  swb_set_msm_shard(swb_ctx*, int rank, int world, swb_combine_fn combine, vo
  * bucket reduction of one under the accumulation of the next; results equal n_msms single calls. */
 int  swb_msm_g1_batch_dev(swb_ctx*, const swb_bases*, const size_t* offsets, const void* const* scalars_dev, const size_t* ns,
                           size_t n_msms, int montgomery, swb_g1_jacobian* outs);
+/* Bucket sharding over `world` GPUs (a power of two): every rank holds ALL bases and sees ALL scalars, but only
+ * fills the buckets b with b mod world == rank of each bucket set (interleaved: equal load whatever the digit
+ * distribution), so the window width -- and with
+ * window tables the single shared bucket set -- stays what one GPU would use while sort, accumulation and bucket
+ * reduction all shrink by `world` (index-range sharding cannot shrink the bucket reduction).  Every swb_msm_g1*
+ * call on the context then returns this rank's share; the full result is the sum of the shares of all ranks
+ * (swb_g1_sum_jacobian, or swb_comm_* below).  world <= 1 switches it off. */
+int  swb_msm_set_bucket_shard(swb_ctx*, int rank, int world);
 /* the signed-digit window width c and window count ceil(254/c) an n-point MSM will use */
 int  swb_msm_plan(swb_ctx*, size_t n, int* window_bits, int* windows);
 /* window width override for tuning/tests (0 = automatic) */

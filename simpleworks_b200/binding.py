@@ -244,13 +244,41 @@ class Backend:
         self._check(self._lib.swb_msm_g1_batch_dev(self._h, bases._h, offs, ptrs, ns, k, int(montgomery), _np_ptr(out)))
         return out
 
-    def set_msm_shard(self, rank: int, world: int, device=None):
+    # ---- multi-GPU: the library's own NCCL communicator ------------------------------------------------
+    def comm_init(self, rank: int, world: int):
+        """Creates the library's NCCL communicator for this context (swb_comm_init).  The only thing that goes
+        through torch.distributed is the 128-byte unique id, broadcast from rank 0 on the default process group
+        (any backend); every later exchange happens inside libswb200."""
+        import torch
+        import torch.distributed as dist
+        uid = ctypes.create_string_buffer(128)
+        if rank == 0:
+            if self._lib.swb_comm_unique_id(uid) != 0:
+                raise SwbError("swb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        dev = f"cuda:{self.device}" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(uid.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        self._check(self._lib.swb_comm_init(self._h, bytes(t.cpu().tolist()), rank, world))
+        self.comm_world = world
+
+    def comm_sum_g1(self, mine: np.ndarray) -> np.ndarray:
+        """(k, 18) Jacobian partial results of this rank -> their sums over all ranks (one all-gather)"""
+        mine = np.ascontiguousarray(mine.reshape(-1, 18))
+        out = np.zeros_like(mine)
+        self._check(self._lib.swb_comm_sum_g1(self._h, _np_ptr(mine), mine.shape[0], _np_ptr(out)))
+        return out
+
+    def set_msm_shard(self, rank: int, world: int, device=None, use_comm: bool = False):
         """Multi-GPU proving (swb_set_msm_shard): every commit / open MSM of the Marlin entry points on this
         backend covers this rank's share only; the partial results are all-gathered with torch.distributed
         (NCCL on `device`, gloo when device is None) and summed, so all ranks continue with the same
         commitments.  world <= 1 switches it off."""
         if world <= 1:
             self._check(self._lib.swb_set_msm_shard(self._h, 0, 1, None, None))
+            self._combine_cb = None
+            return
+        if use_comm:                    # partial results through the library's communicator (comm_init), no callback
+            self._check(self._lib.swb_set_msm_shard(self._h, rank, world, None, None))
             self._combine_cb = None
             return
         cb_t = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
@@ -268,6 +296,11 @@ class Backend:
 
     def set_msm_window_bits(self, c: int):
         self._check(self._lib.swb_msm_set_window_bits(self._h, c))
+
+    def set_msm_bucket_shard(self, rank: int, world: int):
+        """every later MSM on this backend returns the share of the buckets b = rank (mod world) (all bases, all
+        scalars on every rank); world <= 1 switches it off"""
+        self._check(self._lib.swb_msm_set_bucket_shard(self._h, rank, world))
 
     def set_msm_table_policy(self, policy: int):
         """0 automatic, 1 always the window-table path when the bases have tables, -1 always the plain path"""

@@ -169,6 +169,7 @@ void swb_destroy(swb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    swb_comm_destroy(c);
     for (auto& kv : c->vec_cache) cudaFree(kv.second);
     for (auto& sl : c->msm_slot) {
         if (sl.work) { cudaStreamSynchronize(sl.work); cudaStreamDestroy(sl.work); }

@@ -47,13 +47,22 @@ struct swb_ctx {
         cudaEvent_t ev = nullptr;
         void* host_wins = nullptr;     // pinned, MSM_MAX_WINDOWS XYZZ points
         int nwin = 0, cb = 0;
+        int shard_rank = 0, shard_world = 1;   // bucket shard this MSM was planned for (swb_msm_set_bucket_shard)
         bool active = false, empty = false;
     } msm_slot[MSM_SLOTS];
     int scratch_slot = 0;              // suffix of scratch tags while a slot > 0 is being launched
+    // bucket sharding (swb_msm_set_bucket_shard): MSMs on this context only fill the buckets b with
+    // b mod world == rank of every bucket set and return that share of the result
+    int bucket_rank = 0, bucket_world = 1;
     // multi-GPU proving (swb_set_msm_shard): this rank's share of every prover MSM, and who adds them up
     int shard_rank = 0, shard_world = 1;
     int (*shard_combine)(void*, const swb_g1_jacobian*, swb_g1_jacobian*) = nullptr;
     void* shard_user = nullptr;
+
+    // swb_comm_*: NCCL communicator of this context (one process per GPU), staging buffers of the all-gather
+    void* comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    void *comm_dev = nullptr, *comm_host = nullptr;
 
     // cache of freed device blocks for the engine's vectors (vec_alloc / vec_free below), by size
     std::multimap<size_t, void*> vec_cache;
@@ -89,6 +98,8 @@ int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out);
 void* vec_alloc(swb_ctx* c, size_t bytes, size_t* granted);
 void vec_free(swb_ctx* c, void* p, size_t granted);
 int cuda_fail(swb_ctx* c, cudaError_t e, const char* what);
+// comm.cu: out[k] = sum over the ranks of mine[k], k < count -- one all-gather on the context's stream
+int comm_sum_g1(swb_ctx* c, const swb_g1_jacobian* mine, size_t count, swb_g1_jacobian* out);
 // returns device scratch of at least `bytes`, tagged; nullptr + error set on failure
 void* get_scratch(swb_ctx* c, const char* tag, size_t bytes);
 void* get_pinned(swb_ctx* c, size_t bytes);

@@ -331,7 +331,7 @@ struct GpuEngine {
     // collected later: two of them are in flight on the library's MSM slots, so the latency-bound
     // bucket tail of one runs under the accumulation of the next.  The scalars must stay alive until the
     // result has been collected.
-    struct Ticket { int slot; bool done; G1Point value; bool sharded; };
+    struct Ticket { int slot; bool done; G1Point value; bool sharded; bool combined; swb_g1_jacobian share; };
     std::vector<Ticket> tickets;                           // ids ticket_base .. ; finished old ones are dropped in blocks
     size_t ticket_base = 0;
     long slot_owner[swb_ctx::MSM_SLOTS] = {-1, -1, -1};    // ticket id occupying each slot
@@ -347,23 +347,50 @@ struct GpuEngine {
         }
         return p;
     }
+    bool sharding() const { return c->shard_world > 1 && (c->shard_combine || c->comm); }
+    // finishes the local part of a ticket (this rank's share when sharded)
     void collect(size_t id) {
         Ticket& t = tickets.at(id - ticket_base);
         if (t.done) return;
-        swb_g1_jacobian out;
-        ck(msm_end(c, t.slot, &out), "msm");
+        ck(msm_end(c, t.slot, &t.share), "msm");
         slot_owner[t.slot] = -1;
-        if (t.sharded) {                                   // this rank's share -> the sum over all ranks
-            swb_g1_jacobian sum;
-            if (c->shard_combine(c->shard_user, &out, &sum) != 0) throw MarlinError("msm: combining the ranks' partial results failed");
-            out = sum;
-        }
-        t.value = from_jacobian(out);
         t.done = true;
+        if (!t.sharded) {
+            t.value = from_jacobian(t.share);
+            t.combined = true;
+        }
+    }
+    // shares -> sums over all ranks.  With the library's communicator every share that is outstanding (the
+    // commitments of a round are all submitted before the first result is asked for) goes into ONE all-gather;
+    // a caller-supplied callback is invoked per MSM.
+    void combine_pending() {
+        std::vector<size_t> ids;
+        for (size_t k = 0; k < tickets.size(); k++)
+            if (tickets[k].sharded && !tickets[k].combined) ids.push_back(ticket_base + k);
+        if (ids.empty()) return;
+        for (size_t id : ids) collect(id);
+        if (c->shard_combine) {
+            for (size_t id : ids) {
+                Ticket& t = tickets.at(id - ticket_base);
+                swb_g1_jacobian sum;
+                if (c->shard_combine(c->shard_user, &t.share, &sum) != 0) throw MarlinError("msm: combining the ranks' partial results failed");
+                t.value = from_jacobian(sum);
+                t.combined = true;
+            }
+            return;
+        }
+        std::vector<swb_g1_jacobian> mine(ids.size()), sums(ids.size());
+        for (size_t k = 0; k < ids.size(); k++) mine[k] = tickets.at(ids[k] - ticket_base).share;
+        ck(comm_sum_g1(c, mine.data(), mine.size(), sums.data()), "msm (all-gather of the partial results)");
+        for (size_t k = 0; k < ids.size(); k++) {
+            Ticket& t = tickets.at(ids[k] - ticket_base);
+            t.value = from_jacobian(sums[k]);
+            t.combined = true;
+        }
     }
     // scalars of an n-point prover MSM that this rank processes (swb_set_msm_shard)
     size_t msm_local_count(size_t n) {
-        if (!(c->shard_world > 1 && c->shard_combine)) return n;
+        if (!sharding()) return n;
         const size_t base = n / (size_t)c->shard_world, rem = n % (size_t)c->shard_world;
         return base + ((size_t)c->shard_rank < rem ? 1 : 0);
     }
@@ -374,11 +401,12 @@ struct GpuEngine {
         if (slot_owner[slot] >= 0) collect((size_t)slot_owner[slot]);
         if (tickets.size() >= 128) {                       // batches are a handful of MSMs: these are long finished
             for (size_t i = 0; i < 64; i++) collect(ticket_base + i);
+            combine_pending();
             tickets.erase(tickets.begin(), tickets.begin() + 64);
             ticket_base += 64;
         }
         // multi-GPU proving: only this rank's contiguous share of the index range (remainder to the first ranks)
-        const bool sharded = c->shard_world > 1 && c->shard_combine;
+        const bool sharded = sharding();
         size_t lo = 0, cnt = n;
         if (sharded) {
             const size_t base = n / (size_t)c->shard_world, rem = n % (size_t)c->shard_world, r = (size_t)c->shard_rank;
@@ -386,17 +414,19 @@ struct GpuEngine {
             cnt = base + (r < rem ? 1 : 0);
         }
         ck(msm_begin(c, slot, static_cast<swb_bases*>(h), offset + lo, scalars.p + lo, cnt, 1), "msm");
-        tickets.push_back(Ticket{slot, false, G1Point::identity(), sharded});
+        tickets.push_back(Ticket{slot, false, G1Point::identity(), sharded, false, swb_g1_jacobian{}});
         slot_owner[slot] = (long)(ticket_base + tickets.size() - 1);
         return ticket_base + tickets.size() - 1;
     }
     G1Point msm_result(size_t id) {
         OpTimer ot_(c, "msm_result");
         collect(id);
+        if (!tickets.at(id - ticket_base).combined) combine_pending();
         return tickets.at(id - ticket_base).value;
     }
     void msm_drain() {
         for (size_t i = 0; i < tickets.size(); i++) collect(ticket_base + i);
+        combine_pending();
     }
     ~GpuEngine() {
         try { msm_drain(); } catch (...) {}

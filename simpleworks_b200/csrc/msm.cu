@@ -73,7 +73,7 @@ static int pick_window(swb_ctx* c, size_t n) {
 // streams, event and pinned result buffer of a slot, created on first use
 static int slot_prepare(swb_ctx* c, int slot) {
     swb_ctx::MsmSlot& sl = c->msm_slot[slot];
-    if (!sl.host_wins) SWB_CUDA(c, cudaMallocHost(&sl.host_wins, sizeof(G1Xyzz) * MSM_MAX_WINDOWS));
+    if (!sl.host_wins) SWB_CUDA(c, cudaMallocHost(&sl.host_wins, sizeof(G1Xyzz) * 2 * MSM_MAX_WINDOWS));
     if (slot > 0 && !sl.work) {
         int lo = 0, hi = 0;
         SWB_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi is the numerically smaller value
@@ -130,11 +130,32 @@ int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out) {
     SWB_CUDA(c, cudaSetDevice(c->device));
     SWB_CUDA(c, cudaStreamSynchronize(slot > 0 ? sl.tail : c->stream));
     const G1Xyzz* hw = static_cast<const G1Xyzz*>(sl.host_wins);
+    // a bucket shard holds R = sum_k (k + 1) B_k over its LOCAL bucket numbers k; the global number of local bucket k
+    // is world * k + rank, so its share of the set's sum is
+    //     sum_k (world * k + rank + 1) B_k = world * R - (world - rank - 1) * S,   S = plain sum (second half of the buffer)
+    auto small_mul = [](const G1Xyzz& p, uint32_t k) {
+        G1Xyzz t = G1Xyzz::identity();
+        for (int b = 31; b >= 0; b--) {
+            t = t.dbl();
+            if ((k >> b) & 1u) t.add(p);
+        }
+        return t;
+    };
+    auto set_sum = [&](int w) {
+        G1Xyzz r = hw[w];
+        if (sl.shard_world > 1) {
+            r = small_mul(r, (uint32_t)sl.shard_world);
+            G1Xyzz t = small_mul(hw[sl.nwin + w], (uint32_t)(sl.shard_world - sl.shard_rank - 1));
+            t.y = t.y.neg();
+            r.add(t);
+        }
+        return r;
+    };
     // Horner over the bucket sets, most significant first
-    G1Xyzz acc = hw[sl.nwin - 1];
+    G1Xyzz acc = set_sum(sl.nwin - 1);
     for (int w = sl.nwin - 2; w >= 0; w--) {
         for (int k = 0; k < sl.cb; k++) acc = acc.dbl();
-        acc.add(hw[w]);
+        acc.add(set_sum(w));
     }
     xyzz_to_out(acc, out);
     return SWB_OK;
@@ -164,17 +185,33 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
     pl.nwin = nwin;
     pl.tab_stride = tables ? bases->n : 0;
     pl.B = 1u << (cb - 1);
+    pl.shard_rank = 0;
+    pl.shard_shift = 0;
+    pl.compact = false;
+    if (c->bucket_world > 1 && (uint32_t)c->bucket_world <= pl.B / 2) {
+        // bucket sharding: this rank fills the buckets b = rank (mod world) of every set.  On the table path (one
+        // set, pair order free) the other ranks' pairs are dropped right in the digits kernel.
+        while ((1 << pl.shard_shift) < c->bucket_world) pl.shard_shift++;
+        pl.B >>= pl.shard_shift;
+        pl.shard_rank = (uint32_t)c->bucket_rank;
+        pl.compact = tables;
+    }
     pl.nb = (uint32_t)nwin * pl.B;
     pl.total = n * (size_t)ndig;
     pl.seg_len = tables ? pl.total : n;
     SWB_REQUIRE(c, pl.total < ((size_t)1 << 32), "msm: n * windows must be < 2^32");
     {
-        // enough threads to fill the GPU (>= ~512 per SM) but at most 128 additions each
+        // enough threads to fill the GPU (>= ~512 per SM) but at most 128 additions each (re-planned after the digits
+        // kernel when it compacts; these are then upper bounds for the scratch sizes)
         size_t want = pl.total / ((size_t)c->sm_count * 512);
         uint32_t len = 16;
         while (len < 128 && len < want) len <<= 1;
         pl.range_len = len;
         pl.nranges = (uint32_t)((pl.total + len - 1) / len);
+        if (pl.compact) {       // whatever number of pairs survives: at most this many ranges (see msm_plan_ranges)
+            const size_t a = pl.total / 128 + 1, b = (size_t)c->sm_count * 512 + 1;
+            pl.nranges = (uint32_t)(a > b ? a : b);
+        }
         pl.pcap = pl.nranges + pl.nb;
     }
     MsmBuffers bf{};
@@ -191,16 +228,17 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
         bf.seg = (G1Xyzz*)get_scratch(c, "msm_seg", (2 * segs + 2) * sizeof(G1Xyzz));
         bf.seg2 = (G1Xyzz*)get_scratch(c, "msm_seg2", ((size_t)nwin * 24 * 33 + 2) * sizeof(G1Xyzz));   // [sets][jobs][blocks + 1]
     }
-    bf.wins = (G1Xyzz*)get_scratch(c, "msm_wins", (size_t)MSM_MAX_WINDOWS * sizeof(G1Xyzz));
-    if (!bf.keys || !bf.vals || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||
+    bf.wins = (G1Xyzz*)get_scratch(c, "msm_wins", (size_t)2 * MSM_MAX_WINDOWS * sizeof(G1Xyzz));
+    bf.count = (uint32_t*)get_scratch(c, "msm_count", 64);
+    if (!bf.count || !bf.keys || !bf.vals || !bf.range_off || !bf.pkey || !bf.pstart || !bf.heavy || !bf.partial ||
         !bf.buckets || !bf.seg || !bf.seg2 || !bf.wins)
         return SWB_ENOMEM;
     const uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;
     std::unique_ptr<StageTimer> tmp(slot == 0 ? new StageTimer(c, "msm") : nullptr);   // stage timing: slot 0 only
     struct { StageTimer* t; void mark(const char* n) { if (t) t->mark(n); } } tm{tmp.get()};
-    int rc = msm_launch_digits_sort(c, pl, bf, scalars_dev, montgomery, &sorted_keys, &sorted_vals);
+    int rc = msm_launch_digits_sort(c, pl, bf, scalars_dev, montgomery, &sorted_keys, &sorted_vals, tmp.get());
     if (rc != SWB_OK) return rc;
-    tm.mark("digits+sort+count");
+    tm.mark("count");
     rc = msm_launch_accumulate(c, pl, bf, sorted_keys, sorted_vals, bases->xy + 2 * offset);
     if (rc != SWB_OK) return rc;
     tm.mark("accumulate");
@@ -228,7 +266,12 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
 
     sl.nwin = nwin;
     sl.cb = cb;
+    sl.shard_rank = (int)pl.shard_rank;
+    sl.shard_world = 1 << pl.shard_shift;
     SWB_CUDA(c, cudaMemcpyAsync(sl.host_wins, bf.wins, sizeof(G1Xyzz) * nwin, cudaMemcpyDeviceToHost, c->stream));
+    if (pl.shard_shift)
+        SWB_CUDA(c, cudaMemcpyAsync(static_cast<G1Xyzz*>(sl.host_wins) + nwin, bf.wins + MSM_MAX_WINDOWS, sizeof(G1Xyzz) * nwin,
+                                    cudaMemcpyDeviceToHost, c->stream));
     return SWB_OK;
 }
 
@@ -305,12 +348,25 @@ int swb_msm_plan(swb_ctx* c, size_t n, int* window_bits, int* windows) {
 
 int swb_set_msm_shard(swb_ctx* c, int rank, int world, swb_combine_fn combine, void* user) {
     if (!c) return SWB_EARG;
-    if (world <= 1 || !combine) {
+    if (world <= 1) {
         c->shard_rank = 0; c->shard_world = 1; c->shard_combine = nullptr; c->shard_user = nullptr;
         return SWB_OK;
     }
     SWB_REQUIRE(c, rank >= 0 && rank < world, "set_msm_shard: rank out of range");
+    // without a callback the partial results travel through the context's own communicator (swb_comm_init)
+    SWB_REQUIRE(c, combine || (c->comm && c->comm_world == world && c->comm_rank == rank),
+                "set_msm_shard: no combine callback and no communicator of this shape (swb_comm_init)");
     c->shard_rank = rank; c->shard_world = world; c->shard_combine = combine; c->shard_user = user;
+    return SWB_OK;
+}
+
+int swb_msm_set_bucket_shard(swb_ctx* c, int rank, int world) {
+    if (!c) return SWB_EARG;
+    if (world <= 1) { c->bucket_rank = 0; c->bucket_world = 1; return SWB_OK; }
+    SWB_REQUIRE(c, (world & (world - 1)) == 0 && world <= 1024, "msm_set_bucket_shard: world must be a power of two <= 1024");
+    SWB_REQUIRE(c, rank >= 0 && rank < world, "msm_set_bucket_shard: rank out of range");
+    c->bucket_rank = rank;
+    c->bucket_world = world;
     return SWB_OK;
 }
 

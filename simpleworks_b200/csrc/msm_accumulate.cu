@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(G1Xyzz* __restrict__ par
 
 int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,
                           const uint32_t* sorted_vals, const Fq* bases) {
+    if (pl.nranges == 0) return SWB_OK;      // a bucket shard that received no pairs
     k_msm_accumulate<<<(pl.nranges + 127) / 128, 128, 0, c->stream>>>(bf.partial, bf.pkey, bf.range_off, sorted_keys, sorted_vals,
                                                                      bases, pl.total, pl.seg_len, pl.B, pl.range_len, pl.nranges);
     SWB_LAUNCH_CHECK(c, "k_msm_accumulate");

@@ -39,7 +39,10 @@ struct MsmPlan {
     int nwin;            // bucket sets: ndig on the plain path, 1 with window tables
     size_t seg_len;      // pairs per bucket set: n on the plain path, n * ndig with window tables
     size_t tab_stride;   // records per table level (0 = plain path)
-    uint32_t B;          // buckets per set = 2^(cb-1)
+    uint32_t B;          // buckets per set that this call fills: 2^(cb-1), or that divided by the bucket-shard world
+    uint32_t shard_rank, shard_shift;   // bucket sharding: ours are the buckets b with b mod 2^shift == rank, stored at b >> shift
+    bool compact;        // table path under bucket sharding: only the pairs of our buckets are kept (total is then
+                         // known after the digits kernel)
     uint32_t nb;         // total buckets = nwin * B
     size_t total;        // n * ndig (bucket, point) pairs
     uint32_t range_len;  // sorted positions per accumulation thread
@@ -58,12 +61,13 @@ struct MsmBuffers {
     G1Xyzz* buckets;     // [nb]
     G1Xyzz* seg;         // [2][nwin * B / L]  per-segment weighted and plain sums of the bucket reduction
     G1Xyzz* seg2;        // per-job partial sums and values of the bucket reduction
-    G1Xyzz* wins;        // [MSM_MAX_WINDOWS]
+    G1Xyzz* wins;        // [2][MSM_MAX_WINDOWS]: weighted sums sum_k (k+1) B_k, then plain sums sum_k B_k (bucket shards)
+    uint32_t* count;     // [1] pairs kept by the compacting digits kernel
 };
 
 // msm_sort.cu: digits, sort, per-range run counts and their scan
-int msm_launch_digits_sort(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
-                           const uint32_t** sorted_keys, const uint32_t** sorted_vals);
+int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
+                           const uint32_t** sorted_keys, const uint32_t** sorted_vals, StageTimer* tm);
 // msm_accumulate.cu: one thread per range of sorted pairs -> partial sums
 int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,
                           const uint32_t* sorted_vals, const Fq* bases);

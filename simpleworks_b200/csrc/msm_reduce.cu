@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_segments(G1Xyzz* __res
     seg_w[g] = acc;
 }
 
+// (bucket shards also need the plain sum of all buckets: job `plain_job` = sum of every P_s, unweighted)
 __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_bit_sums(G1Xyzz* __restrict__ out, const G1Xyzz* __restrict__ seg_w,
-                                                                   const G1Xyzz* __restrict__ seg_p, uint32_t m, uint32_t per) {
+                                                                   const G1Xyzz* __restrict__ seg_p, uint32_t m, uint32_t per,
+                                                                   uint32_t plain_job) {
     extern __shared__ unsigned char smem_raw[];
     G1Xyzz* buf = reinterpret_cast<G1Xyzz*>(smem_raw);
     const uint32_t t = threadIdx.x, blk = blockIdx.x, job = blockIdx.y, w = blockIdx.z;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_bit_sums(G1Xyzz* __res
     const G1Xyzz* src = (job == 0 ? seg_w : seg_p) + (size_t)w * m;
     G1Xyzz acc = G1Xyzz::identity();
     for (uint32_t s = lo + t; s < hi; s += MSM_TAIL_THREADS)
-        if (job == 0 || ((s >> (job - 1)) & 1u)) acc.add(src[s]);
+        if (job == 0 || job == plain_job || ((s >> (job - 1)) & 1u)) acc.add(src[s]);
     buf[t] = acc;
     __syncthreads();
     for (uint32_t d = MSM_TAIL_THREADS >> 1; d > 0; d >>= 1) {
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_bit_sums(G1Xyzz* __res
 
 // one warp per (job, set): sum the bpj partial results, then weight job 1 + b by 2^b * L
 __global__ void __launch_bounds__(32) k_msm_bit_tree(G1Xyzz* __restrict__ val, const G1Xyzz* __restrict__ part, uint32_t bpj,
-                                                      uint32_t log_L) {
+                                                      uint32_t log_L, uint32_t plain_job) {
     __shared__ G1Xyzz buf[32];
     const uint32_t i = threadIdx.x, job = blockIdx.x, w = blockIdx.y, njobs = gridDim.x;
     buf[i] = i < bpj ? part[((size_t)w * njobs + job) * bpj + i] : G1Xyzz::identity();
@@ -164,16 +166,19 @@ __global__ void __launch_bounds__(32) k_msm_bit_tree(G1Xyzz* __restrict__ val, c
     }
     if (i == 0) {
         G1Xyzz x = buf[0];
-        if (job > 0)
+        if (job > 0 && job != plain_job)
             for (uint32_t k = 0; k < job - 1 + log_L; k++) x = x.dbl();
         val[(size_t)w * njobs + job] = x;
     }
 }
 // one warp per set: sum its (at most 32) weighted job values
-__global__ void __launch_bounds__(32) k_msm_bit_final(G1Xyzz* __restrict__ wins, const G1Xyzz* __restrict__ val, uint32_t njobs) {
+// (the plain job, when present, is the last one: it goes to wins[MSM_MAX_WINDOWS + w] instead of into the sum)
+__global__ void __launch_bounds__(32) k_msm_bit_final(G1Xyzz* __restrict__ wins, const G1Xyzz* __restrict__ val, uint32_t njobs,
+                                                       uint32_t plain_job) {
     __shared__ G1Xyzz buf[32];
     const uint32_t i = threadIdx.x, w = blockIdx.x;
-    buf[i] = i < njobs ? val[(size_t)w * njobs + i] : G1Xyzz::identity();
+    buf[i] = (i < njobs && i != plain_job) ? val[(size_t)w * njobs + i] : G1Xyzz::identity();
+    if (i == plain_job && i < njobs) wins[MSM_MAX_WINDOWS + w] = val[(size_t)w * njobs + i];
     __syncwarp();
     for (uint32_t d = 16; d > 0; d >>= 1) {
         if (i < d) {
@@ -214,7 +219,9 @@ int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     const uint32_t m = B / L;                             // segments per set (a power of two)
     uint32_t nbits = 0;
     while ((1u << nbits) < m) nbits++;
-    const uint32_t njobs = 1 + nbits;                     // <= 1 + 22
+    const bool sharded = pl.shard_shift != 0;             // then the host also needs the plain sum of our buckets
+    const uint32_t plain_job = sharded ? 1 + nbits : 0xffffffffu;
+    const uint32_t njobs = 1 + nbits + (sharded ? 1 : 0); // <= 1 + 22 + 1
     G1Xyzz *seg_w = bf.seg, *seg_p = bf.seg + (size_t)nwin * m;
     k_msm_segments<<<(nwin * m + MSM_TAIL_THREADS - 1) / MSM_TAIL_THREADS, MSM_TAIL_THREADS, 0, c->stream>>>(seg_w, seg_p, bf.buckets, L, nwin * m);
     SWB_LAUNCH_CHECK(c, "k_msm_segments");
@@ -225,11 +232,11 @@ int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf) {
     G1Xyzz* part = bf.seg2;                               // [nwin][njobs][bpj], then [nwin][njobs] values
     G1Xyzz* val = part + (size_t)nwin * njobs * bpj;
     const size_t smem = MSM_TAIL_THREADS * sizeof(G1Xyzz);
-    k_msm_bit_sums<<<dim3(bpj, njobs, nwin), MSM_TAIL_THREADS, smem, c->stream>>>(part, seg_w, seg_p, m, per);
+    k_msm_bit_sums<<<dim3(bpj, njobs, nwin), MSM_TAIL_THREADS, smem, c->stream>>>(part, seg_w, seg_p, m, per, plain_job);
     SWB_LAUNCH_CHECK(c, "k_msm_bit_sums");
-    k_msm_bit_tree<<<dim3(njobs, nwin), 32, 0, c->stream>>>(val, part, bpj, log_L);
+    k_msm_bit_tree<<<dim3(njobs, nwin), 32, 0, c->stream>>>(val, part, bpj, log_L, plain_job);
     SWB_LAUNCH_CHECK(c, "k_msm_bit_tree");
-    k_msm_bit_final<<<nwin, 32, 0, c->stream>>>(bf.wins, val, njobs);
+    k_msm_bit_final<<<nwin, 32, 0, c->stream>>>(bf.wins, val, njobs, plain_job);
     SWB_LAUNCH_CHECK(c, "k_msm_bit_final");
     return SWB_OK;
 }

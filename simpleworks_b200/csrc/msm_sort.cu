@@ -36,46 +36,116 @@ __device__ __forceinline__ void fr_mod_minus(uint32_t* a) {       // a = r - a
 // Table path (tab_stride == N > 0): the point of window w is table entry w*N + i, all windows share
 // the buckets, and a scalar above r/2 is replaced by r - s with every sign flipped (bases in the
 // prime-order subgroup), so nwin = ceil(253 / c) windows suffice.
+// Bucket sharding (shift > 0): only the digits whose bucket b has b mod 2^shift == rank are ours (interleaved, so
+// that every rank gets the same load whatever the digit distribution -- the top window of a 253-bit scalar only
+// reaches the lower buckets); keys are local (b >> shift) and every other digit gets the marker Bloc, like a
+// zero digit.  With COMPACT
+// (table path: one bucket set, so the order of the pairs is free) the marked pairs are not written at
+// all: a block counts what it keeps in shared memory, reserves the space with one atomicAdd on *count and
+// writes its pairs there -- the arrays the sort sees shrink with the number of ranks.
+template <bool COMPACT>
 __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                      const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
-                                                     int montgomery, size_t tab_stride) {
+                                                     int montgomery, size_t tab_stride, uint32_t rank, uint32_t shift, uint32_t Bloc,
+                                                     uint32_t* __restrict__ count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t B = 1u << (c - 1);
-    for (; i < n; i += stride) {
-        Fr s;
-        const uint4* q = reinterpret_cast<const uint4*>(scalars + 8 * i);
-        uint4 a = q[0], b = q[1];
-        s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
-        s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
-        if (montgomery) s = s.to_canonical();
+    __shared__ uint32_t s_cnt, s_base;
+    // compaction is a block-wide step, so every thread of the block runs the same number of rounds
+    const size_t rounds = (n + stride - 1) / stride;
+    for (size_t round = 0; round < rounds; round++, i += stride) {
+        Fr s = Fr::zero();
         uint32_t flip = 0;
-        if (tab_stride) {
-            while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
-            uint32_t t[8];                                    // 2s >= r  <=>  s > r/2
-            uint32_t top = 0;
-            for (int k = 0; k < 8; k++) {
-                t[k] = (s.l[k] << 1) | top;
-                top = s.l[k] >> 31;
-            }
-            if (top || fr_geq_mod(t)) {
-                fr_mod_minus(s.l);
-                flip = 1;
+        const bool live = i < n;
+        if (live) {
+            const uint4* q = reinterpret_cast<const uint4*>(scalars + 8 * i);
+            uint4 a = q[0], b = q[1];
+            s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
+            s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
+            if (montgomery) s = s.to_canonical();
+            if (tab_stride) {
+                while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
+                uint32_t t[8];                                    // 2s >= r  <=>  s > r/2
+                uint32_t top = 0;
+                for (int k = 0; k < 8; k++) {
+                    t[k] = (s.l[k] << 1) | top;
+                    top = s.l[k] >> 31;
+                }
+                if (top || fr_geq_mod(t)) {
+                    fr_mod_minus(s.l);
+                    flip = 1;
+                }
             }
         }
-        uint32_t carry = 0;
-        for (int w = 0; w < nwin; w++) {
+        // walks the windows of s: emit(w, key, value)
+        auto walk = [&](auto&& emit) {
+            uint32_t carry = 0;
+            for (int w = 0; w < nwin; w++) {
+                const int bit = w * c, limb = bit >> 5, off = bit & 31;
+                uint32_t v = 0;
+                if (limb < 8) {
+                    v = s.l[limb] >> off;
+                    if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
+                }
+                v = (v & ((1u << c) - 1u)) + carry;
+                uint32_t neg = 0;
+                if (v > B) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
+                const uint32_t key = (v && ((v - 1) & ((1u << shift) - 1u)) == rank) ? (v - 1) >> shift : Bloc;
+                const uint32_t val = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | ((neg ^ flip) << 31);
+                emit(w, key, val);
+            }
+        };
+        if (!COMPACT) {
+            if (live)
+                walk([&](int w, uint32_t key, uint32_t val) {
+                    keys[(size_t)w * n + i] = key;
+                    vals[(size_t)w * n + i] = val;
+                });
+            continue;
+        }
+        // count, reserve (one global atomic per block and round), write.  The first walk only notes WHICH windows
+        // are ours and what carry entered them (two bit masks), so the second visit touches the kept windows alone.
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        uint64_t keep = 0, cin = 0;
+        if (live) {
+            uint32_t carry = 0;
+            for (int w = 0; w < nwin; w++) {
+                const int bit = w * c, limb = bit >> 5, off = bit & 31;
+                uint32_t v = 0;
+                if (limb < 8) {
+                    v = s.l[limb] >> off;
+                    if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
+                }
+                cin |= (uint64_t)carry << w;
+                v = (v & ((1u << c) - 1u)) + carry;
+                if (v > B) { v = (1u << c) - v; carry = 1; } else carry = 0;
+                if (v && ((v - 1) & ((1u << shift) - 1u)) == rank) keep |= 1ull << w;
+            }
+        }
+        const uint32_t mine = (uint32_t)__popcll(keep);
+        uint32_t my_off = 0;
+        if (mine) my_off = atomicAdd(&s_cnt, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = s_cnt ? atomicAdd(count, s_cnt) : 0u;
+        __syncthreads();
+        uint32_t at = s_base + my_off;
+        while (keep) {
+            const int w = __ffsll((long long)keep) - 1;
+            keep &= keep - 1;
             const int bit = w * c, limb = bit >> 5, off = bit & 31;
             uint32_t v = 0;
             if (limb < 8) {
                 v = s.l[limb] >> off;
                 if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
             }
-            v = (v & ((1u << c) - 1u)) + carry;
+            v = (v & ((1u << c) - 1u)) + (uint32_t)((cin >> w) & 1u);
             uint32_t neg = 0;
-            if (v > B) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
-            keys[(size_t)w * n + i] = v ? v - 1 : B;
-            vals[(size_t)w * n + i] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | ((neg ^ flip) << 31);
+            if (v > B) { v = (1u << c) - v; neg = 1; }
+            keys[at] = (v - 1) >> shift;
+            vals[at] = (uint32_t)((size_t)w * tab_stride + i) | ((neg ^ flip) << 31);
+            at++;
         }
     }
 }
@@ -105,21 +175,56 @@ __global__ void __launch_bounds__(256) k_msm_range_count(uint32_t* __restrict__ 
     }
 }
 
-int msm_launch_digits_sort(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
-                           const uint32_t** sorted_keys, const uint32_t** sorted_vals) {
-    const size_t total = pl.total;
+// fills in what is only known after the digits kernel under compaction: total, seg_len, ranges
+static void msm_plan_ranges(swb_ctx* c, MsmPlan& pl) {
+    // enough threads to fill the GPU (>= ~512 per SM) but at most 128 additions each
+    size_t want = pl.total / ((size_t)c->sm_count * 512);
+    uint32_t len = 16;
+    while (len < 128 && len < want) len <<= 1;
+    pl.range_len = len;
+    pl.nranges = (uint32_t)((pl.total + len - 1) / len);
+}
+
+int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
+                           const uint32_t** sorted_keys, const uint32_t** sorted_vals, StageTimer* tm) {
     {
         size_t blocks = (pl.n + 255) / 256;
         size_t cap = (size_t)c->sm_count * 8;
         if (blocks > cap) blocks = cap;
-        k_msm_digits<<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb, pl.ndig,
-                                                              montgomery, pl.tab_stride);
-        SWB_LAUNCH_CHECK(c, "k_msm_digits");
+        if (pl.compact) {
+            SWB_CUDA(c, cudaMemsetAsync(bf.count, 0, sizeof(uint32_t), c->stream));
+            k_msm_digits<true><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb,
+                                                                         pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, bf.count);
+            SWB_LAUNCH_CHECK(c, "k_msm_digits");
+            // the number of pairs that fell into our bucket range sizes everything downstream
+            uint32_t kept = 0;
+            SWB_CUDA(c, cudaMemcpyAsync(&kept, bf.count, sizeof kept, cudaMemcpyDeviceToHost, c->stream));
+            SWB_CUDA(c, cudaStreamSynchronize(c->stream));
+            pl.total = kept;
+            pl.seg_len = kept;
+            msm_plan_ranges(c, pl);
+        } else {
+            k_msm_digits<false><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb,
+                                                                          pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, nullptr);
+            SWB_LAUNCH_CHECK(c, "k_msm_digits");
+        }
+    }
+    if (tm) tm->mark("digits");
+    const size_t total = pl.total;
+    if (total == 0) {                 // nothing in our bucket range: no partial sums at all
+        SWB_CUDA(c, cudaMemsetAsync(bf.range_off, 0, 2 * sizeof(uint32_t), c->stream));
+        *sorted_keys = bf.keys;
+        *sorted_vals = bf.vals;
+        return SWB_OK;
     }
     uint32_t *sk = nullptr, *sv = nullptr;
     // keys are 0 .. B (B = 2^(cb-1) marks a zero digit): cb bits, sorted inside each bucket set's segment
-    int rc = radix_sort_segmented(c, bf.keys, bf.keys + msm_alt_offset(total), bf.vals, bf.vals + msm_alt_offset(total), pl.seg_len, (uint32_t)pl.nwin, pl.cb, &sk, &sv);
+    int key_bits = 1;
+    while ((1u << key_bits) <= pl.B) key_bits++;          // values 0 .. B
+    const size_t alt = msm_alt_offset(pl.n * (size_t)pl.ndig);   // where the second halves of the buffers start
+    int rc = radix_sort_segmented(c, bf.keys, bf.keys + alt, bf.vals, bf.vals + alt, pl.seg_len, (uint32_t)pl.nwin, key_bits, &sk, &sv);
     if (rc != SWB_OK) return rc;
+    if (tm) tm->mark("sort");
     SWB_CUDA(c, cudaMemsetAsync(bf.range_off, 0, ((size_t)pl.nranges + 1) * sizeof(uint32_t), c->stream));
     k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.seg_len, pl.B, pl.range_len);
     SWB_LAUNCH_CHECK(c, "k_msm_range_count");

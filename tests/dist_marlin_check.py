@@ -3,7 +3,8 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/dist_marlin_check.py [log_n]
 
-Every rank runs the same prover with its commit / open MSMs sharded over the N GPUs (swb_set_msm_shard).
+Every rank runs the same prover with its commit / open MSMs sharded over the N GPUs (swb_set_msm_shard), the
+partial commitments combined by the library's own NCCL communicator (swb_comm_init / swb_comm_sum_g1).
 Checks: the proof of the `mul_chain_1000` fixture has the committed sha256 on every rank (i.e. the bytes of
 a single GPU), a 2^log_n proof verifies, and prints the sharded proving time next to the single-GPU one.
 Launched by tests/test_gpu_marlin.py::test_sharded_proving_two_gpus when two GPUs are visible."""
@@ -45,7 +46,20 @@ def main():
     case = json.load(open(os.path.join(ROOT, "tests", "golden", "marlin_proofs.json")))["cases"]["mul_chain_1000"]
     # single-GPU timing first (no sharding), then sharded
     _, _, t_single = run((1 << log_n, 1 << log_n, 3 << log_n), (1 << log_n) - 2, 3, 5, 3)
-    be.set_msm_shard(rank, world, dev)
+    # the library's own communicator carries the partial commitments (one all-gather per prover round);
+    # SWB_DIST_CALLBACK=1 uses the python callback over torch.distributed instead
+    if os.environ.get("SWB_DIST_CALLBACK"):
+        be.set_msm_shard(rank, world, dev)
+    else:
+        be.comm_init(rank, world)
+        be.set_msm_shard(rank, world, use_comm=True)
+        # the exchange primitive itself: sum of k * G over the ranks, two points per call
+        from oracle import pyoracle as O
+        mine = np.concatenate([O.g1_mul(O.g1_generator(), rank + 1), O.g1_mul(O.g1_generator(), 10 * (rank + 1))])
+        got = be.comm_sum_g1(mine)
+        tot = world * (world + 1) // 2
+        want = np.concatenate([O.g1_mul(O.g1_generator(), tot), O.g1_mul(O.g1_generator(), 10 * tot)])
+        assert np.array_equal(O.g1_to_affine(got), O.g1_to_affine(want)), "swb_comm_sum_g1 gave a wrong sum"
     rng = Rng()
     srs = m.generate_universal_srs(*case["bounds"], rng)
     cs = ConstraintSystem.builtin("mul-chain", 1000, 7, 11)

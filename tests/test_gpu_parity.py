@@ -519,3 +519,43 @@ def test_ntt_four_pass_sizes(be, log_n):
             assert gv == want, (log_n, coset, i)
         # and back: the inverse restores the sparse input
         assert torch.equal(be.ntt_(ys, log_n, inverse=True, coset=coset), sparse)
+
+
+@pytest.mark.parametrize("tables", [False, True])
+def test_msm_bucket_shards_add_up(be, srs_points, tables):
+    """swb_msm_set_bucket_shard: the shares of the bucket ranges of all ranks add up to the full result -- on the
+    plain path (marked pairs) and with window tables (pairs compacted in the digits kernel), for uniform scalars and
+    for a distribution where almost everything lands in one rank's range; a rank that receives nothing returns the
+    identity.  (Run rank by rank on one GPU: the shares do not depend on where they are computed.)"""
+    n = 1 << 15
+    bases = be.load_bases(srs_points[:n])
+    if tables:
+        bases.precompute(11)
+    try:
+        uni = _uniform_mod_r(n, 77)
+        small = np.zeros((n, 4), dtype=np.uint64)
+        small[:, 0] = np.random.RandomState(5).randint(1, 4, size=n) * 8 + 1  # every digit in rank 0's buckets (b = 0 mod 8)
+        small[::97] = uni[::97]
+        for scalars in (uni, small):
+            dev = be.to_device(scalars)
+            full = be.msm(bases, dev)
+            want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(srs_points[:n]), scalars))
+            assert np.array_equal(O.g1_to_affine(full), want)
+            for world in (2, 8):
+                parts = []
+                for rank in range(world):
+                    be.set_msm_bucket_shard(rank, world)
+                    parts.append(be.msm(bases, dev))
+                    parts.append(be.msm(bases, scalars, offset=0))                 # host-buffer entry point, same share
+                be.set_msm_bucket_shard(0, 1)
+                parts = np.concatenate(parts)
+                assert np.array_equal(parts[0::2], parts[1::2])
+                assert np.array_equal(be.g1_sum(parts[0::2]), full), (tables, world)
+        # a rank whose buckets stay empty: the value 3 only has the digit 3 = bucket 2, which is rank 2's
+        be.set_msm_bucket_shard(7, 8)
+        only_small = np.zeros((n, 4), dtype=np.uint64)
+        only_small[:, 0] = 3
+        assert O.points_from_jacobian(be.msm(bases, be.to_device(only_small)))[0] is None
+    finally:
+        be.set_msm_bucket_shard(0, 1)
+        bases.free()
