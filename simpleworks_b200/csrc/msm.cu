@@ -195,6 +195,10 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
         pl.B >>= pl.shard_shift;
         pl.shard_rank = (uint32_t)c->bucket_rank;
         pl.compact = tables;
+    } else if (c->bucket_world > 1 && c->bucket_rank != 0) {
+        // too few buckets to split (tiny MSM, narrow window): rank 0 computes all of it, the others contribute the identity
+        sl.empty = true;
+        return SWB_OK;
     }
     pl.nb = (uint32_t)nwin * pl.B;
     pl.total = n * (size_t)ndig;

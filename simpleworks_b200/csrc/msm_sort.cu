@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
             s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
             if (montgomery) s = s.to_canonical();
             if (tab_stride) {
-                while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
+                if ((s.l[7] >> 28) != 0)                              // r < 2^253 < 2^28 * 2^224: anything below is canonical
+                    while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
                 uint32_t t[8];                                    // 2s >= r  <=>  s > r/2
                 uint32_t top = 0;
                 for (int k = 0; k < 8; k++) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
         // are ours and what carry entered them (two bit masks), so the second visit touches the kept windows alone.
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        uint64_t keep = 0, cin = 0;
+        uint32_t keep = 0, cin = 0;                        // table levels <= 32
         if (live) {
             uint32_t carry = 0;
             for (int w = 0; w < nwin; w++) {
@@ -118,21 +119,30 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
                     v = s.l[limb] >> off;
                     if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
                 }
-                cin |= (uint64_t)carry << w;
+                cin |= carry << w;
                 v = (v & ((1u << c) - 1u)) + carry;
                 if (v > B) { v = (1u << c) - v; carry = 1; } else carry = 0;
-                if (v && ((v - 1) & ((1u << shift) - 1u)) == rank) keep |= 1ull << w;
+                if (v && ((v - 1) & ((1u << shift) - 1u)) == rank) keep |= 1u << w;
             }
         }
-        const uint32_t mine = (uint32_t)__popcll(keep);
-        uint32_t my_off = 0;
-        if (mine) my_off = atomicAdd(&s_cnt, mine);
+        // offsets inside the block: prefix sum over the warp (shuffles), one shared-memory atomic per warp
+        const uint32_t mine = (uint32_t)__popc(keep), lane = threadIdx.x & 31u;
+        uint32_t incl = mine;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        uint32_t warp_base = 0;
+        if (lane == 31 && incl) warp_base = atomicAdd(&s_cnt, incl);
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+        const uint32_t my_off = warp_base + incl - mine;
         __syncthreads();
         if (threadIdx.x == 0) s_base = s_cnt ? atomicAdd(count, s_cnt) : 0u;
         __syncthreads();
         uint32_t at = s_base + my_off;
         while (keep) {
-            const int w = __ffsll((long long)keep) - 1;
+            const int w = __ffs((int)keep) - 1;
             keep &= keep - 1;
             const int bit = w * c, limb = bit >> 5, off = bit & 31;
             uint32_t v = 0;
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
                 v = s.l[limb] >> off;
                 if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
             }
-            v = (v & ((1u << c) - 1u)) + (uint32_t)((cin >> w) & 1u);
+            v = (v & ((1u << c) - 1u)) + ((cin >> w) & 1u);
             uint32_t neg = 0;
             if (v > B) { v = (1u << c) - v; neg = 1; }
             keys[at] = (v - 1) >> shift;

@@ -559,3 +559,22 @@ def test_msm_bucket_shards_add_up(be, srs_points, tables):
     finally:
         be.set_msm_bucket_shard(0, 1)
         bases.free()
+
+
+def test_msm_bucket_shards_tiny_msms(be, srs_points):
+    """MSMs too small to split by bucket (narrow windows): rank 0 returns everything, the other ranks the identity,
+    so the shares still add up (the prover's three-term blinder commitments go this way)."""
+    for n in (1, 3, 20, 40):
+        bases = be.load_bases(srs_points[:n])
+        scalars = _uniform_mod_r(n, 500 + n)
+        full = be.msm(bases, scalars)
+        try:
+            for world in (2, 8):
+                parts = []
+                for rank in range(world):
+                    be.set_msm_bucket_shard(rank, world)
+                    parts.append(be.msm(bases, scalars))
+                assert np.array_equal(be.g1_sum(np.concatenate(parts)), full), (n, world)
+        finally:
+            be.set_msm_bucket_shard(0, 1)
+            bases.free()
