@@ -165,7 +165,10 @@ def marlin_gpu_run(be, lg, proofs):
     rng = Rng()
     t0 = time.perf_counter(); srs = m.generate_universal_srs(1 << lg, 1 << lg, 3 << lg, rng); t1 = time.perf_counter()
     cs = ConstraintSystem.builtin("mul-chain", n, 3, 5)
+    m.profile(True)
     t2 = time.perf_counter(); pk, vk = m.generate_proving_and_verifying_keys(srs, cs); t3 = time.perf_counter()
+    index_phases = m.last_phases()
+    m.profile(False)
     # proofs on the plain MSM path first, then the SRS is told to build its window tables at the next
     # commitment (a long-lived prover gets there by itself after ~20 proofs) and the same number again
     ts_plain, ts, proof = [], [], None
@@ -182,7 +185,7 @@ def marlin_gpu_run(be, lg, proofs):
     tv = time.perf_counter(); ok = m.verify_proof(vk, _gen.fr_mont(3), proof); tv = time.perf_counter() - tv
     return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t3 - t2, "prove_s": min(ts[1:]), "prove_s_all": ts[1:],
             "prove_s_plain_msm_path": min(ts_plain), "prove_s_plain_all": ts_plain, "srs_window_tables_build_s": tune_s,
-            "prove_phases_ms": phases,
+            "index_phases_ms": index_phases, "prove_phases_ms": phases,
             "prove_s_note": "prove_s: SRS powers with window tables (swb_srs_set_tune_after; automatic after ~20 proofs), "
                             "prove_s_plain_msm_path: before them",
             "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts[1:]), "proof_bytes": len(proof)}, proof
@@ -479,7 +482,9 @@ def main():
     if not args.no_tables:
         with_tables = combine(be.msm(bases, scalars_dev))
         be.set_msm_table_policy(-1)
+        be.set_msm_pair_sums(0)           # (the cross-check also crosses the pair-sum passes: table path with, plain path without)
         plain = combine(be.msm(bases, scalars_dev))
+        be.set_msm_pair_sums(1)
         be.set_msm_table_policy(0)
         checks["tables_equal_plain_on_full_input"] = bool(np.array_equal(with_tables, plain))
         assert checks["tables_equal_plain_on_full_input"], "window-table path and plain path disagree on the full input"
@@ -502,7 +507,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = be.launch_count()
-    step_ms, acc_ms, stage_sum = [], [], {}
+    step_ms, acc_ms, pair_ms, stage_sum = [], [], [], {}
     for _ in range(args.steps):
         flush.zero_()
         barrier()
@@ -514,6 +519,7 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
         st = be.last_stages()
         acc_ms.append(st.get("accumulate", float("nan")))
+        pair_ms.append((st.get("pair_bwd"), st.get("pair_sums"), st.get("pair_slots_summed_millions")))
         for k, v in st.items():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
     launches = be.launch_count() - launches0
@@ -617,34 +623,63 @@ def main():
     imad_lo = be.measure_imad_peak("lo", 20000)
     mont = be.measure_mul_peak("fq", 4000)
     acc_avg_s = (sum(acc_ms) / len(acc_ms)) / 1e3
-    alg_lp = share_adds * FQ_MUL_PER_MIXED_ADD * LIMB_PRODUCTS_PER_FQ_MUL
-    achieved = alg_lp / acc_avg_s
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
     traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = tr.get(f"k_msm_accumulate@2^{args.log_n}/{world}")
-    except Exception:
-        pass
     alg_bytes = 128.0 * n_total / world
+    paired = pair_ms and pair_ms[0][0] is not None
+    xyzz_lp = share_adds * FQ_MUL_PER_MIXED_ADD * LIMB_PRODUCTS_PER_FQ_MUL      # what the XYZZ-only algorithm would multiply
+    if paired:
+        # batch-affine pair sums in front of the accumulation: the dominant kernel is k_pair_bwd (all its launches of a
+        # step summed), 5 Fq products per summed slot; the slots really summed are counted on the device
+        bwd_s = sum(p[0] for p in pair_ms) / len(pair_ms) / 1e3
+        pairs_s = sum(p[1] for p in pair_ms) / len(pair_ms) / 1e3
+        slots = sum(p[2] for p in pair_ms) / len(pair_ms) * 1e6
+        alg_lp = slots * 5 * LIMB_PRODUCTS_PER_FQ_MUL
+        kernel, kernel_s = "k_pair_bwd", bwd_s
+        units = (f"{slots:.0f} pair sums per GPU and step (levels 1-4 over {share_adds:.0f} sorted (bucket, point) pairs: {n_total} points x "
+                 f"{n_win} windows (c={c_bits}) / {world}) x 5 Fq mul x 288 limb-products")
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr.get(f"k_pair_bwd@2^{args.log_n}/{world}")
+        except Exception:
+            pass
+    else:
+        alg_lp = xyzz_lp
+        kernel, kernel_s = "k_msm_accumulate", acc_avg_s
+        units = (f"{share_adds:.0f} mixed additions per GPU ({n_total} points x {n_win} windows (c={c_bits}) / {world}) "
+                 "x 10 Fq mul x 288 limb-products")
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr.get(f"k_msm_accumulate@2^{args.log_n}/{world}")
+        except Exception:
+            pass
+    achieved = alg_lp / kernel_s
     roofline = {
-        "kernel": "k_msm_accumulate", "bound": "int32 IMAD pipe (not hbm/tensor: 377-bit modular arithmetic)",
+        "kernel": kernel, "bound": "int32 IMAD pipe (not hbm/tensor: 377-bit modular arithmetic)",
         "achieved": achieved / 1e12, "peak": imad_wide / 1e12, "unit": "T limb-products/s", "frac": achieved / imad_wide,
         "peak_source": "IMAD.WIDE issue rate measured in this run (swb_measure_imad_peak)",
         "frac_of_montgomery_loop_peak": achieved / mont["limb_products_per_s"],
         "imad32_peak_tops": imad_lo / 1e12, "montgomery_loop_peak_tlps": mont["limb_products_per_s"] / 1e12,
-        "kernel_ms": acc_avg_s * 1e3, "kernel_share_of_step": acc_avg_s * 1e3 / ms_per_step,
-        "algorithmic_units": f"{share_adds:.0f} mixed additions per GPU ({n_total} points x {n_win} windows (c={c_bits}) / {world}) "
-                             "x 10 Fq mul x 288 limb-products",
+        "kernel_ms": kernel_s * 1e3, "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
+        "algorithmic_units": units,
         "traffic": traffic,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (ms_per_step / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "note": "128 B/point algorithmic over the whole step; sanity counter only"},
     }
+    if paired:
+        # the same bucket sums through XYZZ mixed additions alone would take n * W * 10 products: what the pair-sum passes
+        # plus the remaining accumulation deliver, expressed in that currency
+        roofline["bucket_sums"] = {
+            "pair_sums_ms": pairs_s * 1e3, "accumulate_ms": acc_avg_s * 1e3,
+            "xyzz_equivalent_tlps": xyzz_lp / (pairs_s + acc_avg_s) / 1e12,
+            "xyzz_equivalent_frac_of_peak": xyzz_lp / (pairs_s + acc_avg_s) / imad_wide,
+            "note": "n*W*10*288 limb-products (SURVEY 8d's algorithmic count for XYZZ accumulation) / time of pair sums + accumulation; "
+                    "above the share the XYZZ kernel alone reached (0.88) because an affine pair sum needs 6 products, not 10"}
 
     progress("timed regions done")
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------------

@@ -172,6 +172,12 @@ int  swb_msm_set_bucket_shard(swb_ctx*, int rank, int world);
 int  swb_msm_plan(swb_ctx*, size_t n, int* window_bits, int* windows);
 /* window width override for tuning/tests (0 = automatic) */
 int  swb_msm_set_window_bits(swb_ctx*, int c);
+/* Batch-affine pair sums: before the bucket accumulation, neighbouring sorted positions of the same bucket are added in
+ * affine coordinates with one shared inversion per thread block (~6 field products per pair instead of the 10 of an
+ * XYZZ mixed addition), then the sums of neighbouring pairs, and so on for up to four levels, so that the accumulation adds
+ * one point per block of up to 16 positions.  1 = automatic (large MSMs with well-filled buckets; the default),
+ * 0 = never, 2..5 = always, with 1..4 levels.  Results are identical. */
+int  swb_msm_set_pair_sums(swb_ctx*, int policy);
 /* which path MSMs over bases with window tables take: 0 = automatic (the rule above), 1 = the table
  * path whatever n is, -1 = the plain path on level 0.  Results are identical; tests and bench.py use it
  * to compare the two paths on the same input. */

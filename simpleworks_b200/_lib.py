@@ -24,7 +24,7 @@ SYMBOLS = [
     "swb_profile_enable", "swb_profile_last",
     "swb_bases_load", "swb_bases_load_dev", "swb_bases_from_powers", "swb_bases_export", "swb_bases_precompute", "swb_bases_table_info",
     "swb_bases_len", "swb_bases_free",
-    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_g1_fr", "swb_msm_g1_batch_dev", "swb_set_msm_shard", "swb_comm_unique_id", "swb_comm_init", "swb_comm_info", "swb_comm_sum_g1", "swb_comm_destroy", "swb_msm_plan", "swb_msm_set_window_bits", "swb_msm_set_table_policy", "swb_msm_set_bucket_shard", "swb_g1_sum_jacobian",
+    "swb_msm_g1", "swb_msm_g1_dev", "swb_msm_g1_fr_dev", "swb_msm_g1_fr", "swb_msm_g1_batch_dev", "swb_set_msm_shard", "swb_comm_unique_id", "swb_comm_init", "swb_comm_info", "swb_comm_sum_g1", "swb_comm_destroy", "swb_msm_plan", "swb_msm_set_window_bits", "swb_msm_set_table_policy", "swb_msm_set_pair_sums", "swb_msm_set_bucket_shard", "swb_g1_sum_jacobian",
     "swb_fixed_base_powers",
     "swb_ntt_fr", "swb_ntt_fr_dev", "swb_ntt_fr_batch_dev",
     "swb_rng_test_rng", "swb_rng_from_seed", "swb_rng_from_entropy", "swb_rng_next_u64", "swb_rng_free",
@@ -120,6 +120,7 @@ def load() -> ctypes.CDLL:
         "swb_msm_plan": (i32, [vp, sz, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
         "swb_msm_set_window_bits": (i32, [vp, i32]),
         "swb_msm_set_table_policy": (i32, [vp, i32]),
+        "swb_msm_set_pair_sums": (i32, [vp, i32]),
         "swb_msm_set_bucket_shard": (i32, [vp, i32, i32]),
         "swb_g1_sum_jacobian": (i32, [vp, vp, sz, vp]),
         "swb_fixed_base_powers": (i32, [vp, vp, vp, sz, vp]),

@@ -302,6 +302,10 @@ class Backend:
         scalars on every rank); world <= 1 switches it off"""
         self._check(self._lib.swb_msm_set_bucket_shard(self._h, rank, world))
 
+    def set_msm_pair_sums(self, policy: int):
+        """batch-affine pair sums before the bucket accumulation: 0 never, 1 automatic, 2 always"""
+        self._check(self._lib.swb_msm_set_pair_sums(self._h, policy))
+
     def set_msm_table_policy(self, policy: int):
         """0 automatic, 1 always the window-table path when the bases have tables, -1 always the plain path"""
         self._check(self._lib.swb_msm_set_table_policy(self._h, policy))

@@ -180,6 +180,7 @@ void swb_destroy(swb_ctx* c) {
     for (auto& kv : c->scratch)
         if (kv.second.p) cudaFree(kv.second.p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->pair_count_host) cudaFreeHost(c->pair_count_host);
     if (c->tw_root) cudaFree(c->tw_root);
     if (c->tw_gen) cudaFree(c->tw_gen);
     if (c->tw_geninv) cudaFree(c->tw_geninv);

@@ -21,6 +21,7 @@ struct swb_ctx {
     std::string err;
     uint64_t launches = 0;
     int msm_window_override = 0;
+    int msm_pair_policy = 1;   // swb_msm_set_pair_sums: batch-affine pair sums before the accumulation (0 never, 1 automatic, 2 always)
     int msm_table_policy = 0;  // swb_msm_set_table_policy: -1 never, 0 automatic, 1 whenever the bases have tables
     int trace = 0;            // SWB_TRACE=1: per-stage CUDA-event timings on stderr
     int profile = 0;          // swb_profile_enable: keep the last call's stage timings
@@ -37,6 +38,7 @@ struct swb_ctx {
     std::map<std::string, Scratch> scratch;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    uint32_t* pair_count_host = nullptr;   // pinned word: summed slots of the last pair-sum pass (profiling)
 
     // MSM slots: slot 0 runs on `stream`; slots 1..MSM_SLOTS-1 have streams of their own (a normal one
     // for sort + accumulation, a high-priority one for the latency-bound bucket tail) and their own
@@ -127,7 +129,26 @@ struct StageTimer {
     swb_ctx* c;
     const char* what;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    // spans: kernels of one kind launched many times inside a stage (begin/end event pairs, summed per name)
+    struct Span { const char* name; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    // counters: 32-bit values in pinned host memory that a copy queued on the stream fills; reported in millions
+    std::vector<std::pair<const char*, const uint32_t*>> counters;
+    void counter(const char* name, const uint32_t* host_value) { if (on()) counters.emplace_back(name, host_value); }
     StageTimer(swb_ctx* ctx, const char* w) : c(ctx), what(w) { mark("start"); }
+    bool on() const { return c->trace || c->profile; }
+    void span_begin(const char* name) {
+        if (!on()) return;
+        Span s{name, nullptr, nullptr};
+        cudaEventCreate(&s.a);
+        cudaEventCreate(&s.b);
+        cudaEventRecord(s.a, c->stream);
+        spans.push_back(s);
+    }
+    void span_end() {
+        if (!on() || spans.empty()) return;
+        cudaEventRecord(spans.back().b, c->stream);
+    }
     void mark(const char* name) {
         if (!c->trace && !c->profile) return;
         cudaEvent_t e;
@@ -146,6 +167,25 @@ struct StageTimer {
             c->last_stages.emplace_back(marks[i].first, (double)ms);
             if (c->trace) fprintf(stderr, " %s=%.3fms", marks[i].first, ms);
         }
+        {
+            std::vector<std::pair<const char*, double>> sums;
+            for (auto& sp : spans) {
+                float ms = 0;
+                cudaEventSynchronize(sp.b);
+                cudaEventElapsedTime(&ms, sp.a, sp.b);
+                bool found = false;
+                for (auto& kv : sums)
+                    if (kv.first == sp.name) { kv.second += ms; found = true; }
+                if (!found) sums.emplace_back(sp.name, (double)ms);
+                cudaEventDestroy(sp.a);
+                cudaEventDestroy(sp.b);
+            }
+            for (auto& kv : sums) {
+                c->last_stages.emplace_back(kv.first, kv.second);
+                if (c->trace) fprintf(stderr, " [%s=%.3fms]", kv.first, kv.second);
+            }
+        }
+        for (auto& kv : counters) c->last_stages.emplace_back(kv.first, (double)*kv.second / 1e6);
         float tot = 0;
         cudaEventElapsedTime(&tot, marks.front().second, marks.back().second);
         c->last_stages.emplace_back("total", (double)tot);

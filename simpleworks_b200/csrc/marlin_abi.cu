@@ -397,8 +397,9 @@ struct GpuEngine {
     bool bucket_mode(const swb_bases* b) const {
         return sharding() && b && b->tab_w > 0 && (c->shard_world & (c->shard_world - 1)) == 0 && !getenv("SWB_SHARD_INDEX");
     }
+    // (sizes the SRS window tables: in a power-of-two world they will be used by bucket, i.e. on whole polynomials)
     size_t msm_local_count(size_t n) {
-        if (!sharding()) return n;
+        if (!sharding() || ((c->shard_world & (c->shard_world - 1)) == 0 && !getenv("SWB_SHARD_INDEX"))) return n;
         const size_t base = n / (size_t)c->shard_world, rem = n % (size_t)c->shard_world;
         return base + ((size_t)c->shard_rank < rem ? 1 : 0);
     }

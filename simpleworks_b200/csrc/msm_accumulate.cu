@@ -104,9 +104,91 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(G1Xyzz* __restrict__ par
     }
 }
 
+// The same walk over a range of sorted positions after msm_pairs.cu has pair-summed them: lvl[p / 2] = L > 0 says that the
+// 2^L positions starting at the even position p are one bucket's points and R_L[p >> L] is their affine sum -- ONE mixed
+// addition for the whole block; L = 0 leaves the two table points of (p, p + 1) to be added as in k_msm_accumulate.
+struct PairLevels {
+    const Fq* R[MSM_PAIR_MAX_LEVELS + 1];
+    const uint8_t* lvl;
+};
+__global__ void __launch_bounds__(128) k_msm_accumulate_paired(G1Xyzz* __restrict__ partial, uint32_t* __restrict__ pkey,
+                                                                const uint32_t* __restrict__ range_off,
+                                                                const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                                const Fq* __restrict__ bases, PairLevels pv, size_t total,
+                                                                size_t n, uint32_t B, uint32_t len, uint32_t nranges) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nranges) return;
+    const size_t p0 = (size_t)r * len;                      // len is a power of two >= 16: blocks of up to 16 positions never straddle ranges
+    const size_t p1 = p0 + len < total ? p0 + len : total;
+    uint32_t out = range_off[r];
+    uint32_t cur = 0xffffffffu;
+    G1Xyzz acc = G1Xyzz::identity();
+    uint32_t set_base = (uint32_t)(p0 / n) * B;
+    size_t set_end = (p0 / n + 1) * n;
+    // ONE point per iteration through ONE copy of the addition code, whatever its origin: lanes of a warp that are at
+    // different kinds of positions do not diverge into separate copies of a 3000-instruction addition.
+    size_t p = p0;                 // next position to look at (even unless `second`)
+    bool second = false;           // the second table point of an unsummed pair is due
+    while (p < p1) {
+        while (p >= set_end) {                               // the bucket set of position p (no division in the loop)
+            set_base += B;
+            set_end += n;
+        }
+        const uint32_t kl = keys[p];
+        uint32_t v = 0;
+        const Fq* src;
+        if (!second) {
+            const uint32_t L = pv.lvl[p >> 1];
+            if (L) {
+                src = pv.R[L] + 2 * (p >> L);
+                p += (size_t)1 << L;
+            } else {
+                v = vals[p];
+                src = bases + 2 * (size_t)(v & 0x7fffffffu);
+                second = p + 1 < p1;
+                p += 1;
+            }
+        } else {
+            v = vals[p];
+            src = bases + 2 * (size_t)(v & 0x7fffffffu);
+            second = false;
+            p += 1;
+        }
+        if (kl >= B) continue;                                   // zero digit / another rank's bucket
+        G1Aff pt = ld_aff(src, 0);
+        const uint32_t k = set_base + kl;
+        if (k != cur) {
+            if (cur != 0xffffffffu) {
+                partial[out] = acc;
+                pkey[out] = cur;
+                out++;
+            }
+            cur = k;
+            acc = G1Xyzz::identity();
+        }
+        if (pt.is_identity()) continue;
+        if (v >> 31) pt.y = pt.y.neg();
+        acc.add_affine(pt.x, pt.y);
+    }
+    if (cur != 0xffffffffu) {
+        partial[out] = acc;
+        pkey[out] = cur;
+    }
+}
+
 int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,
                           const uint32_t* sorted_vals, const Fq* bases) {
     if (pl.nranges == 0) return SWB_OK;      // a bucket shard that received no pairs
+    if (bf.pair_levels > 0) {
+        PairLevels pv{};
+        for (int l = 1; l <= bf.pair_levels; l++) pv.R[l] = bf.pair_sums[l];
+        pv.lvl = bf.pair_lvl;
+        k_msm_accumulate_paired<<<(pl.nranges + 127) / 128, 128, 0, c->stream>>>(bf.partial, bf.pkey, bf.range_off, sorted_keys,
+                                                                                sorted_vals, bases, pv, pl.total, pl.seg_len,
+                                                                                pl.B, pl.range_len, pl.nranges);
+        SWB_LAUNCH_CHECK(c, "k_msm_accumulate_paired");
+        return SWB_OK;
+    }
     k_msm_accumulate<<<(pl.nranges + 127) / 128, 128, 0, c->stream>>>(bf.partial, bf.pkey, bf.range_off, sorted_keys, sorted_vals,
                                                                      bases, pl.total, pl.seg_len, pl.B, pl.range_len, pl.nranges);
     SWB_LAUNCH_CHECK(c, "k_msm_accumulate");

@@ -6,6 +6,7 @@
 namespace swb {
 
 constexpr int MSM_MAX_WINDOWS = 128;
+constexpr int MSM_PAIR_MAX_LEVELS = 4;   // summed blocks of up to 16 positions (the shortest accumulation range)
 // block size of the heavy-bucket gather: a bucket that holds a large share of all points (scalars equal to
 // one, top window) has one partial sum per range, i.e. up to ~10^5 of them, summed by one block
 constexpr int MSM_HEAVY_THREADS = 256;
@@ -63,6 +64,9 @@ struct MsmBuffers {
     G1Xyzz* seg2;        // per-job partial sums and values of the bucket reduction
     G1Xyzz* wins;        // [2][MSM_MAX_WINDOWS]: weighted sums sum_k (k+1) B_k, then plain sums sum_k B_k (bucket shards)
     uint32_t* count;     // [1] pairs kept by the compacting digits kernel
+    int pair_levels;                           // levels of batch-affine pair sums in front of the accumulation (0 = none)
+    Fq* pair_sums[MSM_PAIR_MAX_LEVELS + 1];    // [l]: ceil(total / 2^l) slots of two field elements (msm_pairs.cu)
+    uint8_t* pair_lvl;                         // [ceil(total / 2)] level map read by k_msm_accumulate_paired
 };
 
 // msm_sort.cu: digits, sort, per-range run counts and their scan
@@ -71,6 +75,9 @@ int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const 
 // msm_accumulate.cu: one thread per range of sorted pairs -> partial sums
 int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,
                           const uint32_t* sorted_vals, const Fq* bases);
+// msm_pairs.cu: batch-affine sums of neighbouring same-bucket positions
+int msm_launch_pair_sums(swb_ctx* c, const MsmPlan& pl, Fq* const* R, uint8_t* lvl, int levels, const uint32_t* sorted_keys,
+                         const uint32_t* sorted_vals, const Fq* bases, StageTimer* tm);
 // msm_reduce.cu: partial sums -> buckets -> window sums
 int msm_launch_gather(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf);
 int msm_launch_reduce(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf);

@@ -76,6 +76,28 @@ int main() {
     g1_jac_t js2 = jac; orc_g1_double(&js2);
     if (!same_point(s2, js2)) bad++;
     if (!same_point(acc.dbl(), js2)) bad++;
+    // 4. binary-GCD inversion (msm_pairs.cu inverts with it) against the Fermat inverse, both fields, edge values
+    {
+        int before = bad;
+        for (int it = 0; it < 3000; it++) {
+            Fq a;
+            for (int i = 0; i < 12; i++) a.l[i] = (uint32_t)rng();
+            a.l[11] &= 0x00ffffffu;
+            if (it == 0) a = Fq::one();
+            if (it == 1) a = Fq::one().neg();
+            if (it == 2) { a = Fq::zero(); a.l[0] = 1; }          // raw limb 1 = R^-1
+            if (it == 3) a = Fq::one() + Fq::one();
+            const Fq i1 = a.inverse(), i2 = a.inverse_bingcd();
+            if (!(i1 == i2) || !((a * i2) == Fq::one())) bad++;
+            Fr b;
+            for (int i = 0; i < 8; i++) b.l[i] = (uint32_t)rng();
+            b.l[7] &= 0x0fffffffu;
+            const Fr j1 = b.inverse(), j2 = b.inverse_bingcd();
+            if (!(j1 == j2)) bad++;
+        }
+        if (!Fq::zero().inverse_bingcd().is_zero()) bad++;
+        printf("inverse mismatches: %d\n", bad - before);
+    }
     printf("total mismatches: %d\n", bad);
     return bad != 0;
 }

@@ -578,3 +578,66 @@ def test_msm_bucket_shards_tiny_msms(be, srs_points):
         finally:
             be.set_msm_bucket_shard(0, 1)
             bases.free()
+
+
+@pytest.mark.parametrize("tables", [False, True])
+def test_msm_pair_sums_forced(be, srs_points, tables):
+    """swb_msm_set_pair_sums(2 / 3 / 5): one, two and four levels of batch-affine pair sums in front of the accumulation, forced on inputs of every
+    shape -- uniform, all-equal scalars (one bucket per window holds everything), many zeros and ones, bases that are
+    repeated (P + P: x2 == x1, must fall back to the doubling), negated (P - P), at infinity, the point (0, 1) whose
+    x coordinate is zero like the identity marker's, odd lengths -- against the oracle and against the pass switched off."""
+    n = 6001
+    pts = srs_points[:n].copy()
+    ref = O.points_from_affine(pts[:4])
+    neg0 = O.affine_from_points([(ref[0][0], G.Q_MOD - ref[0][1])])[0]
+    for i in range(40, 80):
+        pts[i] = pts[0]
+    for i in range(80, 100):
+        pts[i] = neg0
+    pts[100] = O.affine_from_points([None])[0]
+    pts[101] = O.affine_from_points([None])[0]
+    if not tables:
+        pts[102] = O.affine_from_points([(0, 1)])[0]          # on the curve (order 3), x = 0; the table path needs subgroup points
+        pts[103] = O.affine_from_points([(0, G.Q_MOD - 1)])[0]
+    bases = be.load_bases(pts)
+    if tables:
+        bases.precompute(9)
+    uni = _uniform_mod_r(n, 31337)
+    same = np.repeat(_uniform_mod_r(1, 5), n, axis=0)
+    runs = uni.copy()
+    runs[40:104] = runs[0]                                      # the special bases share every digit: neighbours after the sort
+    runs[200:1200] = runs[200]
+    marl = uni.copy()
+    kind = np.random.RandomState(3).randint(0, 4, size=n)
+    marl[kind < 2] = 0
+    marl[kind == 2] = 0
+    marl[kind == 2, 0] = 1
+    try:
+        for scalars in (uni, same, runs, marl):
+            want = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(pts), scalars))
+            for m in (n, 4097, 2, 1):
+                sub = np.ascontiguousarray(scalars[:m])
+                if m != n:
+                    want_m = O.g1_to_affine(O.msm_variable_base(np.ascontiguousarray(pts[:m]), sub))
+                else:
+                    want_m = want
+                be.set_msm_pair_sums(0)
+                off = be.msm(bases, be.to_device(sub))
+                assert np.array_equal(O.g1_to_affine(off), want_m), m
+                for pol in (2, 3, 5):
+                    be.set_msm_pair_sums(pol)
+                    got = be.msm(bases, be.to_device(sub))
+                    assert np.array_equal(got, off), (m, pol)
+        # with bucket shards on top
+        be.set_msm_pair_sums(4)
+        full = be.msm(bases, be.to_device(uni))
+        parts = []
+        for rank in range(4):
+            be.set_msm_bucket_shard(rank, 4)
+            parts.append(be.msm(bases, be.to_device(uni)))
+        be.set_msm_bucket_shard(0, 1)
+        assert np.array_equal(be.g1_sum(np.concatenate(parts)), full)
+    finally:
+        be.set_msm_pair_sums(1)
+        be.set_msm_bucket_shard(0, 1)
+        bases.free()
