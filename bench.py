@@ -126,25 +126,30 @@ R_MOD = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
 
 
 def synth_scalars_host(n: int, seed: int) -> np.ndarray:
-    """canonical scalars uniform in [0, r) (SURVEY 8d distribution U): 253-bit draws, redrawn while >= r;
-    (n,4) uint64"""
+    """canonical scalars uniform in [0, r) (SURVEY 8d distribution U) by rejection sampling; (n,4) uint64"""
     rs = np.random.Generator(np.random.PCG64(seed))
     r_limbs = [(R_MOD >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
 
     def draw(m):
+        # uniform below (r_top + 1) * 2^192 -- the smallest such box around [0, r) -- so almost nothing is redrawn
         a = rs.integers(0, 2 ** 64, size=(m, 4), dtype=np.uint64)
-        a[:, 3] &= np.uint64((1 << 61) - 1)
+        a[:, 3] = rs.integers(0, r_limbs[3] + 1, size=m, dtype=np.uint64)
         return a
     a = draw(n)
+    # a draw is below r unless its top limb reaches r's; equality of the top limbs (probability 2^-61) is settled
+    # by the exact comparison
+    top = np.uint64(r_limbs[3])
     while True:
-        ge = np.ones(n, dtype=bool)
-        decided = np.zeros(n, dtype=bool)
-        for j in (3, 2, 1, 0):
-            lt = ~decided & (a[:, j] < np.uint64(r_limbs[j]))
-            gt = ~decided & (a[:, j] > np.uint64(r_limbs[j]))
-            ge[lt] = False
-            decided |= lt | gt
-        bad = np.nonzero(ge)[0]
+        bad = np.nonzero(a[:, 3] >= top)[0]
+        if len(bad):
+            sub = a[bad]
+            eq = sub[:, 3] == top
+            ge = sub[:, 3] > top
+            for j in (2, 1, 0):                       # lexicographic, only where the top limbs tie
+                ge |= eq & (sub[:, j] > np.uint64(r_limbs[j]))
+                eq &= sub[:, j] == np.uint64(r_limbs[j])
+            ge |= eq
+            bad = bad[ge]
         if len(bad) == 0:
             return a
         a[bad] = draw(len(bad))
