@@ -250,7 +250,7 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
         const double per_bucket = pl.nb ? (double)pl.total / (double)pl.nb : 0.0;
         int levels = 0;
         if (c->msm_pair_policy >= 2) levels = c->msm_pair_policy - 1;                 // forced: policy - 1 levels
-        else if (c->msm_pair_policy == 1 && pl.total >= ((size_t)1 << 26)) {      // measured: +9 % at 2^24 points, +12 % at 2^26, nothing at 2^22
+        else if (c->msm_pair_policy == 1 && pl.total >= ((size_t)1 << 27)) {      // measured: +9 % at 2^24 points, +12 % at 2^26, nothing at 2^22
             // a level pays while most aligned blocks of 2^L positions still lie inside one bucket
             while (levels < MSM_PAIR_MAX_LEVELS && per_bucket >= (double)(8u << levels)) levels++;
         }
