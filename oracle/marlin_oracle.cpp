@@ -32,6 +32,7 @@ struct CpuBases {
 };
 
 struct CpuEngine : HostVecOps {
+    static constexpr bool kDeviceIndex = false;     // index(): the host arithmetisation of marlin.hpp
     void vntt(Vec& v, uint32_t log_n, bool inverse, bool coset) {
         if (v.size() != ((size_t)1 << log_n)) throw MarlinError("vntt: size mismatch");
         orc_ntt(reinterpret_cast<fr_t*>(v.data()), log_n, inverse, coset, 0);

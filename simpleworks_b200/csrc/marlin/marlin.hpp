@@ -433,6 +433,39 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, const R1cs& cs, Proving
     pk->dom_h = Domain(ncons);
     pk->dom_x = Domain(ninst);
     const Domain& H = pk->dom_h;
+    typename Engine::Vec rowcol_v;
+    auto upload_rows = [&](const std::vector<SparseRow>& m) {
+        std::vector<uint32_t> start(ncons + 1, 0);
+        for (size_t r = 0; r < ncons; r++) start[r + 1] = start[r] + (uint32_t)row_of(m, r).e.size();
+        std::vector<uint32_t> col(start.back());
+        std::vector<Fr> coef(start.back());
+#pragma omp parallel for schedule(static)
+        for (size_t r = 0; r < m.size(); r++) {
+            uint32_t at = start[r];
+            for (auto& e : m[r].e) { col[at] = col_of(e.second); coef[at] = e.first; at++; }
+        }
+        return eng.csr_upload(start, col, coef, nullptr);
+    };
+    if constexpr (Engine::kDeviceIndex) {
+        // The engine arithmetises where its vectors live (index_ops.cu on the CUDA engine): the host only flattens the
+        // three matrices into CSR arrays and uploads them -- they are needed there anyway, for z_A, z_B, z_C.
+        ph.reset(); ph.reset(new ScopedPhase("i4_upload"));
+        pk->eng = srs.eng;
+        pk->m_a = upload_rows(cs.a);
+        pk->m_b = upload_rows(cs.b);
+        pk->m_c = upload_rows(cs.c);
+        ph.reset(); ph.reset(new ScopedPhase("i2_arith"));
+        auto out = eng.index_arith(pk->m_a, pk->m_b, pk->m_c, ncons, nvar, ninst, H);
+        const size_t nnz = out.nnz;
+        pk->info = IndexInfo{nvar, ncons, nnz, ninst};
+        pk->dom_k = Domain(nnz);
+        if (ahp_max_degree(pk->info.num_constraints, nvar, nnz) > srs.max_degree)
+            throw MarlinError("index: circuit exceeds the universal SRS bound");
+        pk->row_evals = std::move(out.row); pk->col_evals = std::move(out.col);
+        pk->val_a_evals = std::move(out.va); pk->val_b_evals = std::move(out.vb); pk->val_c_evals = std::move(out.vc);
+        rowcol_v = std::move(out.rowcol);
+        pk->m_t = out.m_t;
+    } else {
     ph.reset(); ph.reset(new ScopedPhase("i1_merge_rows"));
     // joint sparsity pattern, row by row, columns in increasing order; rows are independent, so
     // they are merged in parallel: pass 1 counts the distinct columns of each row, pass 2 fills
@@ -553,26 +586,17 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, const R1cs& cs, Proving
     ph.reset(); ph.reset(new ScopedPhase("i4_upload"));
     {
         pk->eng = srs.eng;          // lives as long as the SRS, which the key references anyway (ck.srs)
-        auto upload_rows = [&](const std::vector<SparseRow>& m) {
-            std::vector<uint32_t> start(ncons + 1, 0);
-            for (size_t r = 0; r < ncons; r++) start[r + 1] = start[r] + (uint32_t)row_of(m, r).e.size();
-            std::vector<uint32_t> col(start.back());
-            std::vector<Fr> coef(start.back());
-#pragma omp parallel for schedule(static)
-            for (size_t r = 0; r < m.size(); r++) {
-                uint32_t at = start[r];
-                for (auto& e : m[r].e) { col[at] = col_of(e.second); coef[at] = e.first; at++; }
-            }
-            return eng.csr_upload(start, col, coef, nullptr);
-        };
         pk->m_a = upload_rows(cs.a);
         pk->m_b = upload_rows(cs.b);
         pk->m_c = upload_rows(cs.c);
         pk->m_t = eng.csr_upload(pk->t_start, pk->t_row, pk->t_coef, &pk->t_mat);
     }
+    rowcol_v = eng.vfrom_ptr(rowcol.get(), pk->dom_k.n);
+    }
     ph.reset(); ph.reset(new ScopedPhase("i5_polys_commit"));
     const char* names[6] = {"row", "col", "a_val", "b_val", "c_val", "row_col"};
-    typename Engine::Vec rowcol_v = eng.vfrom_ptr(rowcol.get(), K.n);
+    const Domain& K = pk->dom_k;
+    const size_t nnz = pk->info.num_non_zero;
     const typename Engine::Vec* evs[6] = {&pk->row_evals, &pk->col_evals, &pk->val_a_evals, &pk->val_b_evals, &pk->val_c_evals, &rowcol_v};
     pk->index_polys.clear();
     for (int i = 0; i < 6; i++) {

@@ -4,6 +4,7 @@
 // engine in libswb200.
 #include "ctx.hpp"
 #include "marlin/c_api_impl.hpp"
+#include "index_ops.hpp"
 #include "marlin_ops.hpp"
 #include "polyops.hpp"
 
@@ -239,7 +240,7 @@ struct GpuEngine {
         uint32_t *start = nullptr, *col = nullptr;
         Fr* coef = nullptr;
         uint8_t* tag = nullptr;
-        size_t nrows = 0;
+        size_t nrows = 0, nnz = 0;
     };
     template <class T>
     T* upload(const std::vector<T>& h) {
@@ -252,12 +253,44 @@ struct GpuEngine {
                      const std::vector<uint8_t>* tag) {
         DevCsr* m = new DevCsr();
         m->nrows = start.size() - 1;
+        m->nnz = col.size();
         m->start = upload(start);
         m->col = upload(col);
         m->coef = upload(coef);
         if (tag) m->tag = upload(*tag);
         cu(cudaStreamSynchronize(c->stream), "sync");        // the host vectors may be temporaries
         return m;
+    }
+    // Marlin's index arithmetisation on the device (index_ops.cu): joint sparsity pattern of the three uploaded matrices,
+    // the six evaluation vectors on K and the column-grouped copy for the prover's t polynomial
+    static constexpr bool kDeviceIndex = true;
+    struct IndexOut { size_t nnz = 0; Vec row, col, va, vb, vc, rowcol; void* m_t = nullptr; };
+    IndexOut index_arith(void* ha, void* hb, void* hc, size_t ncons, size_t nvar, size_t ninst, const Domain& H) {
+        OpTimer ot_(c, "index_arith");
+        const DevCsr* ms[3] = {static_cast<DevCsr*>(ha), static_cast<DevCsr*>(hb), static_cast<DevCsr*>(hc)};
+        IndexCsr in[3];
+        for (int w = 0; w < 3; w++) {
+            in[w].start = ms[w]->start; in[w].col = ms[w]->col; in[w].coef = ms[w]->coef; in[w].nnz = ms[w]->nnz;
+        }
+        if (ncons >= ((size_t)1 << 31) || nvar >= ((size_t)1 << 31)) throw MarlinError("index: constraint system too large");
+        IndexJoint j;
+        ck(index_joint_dev(c, in, (uint32_t)ncons, (uint32_t)nvar, (uint32_t)ninst, (uint32_t)H.n, &j), "index (joint pattern)");
+        IndexOut out;
+        out.nnz = j.nnz;
+        out.row = alloc(j.kn); out.col = alloc(j.kn); out.va = alloc(j.kn); out.vb = alloc(j.kn); out.vc = alloc(j.kn);
+        out.rowcol = alloc(j.kn);
+        Vec hel = vdomain(H.log_n);
+        DevCsr* t = new DevCsr();
+        t->nrows = H.n;
+        t->nnz = j.total;
+        cu(cudaMalloc((void**)&t->start, (H.n + 1) * sizeof(uint32_t)), "cudaMalloc");
+        cu(cudaMalloc((void**)&t->col, ((size_t)j.total + 1) * sizeof(uint32_t)), "cudaMalloc");
+        cu(cudaMalloc((void**)&t->coef, ((size_t)j.total + 1) * sizeof(Fr)), "cudaMalloc");
+        cu(cudaMalloc((void**)&t->tag, (size_t)j.total + 1), "cudaMalloc");
+        out.m_t = t;
+        ck(index_fill_dev(c, in, (uint32_t)ncons, (uint32_t)ninst, (uint32_t)H.n, j, hel.p, H.size_inv, out.row.p, out.col.p, out.va.p,
+                          out.vb.p, out.vc.p, out.rowcol.p, t->start, t->col, t->tag, t->coef), "index (evaluations)");
+        return out;
     }
     void csr_free(void* h) {
         DevCsr* m = static_cast<DevCsr*>(h);
