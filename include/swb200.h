@@ -274,10 +274,24 @@ int  swb_marlin_verify(swb_ctx*, const swb_vk*, const swb_fr* public_inputs, siz
                        swb_rng*, int* ok);
 void swb_bytes_free(uint8_t*);
 /* serialize_verifying_key / deserialize_verifying_key (reference src/marlin/serialization.rs:19-31);
- * NULL on malformed input.  (Proving keys hold the device-resident committer key and are not
- * serialised.) */
+ * NULL on malformed input. */
 int  swb_vk_serialize(const swb_vk*, uint8_t** bytes, size_t* len);
 swb_vk* swb_vk_deserialize(const uint8_t* bytes, size_t len);
+/* deserialize_proof / serialize_proof as objects (serialization.rs:5-17): NULL unless the bytes are a canonical
+ * proof (every point on the curve, in the subgroup, coordinates and scalars reduced, nothing trailing);
+ * swb_marlin_verify_proof = verify_proof on the object (mod.rs:79-86). */
+typedef struct swb_proof swb_proof;
+swb_proof* swb_proof_deserialize(const uint8_t* bytes, size_t len);
+int  swb_proof_serialize(const swb_proof*, uint8_t** bytes, size_t* len);
+void swb_proof_free(swb_proof*);
+int  swb_marlin_verify_proof(swb_ctx*, const swb_vk*, const swb_fr* public_inputs, size_t n, const swb_proof*, swb_rng*, int* ok);
+/* serialize_proving_key / deserialize_proving_key (serialization.rs:33-45).  Like upstream's, the bytes carry the
+ * committer key (all SRS powers up to max_degree, 96 bytes each) next to the constraint matrices, so a key loads
+ * without the SRS it was indexed from; the layout ("SWBPK001", csrc/marlin_abi.cu) is this library's own.  Loading
+ * re-derives the index on the device and fails unless it reproduces the verifying key stored in the bytes, which
+ * is returned through vk (may be NULL). */
+int  swb_pk_serialize(swb_ctx*, const swb_pk*, const swb_vk*, uint8_t** bytes, size_t* len);
+int  swb_pk_deserialize(swb_ctx*, const uint8_t* bytes, size_t len, swb_pk** pk, swb_vk** vk);
 /* R1CS interchange ("SWBR1CS1", layout in csrc/marlin/r1cs.hpp and INTEGRATION.md): constraint
  * systems synthesised by the reference's Rust gadgets, exported from ConstraintSystemRef */
 swb_r1cs* swb_r1cs_read(const uint8_t* bytes, size_t len);

@@ -32,7 +32,7 @@ SYMBOLS = [
     "swb_r1cs_free",
     "swb_marlin_profile_enable", "swb_marlin_last_phases", "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_set_tune_after", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
     "swb_marlin_prove", "swb_marlin_verify", "swb_bytes_free",
-    "swb_vk_serialize", "swb_vk_deserialize", "swb_r1cs_read", "swb_r1cs_write",
+    "swb_vk_serialize", "swb_vk_deserialize", "swb_proof_deserialize", "swb_proof_serialize", "swb_proof_free", "swb_marlin_verify_proof", "swb_pk_serialize", "swb_pk_deserialize", "swb_r1cs_read", "swb_r1cs_write",
 ]
 
 _lib = None
@@ -115,6 +115,12 @@ def load() -> ctypes.CDLL:
         "swb_bytes_free": (None, [ctypes.POINTER(ctypes.c_uint8)]),
         "swb_vk_serialize": (i32, [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
         "swb_vk_deserialize": (vp, [ctypes.c_char_p, sz]),
+        "swb_proof_deserialize": (vp, [ctypes.c_char_p, sz]),
+        "swb_proof_serialize": (i32, [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
+        "swb_proof_free": (None, [vp]),
+        "swb_marlin_verify_proof": (i32, [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i32)]),
+        "swb_pk_serialize": (i32, [vp, vp, vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
+        "swb_pk_deserialize": (i32, [vp, ctypes.c_char_p, sz, pvp, pvp]),
         "swb_r1cs_read": (vp, [ctypes.c_char_p, sz]),
         "swb_r1cs_write": (i32, [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(sz)]),
         "swb_msm_plan": (i32, [vp, sz, ctypes.POINTER(i32), ctypes.POINTER(i32)]),

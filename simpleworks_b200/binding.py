@@ -550,6 +550,44 @@ class Marlin:
         self._lib.swb_bytes_free(p)
         return out
 
+    def serialize_proving_key(self, pk, vk) -> bytes:
+        """serialize_proving_key (src/marlin/serialization.rs:33-39): committer key + constraint matrices + verifying key"""
+        p = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self.be._check(self._lib.swb_pk_serialize(self.be._h, pk, vk, ctypes.byref(p), ctypes.byref(n)))
+        out = ctypes.string_at(p, n.value)
+        self._lib.swb_bytes_free(p)
+        return out
+
+    def deserialize_proving_key(self, data: bytes):
+        """deserialize_proving_key (serialization.rs:41-45) -> (pk, vk); the index is re-derived on the device and must
+        reproduce the stored verifying key"""
+        pk, vk = _Handle(), _Handle()
+        self.be._check(self._lib.swb_pk_deserialize(self.be._h, data, len(data), ctypes.byref(pk), ctypes.byref(vk)))
+        return pk.bind(self._lib.swb_pk_free, self.be), vk.bind(self._lib.swb_vk_free)
+
+    def deserialize_proof(self, data: bytes):
+        """deserialize_proof (serialization.rs:14-17): an owned proof object, or SwbError for non-canonical bytes"""
+        h = self._lib.swb_proof_deserialize(data, len(data))
+        if not h:
+            raise SwbError("malformed proof")
+        return _Handle(h).bind(self._lib.swb_proof_free)
+
+    def serialize_proof(self, proof) -> bytes:
+        p = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self.be._check(self._lib.swb_proof_serialize(proof, ctypes.byref(p), ctypes.byref(n)))
+        out = ctypes.string_at(p, n.value)
+        self._lib.swb_bytes_free(p)
+        return out
+
+    def verify_proof_object(self, vk, public_inputs: np.ndarray, proof, rng: "Rng | None" = None) -> bool:
+        ok = ctypes.c_int()
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+        self.be._check(self._lib.swb_marlin_verify_proof(self.be._h, vk, pi.ctypes.data, pi.shape[0], proof, rng._h if rng else None,
+                                                         ctypes.byref(ok)))
+        return bool(ok.value)
+
     def deserialize_verifying_key(self, data: bytes):
         h = self._lib.swb_vk_deserialize(data, len(data))
         if not h:

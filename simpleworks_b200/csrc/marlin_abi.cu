@@ -330,6 +330,34 @@ struct GpuEngine {
         ck(swb_bases_from_powers(c, &gj, &b, n, &out), "bases_from_powers");
         return out;
     }
+    // resident bases from host points (a deserialised committer key)
+    void* bases_load(const std::vector<G1Point>& pts) {
+        std::vector<swb_g1_affine> tmp(pts.size());
+        for (size_t i = 0; i < pts.size(); i++) {
+            memset(&tmp[i], 0, sizeof tmp[i]);
+            if (pts[i].infinity) tmp[i].infinity = 1;
+            else {
+                memcpy(tmp[i].x.l, pts[i].x.l, 48);
+                memcpy(tmp[i].y.l, pts[i].y.l, 48);
+            }
+        }
+        swb_bases* out = nullptr;
+        ck(swb_bases_load(c, tmp.data(), tmp.size(), &out), "bases_load");
+        return out;
+    }
+    // a device-resident CSR matrix back on the host (proving-key serialisation)
+    void csr_download(const void* h, std::vector<uint32_t>* start, std::vector<uint32_t>* col, std::vector<Fr>* coef) {
+        const DevCsr& m = *static_cast<const DevCsr*>(h);
+        start->resize(m.nrows + 1);
+        col->resize(m.nnz);
+        coef->resize(m.nnz);
+        cu(cudaMemcpyAsync(start->data(), m.start, (m.nrows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream), "D2H");
+        if (m.nnz) {
+            cu(cudaMemcpyAsync(col->data(), m.col, m.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream), "D2H");
+            cu(cudaMemcpyAsync(coef->data(), m.coef, m.nnz * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream), "D2H");
+        }
+        cu(cudaStreamSynchronize(c->stream), "sync");
+    }
     void export_bases(void* h, size_t offset, size_t n, G1Point* out) {
         std::vector<swb_g1_affine> tmp(n);
         ck(swb_bases_export(c, static_cast<swb_bases*>(h), offset, n, tmp.data()), "bases_export");
@@ -508,6 +536,7 @@ static void srs_release(swb_srs* s) {
     delete s;
 }
 struct swb_vk { VkHandle* h; };
+struct swb_proof { Proof p; };
 
 extern "C" {
 
@@ -653,6 +682,173 @@ int swb_vk_serialize(const swb_vk* vk, uint8_t** bytes, size_t* len) {
 swb_vk* swb_vk_deserialize(const uint8_t* bytes, size_t len) {
     VkHandle* h = bytes ? vk_from_bytes(bytes, len) : nullptr;
     return h ? new swb_vk{h} : nullptr;
+}
+
+// ---- proofs as objects (deserialize_proof / serialize_proof, reference src/marlin/serialization.rs:5-17) ----------
+swb_proof* swb_proof_deserialize(const uint8_t* bytes, size_t len) {
+    if (!bytes) return nullptr;
+    swb_proof* p = nullptr;
+    try {
+        p = new swb_proof();
+        if (!Proof::deserialize(bytes, len, &p->p)) { delete p; return nullptr; }
+        return p;
+    } catch (...) {
+        delete p;
+        return nullptr;
+    }
+}
+int swb_proof_serialize(const swb_proof* proof, uint8_t** bytes, size_t* len) {
+    if (!proof || !bytes || !len) return SWB_EARG;
+    *bytes = bytes_out(proof->p.serialize(), len);
+    return SWB_OK;
+}
+void swb_proof_free(swb_proof* p) { delete p; }
+int swb_marlin_verify_proof(swb_ctx* c, const swb_vk* vk, const swb_fr* public_inputs, size_t n, const swb_proof* proof, swb_rng* rng,
+                            int* ok) {
+    if (!vk || !ok || (!public_inputs && n) || !proof) return SWB_EARG;
+    size_t len = 0;
+    uint8_t* b = bytes_out(proof->p.serialize(), &len);
+    const int rc = swb_marlin_verify(c, vk, public_inputs, n, b, len, rng, ok);
+    free(b);
+    return rc;
+}
+
+// ---- proving keys (serialize_proving_key / deserialize_proving_key, serialization.rs:33-45) -------------------------
+// "SWBPK001" | u64 max_degree | g, gamma_g (97 B each) | h, beta_h (96 B compressed) | 3 powers of gamma_g (97 B) |
+// u64 n | n powers of g as raw Montgomery (x, y) pairs, 96 B each (the committer key; raw because decompressing
+// millions of points costs a square root each) | u64 len, verifying-key bytes | u64 len, SWBR1CS1 bytes of the padded,
+// squared constraint matrices (no assignment).  Like upstream, the key carries its committer key and needs no SRS to be
+// loaded again; unlike upstream the layout is this library's own (arkworks' is unpinned here).
+// Loading re-derives the index on the device from the matrices and refuses the key unless the verifying key it obtains
+// is byte-identical to the stored one.
+int swb_pk_serialize(swb_ctx* c, const swb_pk* pk, const swb_vk* vk, uint8_t** bytes, size_t* len) {
+    if (!c || !pk || !vk || !bytes || !len || !pk->srs) return SWB_EARG;
+    if (pk->srs->ctx != c) return swb::set_err(c, SWB_EARG, "%s", "pk_serialize: the proving key belongs to another context");
+    try {
+        GpuEngine eng(c);
+        const UniversalSrs<GpuEngine>& srs = *pk->srs->h->srs;
+        const ProvingKey<GpuEngine>& k = pk->h->pk;
+        std::vector<uint8_t> out;
+        const char magic[8] = {'S', 'W', 'B', 'P', 'K', '0', '0', '1'};
+        out.insert(out.end(), magic, magic + 8);
+        put_u64(out, srs.max_degree);
+        put_g1_uncompressed(out, srs.g);
+        put_g1_uncompressed(out, srs.gamma_g);
+        put_g2_compressed(out, srs.h);
+        put_g2_compressed(out, srs.beta_h);
+        if (srs.powers_of_gamma_g.size() != 3) throw MarlinError("pk_serialize: unexpected committer key");
+        for (auto& gp : srs.powers_of_gamma_g) put_g1_uncompressed(out, gp);
+        const size_t np = srs.max_degree + 1;
+        put_u64(out, np);
+        {
+            const size_t at = out.size();
+            out.resize(at + np * 96);
+            const size_t chunk = (size_t)1 << 18;
+            std::vector<G1Point> tmp(chunk);
+            for (size_t i = 0; i < np; i += chunk) {
+                const size_t cnt = np - i < chunk ? np - i : chunk;
+                eng.export_bases(srs.powers_of_g, i, cnt, tmp.data());
+                for (size_t j = 0; j < cnt; j++) {
+                    if (tmp[j].infinity) throw MarlinError("pk_serialize: identity among the SRS powers");
+                    memcpy(&out[at + (i + j) * 96], tmp[j].x.l, 48);
+                    memcpy(&out[at + (i + j) * 96 + 48], tmp[j].y.l, 48);
+                }
+            }
+        }
+        const std::vector<uint8_t> vkb = vk->h->vk.serialize();
+        put_u64(out, vkb.size());
+        out.insert(out.end(), vkb.begin(), vkb.end());
+        // the padded, squared matrices as the key holds them on the device
+        R1cs cs;
+        cs.num_instance = k.info.num_instance;
+        cs.num_witness = k.info.num_variables - k.info.num_instance;
+        std::vector<SparseRow>* rows[3] = {&cs.a, &cs.b, &cs.c};
+        void* ms[3] = {k.m_a, k.m_b, k.m_c};
+        for (int w = 0; w < 3; w++) {
+            std::vector<uint32_t> start, col;
+            std::vector<Fr> coef;
+            eng.csr_download(ms[w], &start, &col, &coef);
+            rows[w]->resize(k.info.num_constraints);
+            for (size_t r = 0; r + 1 < start.size() && r < rows[w]->size(); r++)
+                for (uint32_t e = start[r]; e < start[r + 1]; e++) (*rows[w])[r].e.push_back({coef[e], col[e]});
+        }
+        std::vector<uint8_t> csb;
+        r1cs_write(cs, &csb);
+        put_u64(out, csb.size());
+        out.insert(out.end(), csb.begin(), csb.end());
+        *bytes = bytes_out(out, len);
+        return SWB_OK;
+    } catch (const std::exception& e) {
+        return swb::set_err(c, SWB_EINTERNAL, "pk_serialize: %s", e.what());
+    }
+}
+
+int swb_pk_deserialize(swb_ctx* c, const uint8_t* bytes, size_t len, swb_pk** pk_out, swb_vk** vk_out) {
+    if (!c || !bytes || !pk_out) return SWB_EARG;
+    swb_srs* s = nullptr;
+    swb_pk* p = nullptr;
+    swb_vk* v = nullptr;
+    try {
+        const uint8_t *q = bytes, *end = bytes + len;
+        if (len < 8 || memcmp(q, "SWBPK001", 8) != 0) throw MarlinError("bad magic");
+        q += 8;
+        uint64_t max_degree, np, n;
+        if (!get_u64(q, end, &max_degree) || max_degree >= ((uint64_t)1 << 31)) throw MarlinError("bad max_degree");
+        auto get_g1_unc = [&](G1Point* out) {
+            if (end - q < 97) throw MarlinError("truncated");
+            Fq x, y;
+            if (!fq_from_canonical_bytes(q, &x) || !fq_from_canonical_bytes(q + 48, &y) || q[96] > 1) throw MarlinError("bad point");
+            out->infinity = q[96] != 0;
+            out->x = out->infinity ? Fq::zero() : x;
+            out->y = out->infinity ? Fq::zero() : y;
+            q += 97;
+        };
+        s = new swb_srs{GpuEngine(c), new SrsHandle<GpuEngine>(), c, 1};
+        s->h->srs.reset(new UniversalSrs<GpuEngine>());
+        UniversalSrs<GpuEngine>& srs = *s->h->srs;
+        srs.eng = &s->eng;
+        srs.max_degree = (size_t)max_degree;
+        get_g1_unc(&srs.g);
+        get_g1_unc(&srs.gamma_g);
+        if (!get_g2_compressed(q, end, &srs.h) || !get_g2_compressed(q, end, &srs.beta_h)) throw MarlinError("bad G2 point");
+        srs.powers_of_gamma_g.resize(3);
+        for (auto& gp : srs.powers_of_gamma_g) get_g1_unc(&gp);
+        if (!get_u64(q, end, &np) || np != max_degree + 1 || (uint64_t)(end - q) / 96 < np) throw MarlinError("bad committer key");
+        {
+            std::vector<G1Point> pts((size_t)np);
+            for (size_t i = 0; i < (size_t)np; i++) {
+                memcpy(pts[i].x.l, q + i * 96, 48);
+                memcpy(pts[i].y.l, q + i * 96 + 48, 48);
+                pts[i].infinity = false;
+            }
+            q += (size_t)np * 96;
+            srs.powers_of_g = s->eng.bases_load(pts);
+        }
+        if (!get_u64(q, end, &n) || (uint64_t)(end - q) < n) throw MarlinError("truncated verifying key");
+        const std::vector<uint8_t> vkb(q, q + n);
+        q += n;
+        if (!get_u64(q, end, &n) || (uint64_t)(end - q) != n) throw MarlinError("truncated constraint matrices");
+        std::unique_ptr<R1csHandle> cs(r1cs_from_bytes(q, (size_t)n));
+        if (!cs) throw MarlinError("malformed constraint matrices");
+        // re-derive the index on the device; the stored verifying key is the integrity check (it binds the matrices, the
+        // committer key and the index commitments together)
+        p = new swb_pk{nullptr, nullptr};
+        v = new swb_vk{nullptr};
+        GpuEngine eng(c);
+        std::string err;
+        if (Api::index(eng, s->h, cs.get(), &p->h, &v->h, &err)) throw MarlinError("index: " + err);
+        if (v->h->vk.serialize() != vkb) throw MarlinError("the key does not reproduce its verifying key");
+        p->srs = s;                 // the key owns the only reference to its committer key
+        *pk_out = p;
+        if (vk_out) *vk_out = v;
+        else swb_vk_free(v);
+        return SWB_OK;
+    } catch (const std::exception& e) {
+        if (p) { delete p->h; delete p; }
+        if (v) swb_vk_free(v);
+        if (s) srs_release(s);
+        return swb::set_err(c, SWB_EINTERNAL, "pk_deserialize: %s", e.what());
+    }
 }
 
 }  // extern "C"

@@ -209,3 +209,44 @@ def test_sharded_proving_two_gpus():
                         "--master-port", "29533", script, "14"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])["ok"]
+
+
+def test_proving_key_bytes_round_trip(gpu):
+    """serialize_proving_key / deserialize_proving_key (reference src/marlin/serialization.rs:33-45): a key loaded from
+    its bytes -- on a context that never saw the SRS -- proves the same bytes; tampered or truncated bytes are refused."""
+    from simpleworks_b200.binding import ConstraintSystem, Rng
+    rng = Rng()
+    srs = gpu.generate_universal_srs(400, 400, 1200, rng)
+    cs = ConstraintSystem.builtin("random-sparse", 300, 3, 41)
+    pk, vk = gpu.generate_proving_and_verifying_keys(srs, cs)
+    want = gpu.generate_proof(cs, pk, Rng())
+    blob = gpu.serialize_proving_key(pk, vk)
+    assert blob[:8] == b"SWBPK001" and len(blob) > (gpu.srs_max_degree(srs) + 1) * 96
+    vkb = gpu.serialize_verifying_key(vk)
+    pk.close(); srs.close()                                        # the loaded key must stand on its own
+    pk2, vk2 = gpu.deserialize_proving_key(blob)
+    assert gpu.serialize_verifying_key(vk2) == vkb
+    assert gpu.generate_proof(cs, pk2, Rng()) == want
+    assert gpu.serialize_proving_key(pk2, vk2) == blob
+    from simpleworks_b200._lib import SwbError
+    for bad in (blob[:-1], blob[:1000], b"SWBPK002" + blob[8:], blob[:200] + bytes([blob[200] ^ 1]) + blob[201:],
+                blob[:-40] + bytes([blob[-40] ^ 1]) + blob[-39:]):
+        with pytest.raises(SwbError):
+            gpu.deserialize_proving_key(bad)
+
+
+def test_proof_objects(gpu):
+    """deserialize_proof / serialize_proof / verify_proof on the object (serialization.rs:5-17, mod.rs:79-86)"""
+    import json
+    import os
+    from simpleworks_b200._lib import SwbError
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "marlin_proofs.json")))["cases"]["manual_constraints_a1_b1"]
+    proof_bytes, vk_bytes = bytes.fromhex(case["proof_hex"]), bytes.fromhex(case["vk_hex"])
+    vk = gpu.deserialize_verifying_key(vk_bytes)
+    proof = gpu.deserialize_proof(proof_bytes)
+    assert gpu.serialize_proof(proof) == proof_bytes
+    assert gpu.verify_proof_object(vk, O.fr_mont([1]), proof)
+    assert not gpu.verify_proof_object(vk, O.fr_mont([2]), proof)
+    for bad in (proof_bytes[:-1], proof_bytes + b"\x00", b"", proof_bytes[:16] + b"\xff" * 48 + proof_bytes[64:]):
+        with pytest.raises(SwbError):
+            gpu.deserialize_proof(bad)
