@@ -801,6 +801,7 @@ int swb_pk_deserialize(swb_ctx* c, const uint8_t* bytes, size_t len, swb_pk** pk
             out->infinity = q[96] != 0;
             out->x = out->infinity ? Fq::zero() : x;
             out->y = out->infinity ? Fq::zero() : y;
+            if (!out->infinity && (!(y.sqr() == x.sqr() * x + Fq::one()) || !g1_in_subgroup(*out))) throw MarlinError("point not in G1");
             q += 97;
         };
         s = new swb_srs{GpuEngine(c), new SrsHandle<GpuEngine>(), c, 1};
@@ -816,11 +817,26 @@ int swb_pk_deserialize(swb_ctx* c, const uint8_t* bytes, size_t len, swb_pk** pk
         if (!get_u64(q, end, &np) || np != max_degree + 1 || (uint64_t)(end - q) / 96 < np) throw MarlinError("bad committer key");
         {
             std::vector<G1Point> pts((size_t)np);
+            size_t off_curve = 0;
+#pragma omp parallel for schedule(static) reduction(+ : off_curve)
             for (size_t i = 0; i < (size_t)np; i++) {
                 memcpy(pts[i].x.l, q + i * 96, 48);
                 memcpy(pts[i].y.l, q + i * 96 + 48, 48);
                 pts[i].infinity = false;
+                // raw Montgomery limbs: reduced and on the curve (the subgroup is not re-checked point by point; the
+                // powers an index commits with are bound by the verifying-key comparison below)
+                bool ok = true;
+                for (int k = 11; k >= 0; k--) {
+                    if (pts[i].x.l[k] != FqParams::mod(k)) { ok = pts[i].x.l[k] < FqParams::mod(k); break; }
+                    if (k == 0) ok = false;
+                }
+                for (int k = 11; ok && k >= 0; k--) {
+                    if (pts[i].y.l[k] != FqParams::mod(k)) { ok = pts[i].y.l[k] < FqParams::mod(k); break; }
+                    if (k == 0) ok = false;
+                }
+                if (!ok || !(pts[i].y.sqr() == pts[i].x.sqr() * pts[i].x + Fq::one())) off_curve++;
             }
+            if (off_curve) throw MarlinError("committer key holds points that are not on the curve");
             q += (size_t)np * 96;
             srs.powers_of_g = s->eng.bases_load(pts);
         }
