@@ -17,7 +17,10 @@
 
 namespace swb {
 
-constexpr int NTT_THREADS = 256;
+#ifndef NTT_THREADS_DEF
+#define NTT_THREADS_DEF 256
+#endif
+constexpr int NTT_THREADS = NTT_THREADS_DEF;
 #ifndef NTT_TILE_LOG_DEF
 #define NTT_TILE_LOG_DEF 11
 #endif

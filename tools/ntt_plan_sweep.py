@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--sizes", default="16,18,20,21,22,23,24,25,26")
     ap.add_argument("--default-only", action="store_true")
+    ap.add_argument("--plan", default="", help="only this plan (digits separated by commas) beside the default, for the single size given")
     args = ap.parse_args()
     be = Backend(0)
     be.profile(True)
@@ -47,6 +48,8 @@ def main():
         cands += [tuple(reversed(p)) for p in plans(log_n) if tuple(reversed(p)) != p]
         if args.default_only:
             cands = [None]
+        if args.plan:
+            cands = [None, tuple(int(x) for x in args.plan.split(","))]
         for plan in cands:
             if plan is None:
                 os.environ.pop(f"SWB_NTT_PLAN_{log_n}", None)
