@@ -49,6 +49,8 @@ struct swb_ctx {
         cudaEvent_t ev = nullptr;
         void* host_wins = nullptr;     // pinned, MSM_MAX_WINDOWS XYZZ points
         int nwin = 0, cb = 0;
+        int nres = 1;                  // results the slot will deliver (vectors of a batch)
+        bool batched = false;          // one bucket set per vector, no Horner fold
         int shard_rank = 0, shard_world = 1;   // bucket shard this MSM was planned for (swb_msm_set_bucket_shard)
         bool active = false, empty = false;
     } msm_slot[MSM_SLOTS];
@@ -82,6 +84,8 @@ struct swb_bases {
 
 namespace swb {
 
+constexpr int MSM_MAX_BATCH = 16;   // MSMs that one batched call may hold (one bucket set each)
+
 int set_err(swb_ctx* c, int code, const char* fmt, ...);
 // wait for the context's stream and for the MSM slots' own streams (before device memory they may be
 // reading is released)
@@ -91,6 +95,11 @@ void sync_all_streams(swb_ctx* c);
 // queued on the context's stream), msm_end waits for it and finishes on the host.  A slot holds one
 // MSM at a time.
 int msm_begin(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery);
+// Several scalar vectors over one handle WITH window tables as ONE MSM pipeline (one sort, one accumulation, one bucket
+// reduction; a bucket set per vector): msm_end then delivers `count` results.  msm_can_batch says whether a list qualifies.
+bool msm_can_batch(swb_ctx* c, const swb_bases* bases, size_t count, const size_t* ns);
+int msm_begin_batch(swb_ctx* c, int slot, const swb_bases* bases, size_t count, const size_t* offsets, const void* const* scalars_dev,
+                    const size_t* ns, int montgomery);
 int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out);
 // Device blocks for short-lived vectors (the prover allocates and frees hundreds per proof).  All work of
 // a context is ordered on one stream, so a freed block can be handed to the next request at once;

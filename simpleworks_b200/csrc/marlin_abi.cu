@@ -392,7 +392,17 @@ struct GpuEngine {
     // collected later: two of them are in flight on the library's MSM slots, so the latency-bound
     // bucket tail of one runs under the accumulation of the next.  The scalars must stay alive until the
     // result has been collected.
-    struct Ticket { int slot; bool done; G1Point value; bool sharded; bool combined; swb_g1_jacobian share; };
+    // An MSM is first only NOTED (its scalars must stay alive until the result has been collected); the list is
+    // launched when a result is asked for: over window tables as ONE batched pipeline (msm_begin_batch: one sort, one
+    // accumulation, one bucket reduction for all commitments of a prover round), otherwise one after the other on the
+    // library's two MSM slots, whose bucket tails overlap with the next accumulation.
+    struct Ticket {
+        void* h; size_t offset; const Fr* scalars; size_t n;     // the request
+        bool launched, done, sharded, combined, by_bucket;
+        int slot;
+        G1Point value;
+        swb_g1_jacobian share;
+    };
     std::vector<Ticket> tickets;                           // ids ticket_base .. ; finished old ones are dropped in blocks
     size_t ticket_base = 0;
     long slot_owner[swb_ctx::MSM_SLOTS] = {-1, -1, -1};    // ticket id occupying each slot
@@ -409,17 +419,94 @@ struct GpuEngine {
         return p;
     }
     bool sharding() const { return c->shard_world > 1 && (c->shard_combine || c->comm); }
-    // finishes the local part of a ticket (this rank's share when sharded)
-    void collect(size_t id) {
-        Ticket& t = tickets.at(id - ticket_base);
-        if (t.done) return;
-        ck(msm_end(c, t.slot, &t.share), "msm");
-        slot_owner[t.slot] = -1;
+    // Power-of-two worlds shard by BUCKET (swb_msm_set_bucket_shard: every rank sees the whole polynomial -- it
+    // has it anyway -- and fills its interleaved share of the buckets, so accumulation AND bucket reduction shrink
+    // and the window width stays that of one GPU); other worlds by contiguous index range.
+    // (only over bases with window tables: on the plain path every rank would still sort all pairs, and the index
+    // split measured slightly faster -- 2^20 constraints on two GPUs: 0.248 s against 0.256 s)
+    bool bucket_mode(const swb_bases* b) const {
+        return sharding() && b && b->tab_w > 0 && (c->shard_world & (c->shard_world - 1)) == 0 && !getenv("SWB_SHARD_INDEX");
+    }
+    void finish(Ticket& t) {
         t.done = true;
         if (!t.sharded) {
             t.value = from_jacobian(t.share);
             t.combined = true;
         }
+    }
+    // this rank's part of ticket t as (offset, scalars, n)
+    void local_part(const Ticket& t, size_t* off, const Fr** sc, size_t* n) const {
+        *off = t.offset; *sc = t.scalars; *n = t.n;
+        if (t.sharded && !t.by_bucket) {       // contiguous share of the index range (remainder to the first ranks)
+            const size_t base = t.n / (size_t)c->shard_world, rem = t.n % (size_t)c->shard_world, r = (size_t)c->shard_rank;
+            const size_t lo = r * base + (r < rem ? r : rem);
+            *off = t.offset + lo; *sc = t.scalars + lo; *n = base + (r < rem ? 1 : 0);
+        }
+    }
+    void launch_single(size_t id) {
+        Ticket& t = tickets.at(id - ticket_base);
+        const int slot = next_slot;
+        next_slot = next_slot == 1 ? 2 : 1;
+        if (slot_owner[slot] >= 0) collect((size_t)slot_owner[slot]);
+        size_t off, n;
+        const Fr* sc;
+        local_part(t, &off, &sc, &n);
+        if (t.by_bucket) { c->bucket_rank = c->shard_rank; c->bucket_world = c->shard_world; }
+        const int rc = msm_begin(c, slot, static_cast<swb_bases*>(t.h), off, sc, n, 1);
+        if (t.by_bucket) { c->bucket_rank = 0; c->bucket_world = 1; }     // the plan of this MSM has captured it
+        ck(rc, "msm");
+        t.launched = true;
+        t.slot = slot;
+        slot_owner[slot] = (long)id;
+    }
+    // launches every noted ticket; runs of tickets over the same table-backed handle go out as batches
+    void flush() {
+        size_t k = 0;
+        while (k < tickets.size()) {
+            if (tickets[k].launched) { k++; continue; }
+            size_t e = k;
+            std::vector<size_t> offs, ns;
+            std::vector<const void*> scs;
+            while (e < tickets.size() && !tickets[e].launched && tickets[e].h == tickets[k].h &&
+                   tickets[e].sharded == tickets[k].sharded && tickets[e].by_bucket == tickets[k].by_bucket && e - k < (size_t)MSM_MAX_BATCH) {
+                size_t off, n;
+                const Fr* sc;
+                local_part(tickets[e], &off, &sc, &n);
+                offs.push_back(off); ns.push_back(n); scs.push_back(sc);
+                e++;
+            }
+            swb_bases* b = static_cast<swb_bases*>(tickets[k].h);
+            if (e - k >= 2 && msm_can_batch(c, b, e - k, ns.data())) {
+                // the slots must be idle: the batch runs on the context's stream with slot 0's scratch
+                for (int sl = 1; sl < swb_ctx::MSM_SLOTS; sl++)
+                    if (slot_owner[sl] >= 0) collect((size_t)slot_owner[sl]);
+                if (tickets[k].by_bucket) { c->bucket_rank = c->shard_rank; c->bucket_world = c->shard_world; }
+                int rc = msm_begin_batch(c, 0, b, e - k, offs.data(), scs.data(), ns.data(), 1);
+                if (tickets[k].by_bucket) { c->bucket_rank = 0; c->bucket_world = 1; }
+                ck(rc, "msm (batch)");
+                std::vector<swb_g1_jacobian> outs(e - k);
+                ck(msm_end(c, 0, outs.data()), "msm (batch)");
+                for (size_t q = k; q < e; q++) {
+                    tickets[q].launched = true;
+                    tickets[q].slot = 0;
+                    tickets[q].share = outs[q - k];
+                    finish(tickets[q]);
+                }
+            } else {
+                for (size_t q = k; q < e; q++) launch_single(ticket_base + q);
+            }
+            k = e;
+        }
+    }
+    // finishes the local part of a ticket (this rank's share when sharded)
+    void collect(size_t id) {
+        Ticket& t = tickets.at(id - ticket_base);
+        if (t.done) return;
+        if (!t.launched) flush();
+        if (t.done) return;
+        ck(msm_end(c, t.slot, &t.share), "msm");
+        slot_owner[t.slot] = -1;
+        finish(t);
     }
     // shares -> sums over all ranks.  With the library's communicator every share that is outstanding (the
     // commitments of a round are all submitted before the first result is asked for) goes into ONE all-gather;
@@ -449,15 +536,6 @@ struct GpuEngine {
             t.combined = true;
         }
     }
-    // scalars of an n-point prover MSM that this rank processes (swb_set_msm_shard)
-    // Power-of-two worlds shard by BUCKET (swb_msm_set_bucket_shard: every rank sees the whole polynomial -- it
-    // has it anyway -- and fills its interleaved share of the buckets, so accumulation AND bucket reduction shrink
-    // and the window width stays that of one GPU); other worlds by contiguous index range.
-    // (only over bases with window tables: on the plain path every rank would still sort all pairs, and the index
-    // split measured slightly faster -- 2^20 constraints on two GPUs: 0.248 s against 0.256 s)
-    bool bucket_mode(const swb_bases* b) const {
-        return sharding() && b && b->tab_w > 0 && (c->shard_world & (c->shard_world - 1)) == 0 && !getenv("SWB_SHARD_INDEX");
-    }
     // (sizes the SRS window tables: in a power-of-two world they will be used by bucket, i.e. on whole polynomials)
     size_t msm_local_count(size_t n) {
         if (!sharding() || ((c->shard_world & (c->shard_world - 1)) == 0 && !getenv("SWB_SHARD_INDEX"))) return n;
@@ -466,30 +544,19 @@ struct GpuEngine {
     }
     size_t msm_submit(void* h, size_t offset, const Vec& scalars, size_t n) {
         OpTimer ot_(c, "msm_submit");
-        const int slot = next_slot;
-        next_slot = next_slot == 1 ? 2 : 1;
-        if (slot_owner[slot] >= 0) collect((size_t)slot_owner[slot]);
         if (tickets.size() >= 128) {                       // batches are a handful of MSMs: these are long finished
             for (size_t i = 0; i < 64; i++) collect(ticket_base + i);
             combine_pending();
             tickets.erase(tickets.begin(), tickets.begin() + 64);
             ticket_base += 64;
         }
-        // multi-GPU proving: only this rank's contiguous share of the index range (remainder to the first ranks)
-        const bool sharded = sharding();
-        size_t lo = 0, cnt = n;
-        const bool by_bucket = bucket_mode(static_cast<swb_bases*>(h));
-        if (sharded && !by_bucket) {
-            const size_t base = n / (size_t)c->shard_world, rem = n % (size_t)c->shard_world, r = (size_t)c->shard_rank;
-            lo = r * base + (r < rem ? r : rem);
-            cnt = base + (r < rem ? 1 : 0);
-        }
-        if (by_bucket) { c->bucket_rank = c->shard_rank; c->bucket_world = c->shard_world; }
-        const int rc_begin = msm_begin(c, slot, static_cast<swb_bases*>(h), offset + lo, scalars.p + lo, cnt, 1);
-        if (by_bucket) { c->bucket_rank = 0; c->bucket_world = 1; }     // the plan of this MSM has captured it
-        ck(rc_begin, "msm");
-        tickets.push_back(Ticket{slot, false, G1Point::identity(), sharded, false, swb_g1_jacobian{}});
-        slot_owner[slot] = (long)(ticket_base + tickets.size() - 1);
+        Ticket t{};
+        t.h = h; t.offset = offset; t.scalars = scalars.p; t.n = n;
+        t.sharded = sharding();
+        t.by_bucket = bucket_mode(static_cast<swb_bases*>(h));
+        t.slot = -1;
+        t.value = G1Point::identity();
+        tickets.push_back(t);
         return ticket_base + tickets.size() - 1;
     }
     G1Point msm_result(size_t id) {

@@ -84,21 +84,48 @@ static int slot_prepare(swb_ctx* c, int slot) {
     return SWB_OK;
 }
 
-static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery);
+static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, const MsmBatch& batch, int montgomery);
 
-int msm_begin(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery) {
+// can these vectors run as ONE batched MSM (one bucket set each over the handle's window tables)?
+bool msm_can_batch(swb_ctx* c, const swb_bases* bases, size_t count, const size_t* ns) {
+    if (!bases || bases->tab_w == 0 || c->msm_window_override || c->msm_table_policy < 0 || count < 2 || count > (size_t)MSM_MAX_BATCH) return false;
+    size_t total = 0;
+    for (size_t k = 0; k < count; k++) total += ns[k];
+    // the shared rule of the table path, for the batch as a whole: a few points per bucket
+    return total < ((size_t)1 << 31) &&
+           (c->msm_table_policy > 0 || total * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1)) * count);
+}
+
+int msm_begin_batch(swb_ctx* c, int slot, const swb_bases* bases, size_t count, const size_t* offsets, const void* const* scalars_dev,
+                    const size_t* ns, int montgomery) {
     SWB_REQUIRE(c, slot >= 0 && slot < swb_ctx::MSM_SLOTS, "msm: bad slot");
     SWB_REQUIRE(c, !c->msm_slot[slot].active, "msm: slot already holds an MSM");
-    SWB_REQUIRE(c, bases != nullptr, "msm: NULL argument");
+    SWB_REQUIRE(c, bases != nullptr && count >= 1 && count <= (size_t)MSM_MAX_BATCH && offsets && scalars_dev && ns, "msm: bad batch");
     SWB_REQUIRE(c, bases->ctx == c, "msm: bases belong to another context");
-    SWB_REQUIRE(c, offset <= bases->n && n <= bases->n - offset, "msm: offset + n exceeds the loaded bases");
-    SWB_REQUIRE(c, n < ((size_t)1 << 31), "msm: n must be < 2^31");
-    SWB_REQUIRE(c, n == 0 || scalars_dev != nullptr, "msm: NULL scalars");
+    MsmBatch batch{};
+    size_t total = 0;
+    uint32_t kept = 0;
+    for (size_t k = 0; k < count; k++) {
+        SWB_REQUIRE(c, offsets[k] <= bases->n && ns[k] <= bases->n - offsets[k], "msm: offset + n exceeds the loaded bases");
+        SWB_REQUIRE(c, ns[k] == 0 || scalars_dev[k] != nullptr, "msm: NULL scalars");
+        // empty vectors keep their bucket set (it stays empty), so that results stay in the caller's order
+        batch.scalars[kept] = (const uint32_t*)scalars_dev[k];
+        batch.start[kept] = (uint32_t)total;
+        batch.offset[kept] = (uint32_t)offsets[k];
+        total += ns[k];
+        kept++;
+    }
+    SWB_REQUIRE(c, total < ((size_t)1 << 31), "msm: n must be < 2^31");
+    batch.start[kept] = (uint32_t)total;
+    batch.count = kept;
+    SWB_REQUIRE(c, count == 1 || msm_can_batch(c, bases, count, ns) || total == 0, "msm: these vectors cannot run as one batch");
     SWB_CUDA(c, cudaSetDevice(c->device));
     int rc = slot_prepare(c, slot);
     if (rc != SWB_OK) return rc;
     swb_ctx::MsmSlot& sl = c->msm_slot[slot];
+    const size_t n = total;
     sl.empty = n == 0;
+    sl.nres = (int)count;
     if (n == 0) {
         sl.active = true;
         return SWB_OK;
@@ -111,20 +138,25 @@ int msm_begin(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const
         c->stream = sl.work;
         c->scratch_slot = slot;
     }
-    rc = msm_enqueue(c, slot, bases, offset, scalars_dev, n, montgomery);
+    rc = msm_enqueue(c, slot, bases, batch, montgomery);
     c->stream = main_stream;
     c->scratch_slot = 0;
     if (rc == SWB_OK) sl.active = true;
     return rc;
 }
 
+int msm_begin(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery) {
+    return msm_begin_batch(c, slot, bases, 1, &offset, &scalars_dev, &n, montgomery);
+}
+
+// outs: one result per vector of the batch (one for a plain msm_begin)
 int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out) {
     SWB_REQUIRE(c, slot >= 0 && slot < swb_ctx::MSM_SLOTS && out, "msm: bad slot");
     swb_ctx::MsmSlot& sl = c->msm_slot[slot];
     SWB_REQUIRE(c, sl.active, "msm: slot holds no MSM");
     sl.active = false;
     if (sl.empty) {
-        xyzz_to_out(G1Xyzz::identity(), out);
+        for (int k = 0; k < sl.nres; k++) xyzz_to_out(G1Xyzz::identity(), out + k);
         return SWB_OK;
     }
     SWB_CUDA(c, cudaSetDevice(c->device));
@@ -151,6 +183,10 @@ int msm_end(swb_ctx* c, int slot, swb_g1_jacobian* out) {
         }
         return r;
     };
+    if (sl.batched) {                       // one bucket set per vector: its sum is the vector's result
+        for (int k = 0; k < sl.nres; k++) xyzz_to_out(set_sum(k), out + k);
+        return SWB_OK;
+    }
     // Horner over the bucket sets, most significant first
     G1Xyzz acc = set_sum(sl.nwin - 1);
     for (int w = sl.nwin - 2; w >= 0; w--) {
@@ -169,14 +205,16 @@ static int msm_run(swb_ctx* c, const swb_bases* bases, size_t offset, const void
     return msm_end(c, 0, out);
 }
 
-static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offset, const void* scalars_dev, size_t n, int montgomery) {
+static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, const MsmBatch& batch, int montgomery) {
     swb_ctx::MsmSlot& sl = c->msm_slot[slot];
-    // window tables are worth it once the shared buckets hold a few points each
-    const bool tables = bases->tab_w > 0 && !c->msm_window_override && c->msm_table_policy >= 0 &&
-                        (c->msm_table_policy > 0 || n * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1)));
+    const size_t n = batch.start[batch.count];
+    const bool batched = batch.count > 1;
+    // window tables are worth it once the shared buckets hold a few points each (a batch always runs over them)
+    const bool tables = batched || (bases->tab_w > 0 && !c->msm_window_override && c->msm_table_policy >= 0 &&
+                                    (c->msm_table_policy > 0 || n * (size_t)bases->tab_w >= ((size_t)8 << (bases->tab_c - 1))));
     const int cb = tables ? bases->tab_c : pick_window(c, n);
     const int ndig = tables ? bases->tab_w : (254 + cb - 1) / cb;
-    const int nwin = tables ? 1 : ndig;
+    const int nwin = tables ? (int)batch.count : ndig;        // bucket sets
     SWB_REQUIRE(c, ndig <= MSM_MAX_WINDOWS, "msm: too many windows");
     MsmPlan pl{};
     pl.n = n;
@@ -201,6 +239,7 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
         return SWB_OK;
     }
     pl.nb = (uint32_t)nwin * pl.B;
+    pl.key_space = tables ? pl.nb : pl.B;     // table path: one segment, the key says which set; plain path: a segment per set
     pl.total = n * (size_t)ndig;
     pl.seg_len = tables ? pl.total : n;
     SWB_REQUIRE(c, pl.total < ((size_t)1 << 32), "msm: n * windows must be < 2^32");
@@ -240,7 +279,7 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
     const uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;
     std::unique_ptr<StageTimer> tmp(slot == 0 ? new StageTimer(c, "msm") : nullptr);   // stage timing: slot 0 only
     struct { StageTimer* t; void mark(const char* n) { if (t) t->mark(n); } } tm{tmp.get()};
-    int rc = msm_launch_digits_sort(c, pl, bf, scalars_dev, montgomery, &sorted_keys, &sorted_vals, tmp.get());
+    int rc = msm_launch_digits_sort(c, pl, bf, batch, montgomery, &sorted_keys, &sorted_vals, tmp.get());
     if (rc != SWB_OK) return rc;
     tm.mark("count");
     // batch-affine pair sums first when buckets are well filled and the input is large enough to amortise the block-wide
@@ -264,13 +303,13 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
             }
             bf.pair_lvl = (uint8_t*)get_scratch(c, "msm_pair_lvl", (pl.total + 1) / 2 + 64);
             if (!bf.pair_lvl) return SWB_ENOMEM;
-            rc = msm_launch_pair_sums(c, pl, bf.pair_sums, bf.pair_lvl, levels, sorted_keys, sorted_vals, bases->xy + 2 * offset, tmp.get());
+            rc = msm_launch_pair_sums(c, pl, bf.pair_sums, bf.pair_lvl, levels, sorted_keys, sorted_vals, bases->xy, tmp.get());
             if (rc != SWB_OK) return rc;
             bf.pair_levels = levels;
             tm.mark("pair_sums");
         }
     }
-    rc = msm_launch_accumulate(c, pl, bf, sorted_keys, sorted_vals, bases->xy + 2 * offset);
+    rc = msm_launch_accumulate(c, pl, bf, sorted_keys, sorted_vals, bases->xy);
     if (rc != SWB_OK) return rc;
     tm.mark("accumulate");
     if (slot > 0) {
@@ -297,6 +336,7 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, size_t offs
 
     sl.nwin = nwin;
     sl.cb = cb;
+    sl.batched = tables && batched;
     sl.shard_rank = (int)pl.shard_rank;
     sl.shard_world = 1 << pl.shard_shift;
     SWB_CUDA(c, cudaMemcpyAsync(sl.host_wins, bf.wins, sizeof(G1Xyzz) * nwin, cudaMemcpyDeviceToHost, c->stream));
@@ -438,11 +478,21 @@ int swb_msm_g1_batch_dev(swb_ctx* c, const swb_bases* b, const size_t* offsets, 
                          size_t n_msms, int montgomery, swb_g1_jacobian* outs) {
     if (!c) return SWB_EARG;
     SWB_REQUIRE(c, n_msms == 0 || (offsets && scalars_dev && ns && outs), "msm_batch: NULL argument");
-    // two MSMs in flight on slots 1 and 2: the bucket tail of one runs under the accumulation of the next
     int rc = SWB_OK;
+    // over window tables: ONE pipeline for up to MSM_MAX_BATCH vectors at a time (a bucket set each)
+    size_t done = 0;
+    while (done < n_msms && rc == SWB_OK) {
+        size_t cnt = n_msms - done < (size_t)MSM_MAX_BATCH ? n_msms - done : (size_t)MSM_MAX_BATCH;
+        if (cnt < 2 || !msm_can_batch(c, b, cnt, ns + done)) break;
+        rc = msm_begin_batch(c, 0, b, cnt, offsets + done, scalars_dev + done, ns + done, montgomery);
+        if (rc == SWB_OK) rc = msm_end(c, 0, outs + done);
+        done += cnt;
+    }
+    if (rc != SWB_OK || done == n_msms) return rc;
+    // otherwise two MSMs in flight on slots 1 and 2: the bucket tail of one runs under the accumulation of the next
     size_t pending[swb_ctx::MSM_SLOTS] = {0, 0, 0};
     bool busy[swb_ctx::MSM_SLOTS] = {false, false, false};
-    for (size_t i = 0; i < n_msms && rc == SWB_OK; i++) {
+    for (size_t i = done; i < n_msms && rc == SWB_OK; i++) {
         const int slot = 1 + (int)(i & 1);
         if (busy[slot]) {
             rc = msm_end(c, slot, &outs[pending[slot]]);

@@ -185,12 +185,12 @@ int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, c
         pv.lvl = bf.pair_lvl;
         k_msm_accumulate_paired<<<(pl.nranges + 127) / 128, 128, 0, c->stream>>>(bf.partial, bf.pkey, bf.range_off, sorted_keys,
                                                                                 sorted_vals, bases, pv, pl.total, pl.seg_len,
-                                                                                pl.B, pl.range_len, pl.nranges);
+                                                                                pl.key_space, pl.range_len, pl.nranges);
         SWB_LAUNCH_CHECK(c, "k_msm_accumulate_paired");
         return SWB_OK;
     }
     k_msm_accumulate<<<(pl.nranges + 127) / 128, 128, 0, c->stream>>>(bf.partial, bf.pkey, bf.range_off, sorted_keys, sorted_vals,
-                                                                     bases, pl.total, pl.seg_len, pl.B, pl.range_len, pl.nranges);
+                                                                     bases, pl.total, pl.seg_len, pl.key_space, pl.range_len, pl.nranges);
     SWB_LAUNCH_CHECK(c, "k_msm_accumulate");
     return SWB_OK;
 }

@@ -33,8 +33,18 @@ inline uint32_t msm_reduce_seg_len(uint32_t nwin, uint32_t B) {
 // 256-byte boundary so that the accumulation kernel can read either with 16-byte loads
 inline size_t msm_alt_offset(size_t total) { return (total + 63) & ~(size_t)63; }
 
+
+// the scalar vectors of a (possibly batched) MSM: vector k has start[k + 1] - start[k] scalars whose bases begin at
+// record offset[k] of the handle
+struct MsmBatch {
+    const uint32_t* scalars[MSM_MAX_BATCH];
+    uint32_t start[MSM_MAX_BATCH + 1];
+    uint32_t offset[MSM_MAX_BATCH];
+    uint32_t count;
+};
+
 struct MsmPlan {
-    size_t n;            // points
+    size_t n;            // points (all vectors of a batch together)
     int cb;              // window bits
     int ndig;            // digits (windows) per scalar
     int nwin;            // bucket sets: ndig on the plain path, 1 with window tables
@@ -45,6 +55,8 @@ struct MsmPlan {
     bool compact;        // table path under bucket sharding: only the pairs of our buckets are kept (total is then
                          // known after the digits kernel)
     uint32_t nb;         // total buckets = nwin * B
+    uint32_t key_space;  // keys below this are buckets, the value itself marks "no bucket": B when every bucket set has its
+                         // own segment of the pair list, nb for a batch (sets told apart by the key, one segment)
     size_t total;        // n * ndig (bucket, point) pairs
     uint32_t range_len;  // sorted positions per accumulation thread
     uint32_t nranges;    // ceil(total / range_len)
@@ -70,7 +82,7 @@ struct MsmBuffers {
 };
 
 // msm_sort.cu: digits, sort, per-range run counts and their scan
-int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
+int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const MsmBatch& batch, int montgomery,
                            const uint32_t** sorted_keys, const uint32_t** sorted_vals, StageTimer* tm);
 // msm_accumulate.cu: one thread per range of sorted pairs -> partial sums
 int msm_launch_accumulate(swb_ctx* c, const MsmPlan& pl, const MsmBuffers& bf, const uint32_t* sorted_keys,

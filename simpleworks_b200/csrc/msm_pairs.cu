@@ -254,10 +254,10 @@ int msm_launch_pair_sums(swb_ctx* c, const MsmPlan& pl, Fq* const* R, uint8_t* l
             sc.flag = (uint8_t*)(sc.tile_prod + tiles);
             if (tm) tm->span_begin(L == 1 ? "pair_fwd_gather" : "pair_fwd_upper");
             if (L == 1)
-                k_pair_fwd<true><<<tiles, PAIR_THREADS, 0, c->stream>>>(sc, sorted_keys, sorted_vals, bases, total, pl.seg_len, pl.B,
+                k_pair_fwd<true><<<tiles, PAIR_THREADS, 0, c->stream>>>(sc, sorted_keys, sorted_vals, bases, total, pl.seg_len, pl.key_space,
                                                                          (uint32_t)L, chunk0, cs, M);
             else
-                k_pair_fwd<false><<<tiles, PAIR_THREADS, 0, c->stream>>>(sc, sorted_keys, sorted_vals, R[L - 1], total, pl.seg_len, pl.B,
+                k_pair_fwd<false><<<tiles, PAIR_THREADS, 0, c->stream>>>(sc, sorted_keys, sorted_vals, R[L - 1], total, pl.seg_len, pl.key_space,
                                                                           (uint32_t)L, chunk0, cs, M);
             SWB_LAUNCH_CHECK(c, "k_pair_fwd");
             if (tm) tm->span_end();

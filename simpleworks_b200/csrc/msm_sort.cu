@@ -43,11 +43,14 @@ __device__ __forceinline__ void fr_mod_minus(uint32_t* a) {       // a = r - a
 // (table path: one bucket set, so the order of the pairs is free) the marked pairs are not written at
 // all: a block counts what it keeps in shared memory, reserves the space with one atomicAdd on *count and
 // writes its pairs there -- the arrays the sort sees shrink with the number of ranks.
+// A batch (several scalar vectors over one bases handle, table path only) gives vector k its own bucket set: its keys are
+// k * Bloc + bucket, its points start at record batch.offset[k]; the marker is the number of buckets of the whole batch.
 template <bool COMPACT>
 __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                     const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
+                                                     MsmBatch batch, size_t n, int c, int nwin,
                                                      int montgomery, size_t tab_stride, uint32_t rank, uint32_t shift, uint32_t Bloc,
                                                      uint32_t* __restrict__ count) {
+    const uint32_t marker = Bloc * batch.count;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t B = 1u << (c - 1);
@@ -58,8 +61,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
         Fr s = Fr::zero();
         uint32_t flip = 0;
         const bool live = i < n;
+        uint32_t vec = 0;                                   // which vector of the batch scalar i belongs to
+        if (live)
+            while (vec + 1 < batch.count && (uint32_t)i >= batch.start[vec + 1]) vec++;
+        const uint32_t key0 = vec * Bloc;                   // first key of its bucket set
+        const size_t rec = live ? (size_t)batch.offset[vec] + (i - batch.start[vec]) : 0;      // its base record
         if (live) {
-            const uint4* q = reinterpret_cast<const uint4*>(scalars + 8 * i);
+            const uint4* q = reinterpret_cast<const uint4*>(batch.scalars[vec] + 8 * (i - batch.start[vec]));
             uint4 a = q[0], b = q[1];
             s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
             s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
@@ -92,8 +100,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
                 v = (v & ((1u << c) - 1u)) + carry;
                 uint32_t neg = 0;
                 if (v > B) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
-                const uint32_t key = (v && ((v - 1) & ((1u << shift) - 1u)) == rank) ? (v - 1) >> shift : Bloc;
-                const uint32_t val = (uint32_t)(tab_stride ? (size_t)w * tab_stride + i : i) | ((neg ^ flip) << 31);
+                const uint32_t key = (v && ((v - 1) & ((1u << shift) - 1u)) == rank) ? key0 + ((v - 1) >> shift) : marker;
+                const uint32_t val = (uint32_t)(tab_stride ? (size_t)w * tab_stride + rec : rec) | ((neg ^ flip) << 31);
                 emit(w, key, val);
             }
         };
@@ -153,8 +161,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
             v = (v & ((1u << c) - 1u)) + ((cin >> w) & 1u);
             uint32_t neg = 0;
             if (v > B) { v = (1u << c) - v; neg = 1; }
-            keys[at] = (v - 1) >> shift;
-            vals[at] = (uint32_t)((size_t)w * tab_stride + i) | ((neg ^ flip) << 31);
+            keys[at] = key0 + ((v - 1) >> shift);
+            vals[at] = (uint32_t)((size_t)w * tab_stride + rec) | ((neg ^ flip) << 31);
             at++;
         }
     }
@@ -195,7 +203,7 @@ static void msm_plan_ranges(swb_ctx* c, MsmPlan& pl) {
     pl.nranges = (uint32_t)((pl.total + len - 1) / len);
 }
 
-int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const void* scalars_dev, int montgomery,
+int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const MsmBatch& batch, int montgomery,
                            const uint32_t** sorted_keys, const uint32_t** sorted_vals, StageTimer* tm) {
     {
         size_t blocks = (pl.n + 255) / 256;
@@ -203,7 +211,7 @@ int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const 
         if (blocks > cap) blocks = cap;
         if (pl.compact) {
             SWB_CUDA(c, cudaMemsetAsync(bf.count, 0, sizeof(uint32_t), c->stream));
-            k_msm_digits<true><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb,
+            k_msm_digits<true><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, batch, pl.n, pl.cb,
                                                                          pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, bf.count);
             SWB_LAUNCH_CHECK(c, "k_msm_digits");
             // the number of pairs that fell into our bucket range sizes everything downstream
@@ -214,7 +222,7 @@ int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const 
             pl.seg_len = kept;
             msm_plan_ranges(c, pl);
         } else {
-            k_msm_digits<false><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, (const uint32_t*)scalars_dev, pl.n, pl.cb,
+            k_msm_digits<false><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, batch, pl.n, pl.cb,
                                                                           pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, nullptr);
             SWB_LAUNCH_CHECK(c, "k_msm_digits");
         }
@@ -230,13 +238,16 @@ int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const 
     uint32_t *sk = nullptr, *sv = nullptr;
     // keys are 0 .. B (B = 2^(cb-1) marks a zero digit): cb bits, sorted inside each bucket set's segment
     int key_bits = 1;
-    while ((1u << key_bits) <= pl.B) key_bits++;          // values 0 .. B
+    while ((1u << key_bits) <= pl.key_space) key_bits++;   // values 0 .. key_space
     const size_t alt = msm_alt_offset(pl.n * (size_t)pl.ndig);   // where the second halves of the buffers start
-    int rc = radix_sort_segmented(c, bf.keys, bf.keys + alt, bf.vals, bf.vals + alt, pl.seg_len, (uint32_t)pl.nwin, key_bits, &sk, &sv);
+    // segments of the pair list: one per bucket set on the plain path, a single one over window tables (where a batch tells its
+    // sets apart by the key)
+    const uint32_t nseg = pl.tab_stride ? 1u : (uint32_t)pl.nwin;
+    int rc = radix_sort_segmented(c, bf.keys, bf.keys + alt, bf.vals, bf.vals + alt, pl.seg_len, nseg, key_bits, &sk, &sv);
     if (rc != SWB_OK) return rc;
     if (tm) tm->mark("sort");
     SWB_CUDA(c, cudaMemsetAsync(bf.range_off, 0, ((size_t)pl.nranges + 1) * sizeof(uint32_t), c->stream));
-    k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.seg_len, pl.B, pl.range_len);
+    k_msm_range_count<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(bf.range_off, sk, total, pl.seg_len, pl.key_space, pl.range_len);
     SWB_LAUNCH_CHECK(c, "k_msm_range_count");
     rc = exclusive_scan_u32(c, bf.range_off, (size_t)pl.nranges + 1);
     if (rc != SWB_OK) return rc;
