@@ -451,9 +451,20 @@ void index(Engine& eng, const UniversalSrs<Engine>& srs, const R1cs& cs, Proving
         // three matrices into CSR arrays and uploads them -- they are needed there anyway, for z_A, z_B, z_C.
         ph.reset(); ph.reset(new ScopedPhase("i4_upload"));
         pk->eng = srs.eng;
-        pk->m_a = upload_rows(cs.a);
-        pk->m_b = upload_rows(cs.b);
-        pk->m_c = upload_rows(cs.c);
+        auto stage_rows = [&](const std::vector<SparseRow>& m) {
+            std::vector<uint32_t> start(ncons + 1, 0);
+            for (size_t r = 0; r < ncons; r++) start[r + 1] = start[r] + (uint32_t)row_of(m, r).e.size();
+            return eng.csr_upload_filled(start, [&](uint32_t* col, Fr* coef) {
+#pragma omp parallel for schedule(static)
+                for (size_t r = 0; r < m.size(); r++) {
+                    uint32_t at = start[r];
+                    for (auto& e : m[r].e) { col[at] = col_of(e.second); coef[at] = e.first; at++; }
+                }
+            });
+        };
+        pk->m_a = stage_rows(cs.a);
+        pk->m_b = stage_rows(cs.b);
+        pk->m_c = stage_rows(cs.c);
         ph.reset(); ph.reset(new ScopedPhase("i2_arith"));
         auto out = eng.index_arith(pk->m_a, pk->m_b, pk->m_c, ncons, nvar, ninst, H);
         const size_t nnz = out.nnz;

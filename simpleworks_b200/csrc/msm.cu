@@ -289,7 +289,10 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, const MsmBa
         const double per_bucket = pl.nb ? (double)pl.total / (double)pl.nb : 0.0;
         int levels = 0;
         if (c->msm_pair_policy >= 2) levels = c->msm_pair_policy - 1;                 // forced: policy - 1 levels
-        else if (c->msm_pair_policy == 1 && pl.total >= ((size_t)1 << 27)) {      // measured: +9 % at 2^24 points, +12 % at 2^26, nothing at 2^22
+        else if (c->msm_pair_policy == 1 &&
+                 (pl.total >= ((size_t)1 << 27) || (pl.total >= ((size_t)1 << 26) && per_bucket >= 128.0))) {
+            // measured: +9 % at 2^24 points, +12 % at 2^26, nothing at 2^22; a 1/8 bucket share of 2^26 (92 M pairs, 176 per
+            // bucket) still gains 3-7 %
             // a level pays while most aligned blocks of 2^L positions still lie inside one bucket
             while (levels < MSM_PAIR_MAX_LEVELS && per_bucket >= (double)(8u << levels)) levels++;
         }

@@ -18,6 +18,7 @@ def main():
     from simpleworks_b200.binding import Backend
     ap = argparse.ArgumentParser()
     ap.add_argument("--log-n", type=int, default=26)
+    ap.add_argument("--pairs", type=int, default=1, help="swb_msm_set_pair_sums policy")
     args = ap.parse_args()
     be = Backend(0)
     n = 1 << args.log_n
@@ -26,6 +27,7 @@ def main():
     print("tables", bases.table_info(), flush=True)
     dev = torch.from_numpy(bench.synth_scalars_host(n, 1234).view(np.int64)).to("cuda:0")
     be.profile(True)
+    be.set_msm_pair_sums(args.pairs)
     out = {}
     for world in (1, 2, 4, 8):
         rows = []
