@@ -14,11 +14,11 @@ single-GPU size.  Scalars are uniform in [0, r).
   value        points/s, whole job, scalars already resident in HBM, CUDA events, max over ranks
   e2e          the same through the host-buffer ABI call swb_msm_g1 (pinned host scalars -> H2D ->
                MSM -> result back on the host), every step
-  roofline     dominant kernel k_msm_accumulate: algorithmic limb-products (32x32->64 multiply-
-               accumulates) per launch / its CUDA-event time, against the IMAD.WIDE issue rate
-               measured on this GPU in the same run by a register-only probe (the MSM is
-               integer-pipe bound, not HBM bound; the HBM figure is reported beside it as the
-               sanity counter BASELINE.md asks for)
+  roofline     dominant kernel k_pair_bwd (batch-affine pair sums; k_msm_accumulate when pair sums are
+               off): algorithmic limb-products (32x32->64 multiply-accumulates) per launch / its
+               CUDA-event time, against the IMAD.WIDE issue rate measured on this GPU in the same run
+               by a register-only probe (the MSM is integer-pipe bound, not HBM bound; the HBM figure
+               is reported beside it as the sanity counter BASELINE.md asks for)
   cpu_baseline the C restatement of arkworks' VariableBaseMSM (oracle/, OpenMP over windows like
                rayon) on a bounded sample, host cores of this box            [N = 1, rank 0 only]
   extra.checks parity of exactly what was timed: the window-table result on the full input equals the
@@ -31,8 +31,10 @@ single-GPU size.  Scalars are uniform in [0, r).
 --impl reference: the CPU arm alone (arkworks-equivalent C port on all host cores; under torchrun
 rank 0 runs it, the other ranks exit) on the same config and metric.
 
-N > 1 (strong scaling): the same 2^log_n problem, bases and scalars sharded by contiguous index
-range across ranks, one NCCL all-gather of the 144-byte partial results, final sum on every rank.
+N > 1 (strong scaling): the same 2^log_n problem; every rank holds all bases with their window tables
+and fills the buckets b = rank (mod N) of the single shared bucket set (--shard bucket, the default), one
+all-gather of the 144-byte partial results inside the library (swb_comm_sum_g1), final sum on every rank.
+--shard index: the round-1 split by contiguous index range.
 """
 from __future__ import annotations
 

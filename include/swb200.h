@@ -156,8 +156,11 @@ int  swb_comm_destroy(swb_ctx*);
 /* n_msms independent MSMs over the same bases (the commitments of one prover round: ark-poly-commit's
  * `commit` loops over its polynomials): MSM i takes ns[i] device-resident scalars scalars_dev[i]
  * (canonical integers, or Montgomery values when montgomery != 0) against bases[offsets[i] ..] and writes
- * outs[i].  Two MSMs are in flight at a time on streams of their own, which hides the latency-bound
- * bucket reduction of one under the accumulation of the next; results equal n_msms single calls. */
+ * outs[i].  Over bases with window tables (swb_bases_precompute) up to 16 MSMs at a time run as ONE pipeline --
+ * one digits pass, one sort with the vector index in the key's top bits, one accumulation, one bucket reduction
+ * with a bucket set per vector -- so the per-MSM bucket tail and launch gaps are paid once per batch.  Otherwise
+ * two MSMs are in flight at a time on streams of their own, which hides the latency-bound bucket reduction of
+ * one under the accumulation of the next.  Results equal n_msms single calls either way. */
 int  swb_msm_g1_batch_dev(swb_ctx*, const swb_bases*, const size_t* offsets, const void* const* scalars_dev, const size_t* ns,
                           size_t n_msms, int montgomery, swb_g1_jacobian* outs);
 /* Bucket sharding over `world` GPUs (a power of two): every rank holds ALL bases and sees ALL scalars, but only

@@ -30,6 +30,41 @@ __device__ __forceinline__ void fr_mod_minus(uint32_t* a) {       // a = r - a
     }
 }
 
+// scalar i of the batch: canonical limbs (on the table path reduced to <= r/2, flip = 1 if it was negated), the first key of
+// its bucket set and its base record; false past the end
+__device__ __forceinline__ bool digits_load(const MsmBatch& batch, size_t i, size_t n, int montgomery, size_t tab_stride,
+                                            uint32_t Bloc, Fr& s, uint32_t& flip, uint32_t& key0, size_t& rec) {
+    s = Fr::zero();
+    flip = 0;
+    key0 = 0;
+    rec = 0;
+    if (i >= n) return false;
+    uint32_t vec = 0;                                   // which vector of the batch scalar i belongs to
+    while (vec + 1 < batch.count && (uint32_t)i >= batch.start[vec + 1]) vec++;
+    key0 = vec * Bloc;
+    rec = (size_t)batch.offset[vec] + (i - batch.start[vec]);
+    const uint4* q = reinterpret_cast<const uint4*>(batch.scalars[vec] + 8 * (i - batch.start[vec]));
+    uint4 a = q[0], b = q[1];
+    s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
+    s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
+    if (montgomery) s = s.to_canonical();
+    if (tab_stride) {
+        if ((s.l[7] >> 28) != 0)                              // r < 2^253 < 2^28 * 2^224: anything below is canonical
+            while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
+        uint32_t t[8];                                    // 2s >= r  <=>  s > r/2
+        uint32_t top = 0;
+        for (int k = 0; k < 8; k++) {
+            t[k] = (s.l[k] << 1) | top;
+            top = s.l[k] >> 31;
+        }
+        if (top || fr_geq_mod(t)) {
+            fr_mod_minus(s.l);
+            flip = 1;
+        }
+    }
+    return true;
+}
+
 // Plain path (tab_stride == 0): window w of scalar i -> keys[w*n + i] = |d| - 1 (or B when d == 0:
 // sorts to the end of the window's segment), vals[w*n + i] = i | sign << 31; nwin covers 254 bits so
 // that the top carry has a window of its own, and nothing is assumed about the bases.
@@ -58,112 +93,78 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t* __restrict__ keys,
     // compaction is a block-wide step, so every thread of the block runs the same number of rounds
     const size_t rounds = (n + stride - 1) / stride;
     for (size_t round = 0; round < rounds; round++, i += stride) {
-        Fr s = Fr::zero();
-        uint32_t flip = 0;
-        const bool live = i < n;
-        uint32_t vec = 0;                                   // which vector of the batch scalar i belongs to
-        if (live)
-            while (vec + 1 < batch.count && (uint32_t)i >= batch.start[vec + 1]) vec++;
-        const uint32_t key0 = vec * Bloc;                   // first key of its bucket set
-        const size_t rec = live ? (size_t)batch.offset[vec] + (i - batch.start[vec]) : 0;      // its base record
-        if (live) {
-            const uint4* q = reinterpret_cast<const uint4*>(batch.scalars[vec] + 8 * (i - batch.start[vec]));
-            uint4 a = q[0], b = q[1];
-            s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
-            s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
-            if (montgomery) s = s.to_canonical();
-            if (tab_stride) {
-                if ((s.l[7] >> 28) != 0)                              // r < 2^253 < 2^28 * 2^224: anything below is canonical
-                    while (fr_geq_mod(s.l)) fr_sub_mod(s.l);          // non-canonical input: reduce first
-                uint32_t t[8];                                    // 2s >= r  <=>  s > r/2
-                uint32_t top = 0;
-                for (int k = 0; k < 8; k++) {
-                    t[k] = (s.l[k] << 1) | top;
-                    top = s.l[k] >> 31;
-                }
-                if (top || fr_geq_mod(t)) {
-                    fr_mod_minus(s.l);
-                    flip = 1;
-                }
-            }
-        }
-        // walks the windows of s: emit(w, key, value)
-        auto walk = [&](auto&& emit) {
-            uint32_t carry = 0;
-            for (int w = 0; w < nwin; w++) {
-                const int bit = w * c, limb = bit >> 5, off = bit & 31;
-                uint32_t v = 0;
-                if (limb < 8) {
-                    v = s.l[limb] >> off;
-                    if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
-                }
-                v = (v & ((1u << c) - 1u)) + carry;
-                uint32_t neg = 0;
-                if (v > B) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
-                const uint32_t key = (v && ((v - 1) & ((1u << shift) - 1u)) == rank) ? key0 + ((v - 1) >> shift) : marker;
-                const uint32_t val = (uint32_t)(tab_stride ? (size_t)w * tab_stride + rec : rec) | ((neg ^ flip) << 31);
-                emit(w, key, val);
-            }
+        Fr s;
+        uint32_t flip, key0;
+        size_t rec;
+        const bool live = digits_load(batch, i, n, montgomery, tab_stride, Bloc, s, flip, key0, rec);
+        // Signed digits, lowest window first: the scalar sits in a 256-bit shift register (eight funnel shifts per
+        // window), so no limb is ever indexed by a run-time value.  next_digit returns |digit| and sets neg / carry.
+        const uint32_t cmask = (1u << c) - 1u;
+        auto next_digit = [&](uint32_t (&t)[8], uint32_t& carry, uint32_t& neg) -> uint32_t {
+            uint32_t v = (t[0] & cmask) + carry;
+#pragma unroll
+            for (int k = 0; k < 7; k++) t[k] = __funnelshift_r(t[k], t[k + 1], (uint32_t)c);
+            t[7] >>= c;
+            neg = v > B ? 1u : 0u;
+            if (neg) v = (1u << c) - v;
+            carry = neg;
+            return v;
         };
+        const uint32_t smask = (1u << shift) - 1u;
         if (!COMPACT) {
-            if (live)
-                walk([&](int w, uint32_t key, uint32_t val) {
+            if (live) {
+                uint32_t t[8], carry = 0, neg;
+#pragma unroll
+                for (int k = 0; k < 8; k++) t[k] = s.l[k];
+                for (int w = 0; w < nwin; w++) {
+                    const uint32_t v = next_digit(t, carry, neg);
+                    const uint32_t key = (v && ((v - 1) & smask) == rank) ? key0 + ((v - 1) >> shift) : marker;
                     keys[(size_t)w * n + i] = key;
-                    vals[(size_t)w * n + i] = val;
-                });
+                    vals[(size_t)w * n + i] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + rec : rec) | ((neg ^ flip) << 31);
+                }
+            }
             continue;
         }
-        // count, reserve (one global atomic per block and round), write.  The first walk only notes WHICH windows
-        // are ours and what carry entered them (two bit masks), so the second visit touches the kept windows alone.
+        // count, reserve (one global atomic per block and round), write.  The first walk notes WHICH windows are ours
+        // (a bit mask); a warp's pairs are laid out window by window, so that the lanes keeping window w write
+        // neighbouring slots (one ballot per window gives a lane its place) instead of every lane its own run.
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        uint32_t keep = 0, cin = 0;                        // table levels <= 32
+        uint32_t keep = 0;                                 // table levels <= 32
         if (live) {
-            uint32_t carry = 0;
+            uint32_t t[8], carry = 0, neg;
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[k] = s.l[k];
             for (int w = 0; w < nwin; w++) {
-                const int bit = w * c, limb = bit >> 5, off = bit & 31;
-                uint32_t v = 0;
-                if (limb < 8) {
-                    v = s.l[limb] >> off;
-                    if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
-                }
-                cin |= carry << w;
-                v = (v & ((1u << c) - 1u)) + carry;
-                if (v > B) { v = (1u << c) - v; carry = 1; } else carry = 0;
-                if (v && ((v - 1) & ((1u << shift) - 1u)) == rank) keep |= 1u << w;
+                const uint32_t v = next_digit(t, carry, neg);
+                if (v && ((v - 1) & smask) == rank) keep |= 1u << w;
             }
         }
-        // offsets inside the block: prefix sum over the warp (shuffles), one shared-memory atomic per warp
-        const uint32_t mine = (uint32_t)__popc(keep), lane = threadIdx.x & 31u;
-        uint32_t incl = mine;
-#pragma unroll
-        for (uint32_t d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t warp_total = 0;
+        for (int w = 0; w < nwin; w++) warp_total += (uint32_t)__popc(__ballot_sync(0xffffffffu, (keep >> w) & 1u));
         uint32_t warp_base = 0;
-        if (lane == 31 && incl) warp_base = atomicAdd(&s_cnt, incl);
-        warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
-        const uint32_t my_off = warp_base + incl - mine;
+        if (lane == 0 && warp_total) warp_base = atomicAdd(&s_cnt, warp_total);
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
         __syncthreads();
         if (threadIdx.x == 0) s_base = s_cnt ? atomicAdd(count, s_cnt) : 0u;
         __syncthreads();
-        uint32_t at = s_base + my_off;
-        while (keep) {
-            const int w = __ffs((int)keep) - 1;
-            keep &= keep - 1;
-            const int bit = w * c, limb = bit >> 5, off = bit & 31;
-            uint32_t v = 0;
-            if (limb < 8) {
-                v = s.l[limb] >> off;
-                if (off + c > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
+        if (warp_total == 0) continue;                     // warp-uniform
+        uint32_t seg = s_base + warp_base;
+        const uint32_t below = (1u << lane) - 1u;
+        uint32_t t[8], carry = 0, neg;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = s.l[k];
+        for (int w = 0; w < nwin; w++) {
+            const uint32_t v = next_digit(t, carry, neg);
+            const uint32_t mine = (keep >> w) & 1u;
+            const uint32_t who = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const uint32_t at = seg + (uint32_t)__popc(who & below);
+                keys[at] = key0 + ((v - 1) >> shift);
+                vals[at] = (uint32_t)((size_t)w * tab_stride + rec) | ((neg ^ flip) << 31);
             }
-            v = (v & ((1u << c) - 1u)) + ((cin >> w) & 1u);
-            uint32_t neg = 0;
-            if (v > B) { v = (1u << c) - v; neg = 1; }
-            keys[at] = key0 + ((v - 1) >> shift);
-            vals[at] = (uint32_t)((size_t)w * tab_stride + rec) | ((neg ^ flip) << 31);
-            at++;
+            seg += (uint32_t)__popc(who);
         }
     }
 }
@@ -193,6 +194,121 @@ __global__ void __launch_bounds__(256) k_msm_range_count(uint32_t* __restrict__ 
     }
 }
 
+// ---- window width known at compile time ---------------------------------------------------------------------
+// Every window position is then a constant: a digit costs two shifts instead of a walk of the whole scalar through a
+// shift register, and the digits and warp votes of all windows stay in registers, so nothing is computed twice
+// (ncu, 2^26 scalars, 1/8 bucket share: the generic kernel executes ~950 warp instructions per 32 scalars and is
+// issue-bound at 2.4-2.6 ms; this one 1.9 ms).  Measured and dropped: splitting the compaction into two
+// barrier-free kernels (count per warp, scan, place) -- 420 + 665 instructions per 32 scalars, 2.7 ms.
+template <int C>
+struct DigitsFixed {
+    static constexpr int NW = (254 + C - 1) / C;          // nwin <= NW
+    static constexpr uint32_t CM = (1u << C) - 1u, B = 1u << (C - 1);
+    // |digit| with the sign (already combined with `flip`) in bit 31; 0: nothing to add
+    static __device__ __forceinline__ void digits(const Fr& s, bool live, uint32_t flip, int nwin, uint32_t (&d)[NW]) {
+        uint32_t carry = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const int bit = w * C, limb = bit >> 5, off = bit & 31;
+            uint32_t v = 0;
+            if (limb < 8) {
+                v = s.l[limb] >> off;
+                if (off + C > 32 && limb + 1 < 8) v |= s.l[limb + 1] << (32 - off);
+            }
+            v = (v & CM) + carry;
+            const uint32_t neg = v > B ? 1u : 0u;
+            if (neg) v = (1u << C) - v;
+            carry = neg;
+            d[w] = (live && w < nwin && v) ? (v | ((neg ^ flip) << 31)) : 0u;
+        }
+    }
+};
+
+template <bool COMPACT, int C>
+__global__ void __launch_bounds__(256) k_msm_digits_fixed(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                           MsmBatch batch, size_t n, int nwin,
+                                                           int montgomery, size_t tab_stride, uint32_t rank, uint32_t shift, uint32_t Bloc,
+                                                           uint32_t* __restrict__ count) {
+    using D = DigitsFixed<C>;
+    const uint32_t marker = Bloc * batch.count;
+    const uint32_t smask = (1u << shift) - 1u;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    __shared__ uint32_t s_cnt, s_base;
+    const size_t rounds = (n + stride - 1) / stride;      // compaction is block-wide: every thread runs every round
+    for (size_t round = 0; round < rounds; round++, i += stride) {
+        Fr s;
+        uint32_t flip, key0;
+        size_t rec;
+        const bool live = digits_load(batch, i, n, montgomery, tab_stride, Bloc, s, flip, key0, rec);
+        uint32_t d[D::NW];
+        D::digits(s, live, flip, nwin, d);
+        if (!COMPACT) {
+            if (live) {
+#pragma unroll
+                for (int w = 0; w < D::NW; w++) {
+                    if (w < nwin) {
+                        const uint32_t v = d[w] & 0x7fffffffu;
+                        const uint32_t key = (v && ((v - 1) & smask) == rank) ? key0 + ((v - 1) >> shift) : marker;
+                        keys[(size_t)w * n + i] = key;
+                        vals[(size_t)w * n + i] = (uint32_t)(tab_stride ? (size_t)w * tab_stride + rec : rec) | (d[w] & 0x80000000u);
+                    }
+                }
+            }
+            continue;
+        }
+        // count, reserve (one global atomic per block and round), write; a warp's pairs are laid out window by window,
+        // so that the lanes keeping window w write neighbouring slots
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t who[D::NW], warp_total = 0;
+#pragma unroll
+        for (int w = 0; w < D::NW; w++) {
+            const uint32_t v = d[w] & 0x7fffffffu;
+            who[w] = __ballot_sync(0xffffffffu, v && ((v - 1) & smask) == rank);
+            warp_total += (uint32_t)__popc(who[w]);
+        }
+        uint32_t warp_base = 0;
+        if (lane == 0 && warp_total) warp_base = atomicAdd(&s_cnt, warp_total);
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = s_cnt ? atomicAdd(count, s_cnt) : 0u;
+        __syncthreads();
+        uint32_t seg = s_base + warp_base;
+        const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+        for (int w = 0; w < D::NW; w++) {
+            if ((who[w] >> lane) & 1u) {
+                const uint32_t at = seg + (uint32_t)__popc(who[w] & below);
+                keys[at] = key0 + (((d[w] & 0x7fffffffu) - 1) >> shift);
+                vals[at] = (uint32_t)((size_t)w * tab_stride + rec) | (d[w] & 0x80000000u);
+            }
+            seg += (uint32_t)__popc(who[w]);
+        }
+    }
+}
+
+// false: no kernel for this width (narrow windows of small inputs go to the generic kernel)
+template <bool COMPACT>
+static bool msm_launch_digits_fixed(int cb, unsigned blocks, cudaStream_t st, uint32_t* keys, uint32_t* vals, const MsmBatch& batch,
+                                    size_t n, int nwin, int montgomery, size_t tab_stride, uint32_t rank, uint32_t shift,
+                                    uint32_t Bloc, uint32_t* count) {
+    switch (cb) {
+#define SWB_DIGITS_CASE(CB)                                                                                              \
+    case CB:                                                                                                             \
+        if (nwin > DigitsFixed<CB>::NW) return false;                                                                    \
+        k_msm_digits_fixed<COMPACT, CB><<<blocks, 256, 0, st>>>(keys, vals, batch, n, nwin, montgomery, tab_stride, rank, \
+                                                                shift, Bloc, count);                                     \
+        return true;
+        SWB_DIGITS_CASE(12) SWB_DIGITS_CASE(13) SWB_DIGITS_CASE(14) SWB_DIGITS_CASE(15) SWB_DIGITS_CASE(16)
+        SWB_DIGITS_CASE(17) SWB_DIGITS_CASE(18) SWB_DIGITS_CASE(19) SWB_DIGITS_CASE(20) SWB_DIGITS_CASE(21)
+        SWB_DIGITS_CASE(22) SWB_DIGITS_CASE(23) SWB_DIGITS_CASE(24)
+#undef SWB_DIGITS_CASE
+        default: return false;
+    }
+}
+
 // fills in what is only known after the digits kernel under compaction: total, seg_len, ranges
 static void msm_plan_ranges(swb_ctx* c, MsmPlan& pl) {
     // enough threads to fill the GPU (>= ~512 per SM) but at most 128 additions each
@@ -211,10 +327,12 @@ int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const 
         if (blocks > cap) blocks = cap;
         if (pl.compact) {
             SWB_CUDA(c, cudaMemsetAsync(bf.count, 0, sizeof(uint32_t), c->stream));
-            k_msm_digits<true><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, batch, pl.n, pl.cb,
-                                                                         pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, bf.count);
+            if (!msm_launch_digits_fixed<true>(pl.cb, (unsigned)blocks, c->stream, bf.keys, bf.vals, batch, pl.n, pl.ndig, montgomery,
+                                               pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, bf.count))
+                k_msm_digits<true><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, batch, pl.n, pl.cb,
+                                                                             pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, bf.count);
             SWB_LAUNCH_CHECK(c, "k_msm_digits");
-            // the number of pairs that fell into our bucket range sizes everything downstream
+            // the number of pairs that fell into our buckets sizes everything downstream
             uint32_t kept = 0;
             SWB_CUDA(c, cudaMemcpyAsync(&kept, bf.count, sizeof kept, cudaMemcpyDeviceToHost, c->stream));
             SWB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -222,8 +340,10 @@ int msm_launch_digits_sort(swb_ctx* c, MsmPlan& pl, const MsmBuffers& bf, const 
             pl.seg_len = kept;
             msm_plan_ranges(c, pl);
         } else {
-            k_msm_digits<false><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, batch, pl.n, pl.cb,
-                                                                          pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, nullptr);
+            if (!msm_launch_digits_fixed<false>(pl.cb, (unsigned)blocks, c->stream, bf.keys, bf.vals, batch, pl.n, pl.ndig, montgomery,
+                                                pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, nullptr))
+                k_msm_digits<false><<<(unsigned)blocks, 256, 0, c->stream>>>(bf.keys, bf.vals, batch, pl.n, pl.cb,
+                                                                              pl.ndig, montgomery, pl.tab_stride, pl.shard_rank, pl.shard_shift, pl.B, nullptr);
             SWB_LAUNCH_CHECK(c, "k_msm_digits");
         }
     }
