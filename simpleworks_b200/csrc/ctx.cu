@@ -184,6 +184,7 @@ void swb_destroy(swb_ctx* c) {
     if (c->tw_root) cudaFree(c->tw_root);
     if (c->tw_gen) cudaFree(c->tw_gen);
     if (c->tw_geninv) cudaFree(c->tw_geninv);
+    if (c->tw_full) cudaFree(c->tw_full);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -32,6 +32,9 @@ struct swb_ctx {
     swb::Fr* tw_root = nullptr;   // [3][1024]
     swb::Fr* tw_gen = nullptr;    // [3][1024]
     swb::Fr* tw_geninv = nullptr; // [3][1024]
+    swb::Fr* tw_full = nullptr;   // [2^tw_full_log] powers of the 2^tw_full_log-th root of unity (inter-digit twiddles by direct lookup)
+    uint32_t tw_full_log = 0;
+    bool tw_full_failed = false;  // allocation refused once: stay on running products
 
     // grow-only scratch arena so repeated calls do not cudaMalloc in the timed path
     struct Scratch { void* p = nullptr; size_t bytes = 0; };

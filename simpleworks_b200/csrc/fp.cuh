@@ -94,6 +94,49 @@ struct Fp {
         for (int i = 0; i < N; i++) t.l[i] = borrow ? t.l[i] : s[i];
     }
 
+    // ---- lazy range [0, 2p) (Harvey butterflies; the moduli leave >= 3 spare top bits, so 4p fits) ----------
+    // limb i of 2p
+    static SWB_HD constexpr uint32_t mod2(int i) { return (P::mod(i) << 1) | (i ? (P::mod(i - 1) >> 31) : 0u); }
+    // t < 4p -> t mod-ish 2p: (t >= 2p) ? t - 2p : t
+    static SWB_HD void final_sub2(Fp& t) {
+        uint32_t s[N];
+        s[0] = ptx::sub_cc(t.l[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) s[i] = ptx::subc_cc(t.l[i], mod2(i));
+        uint32_t borrow = ptx::subc(0u, 0u);
+#pragma unroll
+        for (int i = 0; i < N; i++) t.l[i] = borrow ? t.l[i] : s[i];
+    }
+    // a, b in [0, 2p) -> a + b in [0, 2p)
+    static SWB_HD Fp add_lazy(const Fp& a, const Fp& b) {
+        Fp r;
+        r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+        r.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);
+        final_sub2(r);
+        return r;
+    }
+    // a, b in [0, 2p) -> a - b + 2p in (0, 4p): no comparison at all; feed it to mul_lazy or final_sub2
+    static SWB_HD Fp sub_lazy(const Fp& a, const Fp& b) {
+        Fp r;
+        r.l[0] = ptx::add_cc(a.l[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], mod2(i));
+        r.l[N - 1] = ptx::addc(a.l[N - 1], mod2(N - 1));
+        r.l[0] = ptx::sub_cc(r.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = ptx::subc_cc(r.l[i], b.l[i]);
+        r.l[N - 1] = ptx::subc(r.l[N - 1], b.l[N - 1]);
+        return r;
+    }
+    // t in [0, 2p) -> canonical
+    static SWB_HD Fp reduce_lazy(const Fp& t) {
+        Fp r = t;
+        final_sub(r);
+        return r;
+    }
+
     friend SWB_HD Fp operator+(const Fp& a, const Fp& b) {
         Fp r;
         r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
@@ -180,7 +223,12 @@ struct Fp {
     }
 
     // the device schedule (also runs on the host through the emulated carry flag, for tests)
-    static SWB_HD Fp mul_limb_schedule(const Fp& a, const Fp& b) {
+    static SWB_HD Fp mul_limb_schedule(const Fp& a, const Fp& b) { return mul_limb_schedule_t<true>(a, b); }
+    // Montgomery product without the final conditional subtraction: for a < 4p and b < p (or the other way round) the
+    // running value stays below a + p < 2^(32 N) and the result (a b + m p) / R is below 2p
+    static SWB_HD Fp mul_lazy(const Fp& a, const Fp& b) { return mul_limb_schedule_t<false>(a, b); }
+    template <bool REDUCE>
+    static SWB_HD Fp mul_limb_schedule_t(const Fp& a, const Fp& b) {
         uint32_t ev[N], od[N];
         // row 0: nothing to accumulate onto
         {
@@ -205,7 +253,7 @@ struct Fp {
 #pragma unroll
         for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(ev[k], od[k + 1]);
         r.l[N - 1] = ptx::addc(ev[N - 1], 0u);
-        final_sub(r);
+        if (REDUCE) final_sub(r);
         return r;
     }
 #if !defined(__CUDA_ARCH__)

@@ -25,7 +25,7 @@ constexpr int NTT_THREADS = NTT_THREADS_DEF;
 #define NTT_TILE_LOG_DEF 11
 #endif
 #ifndef NTT_MIN_BLOCKS
-#define NTT_MIN_BLOCKS 1
+#define NTT_MIN_BLOCKS 3
 #endif
 constexpr int NTT_TILE_LOG = NTT_TILE_LOG_DEF;   // R*T = 2048 elements = 64 KB of shared memory
 constexpr uint32_t NTT_MAX_LOG = 30;
@@ -47,6 +47,8 @@ struct NttPass {
     uint32_t inverse, pre_coset, post_coset, post_scale;
     Fr scale;            // n^-1 (Montgomery) when post_scale
     size_t batch_stride;
+    const Fr* tw_full;   // column mode: powers of the 2^full_log-th root of unity, or NULL (running products)
+    uint32_t full_log;
 };
 
 __device__ __forceinline__ Fr tw_lookup(const Fr* __restrict__ tab, uint32_t e) {
@@ -179,9 +181,12 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_ntt_pass(NttPas
 #pragma unroll
             for (int q = 0; q < NTT_BF_ILP; q++) {
                 if (!on[q]) continue;
-                const Fr sum = u[q] + v[q];
-                Fr dif = u[q] - v[q];
-                if (ex[q]) dif = dif * tw[q];
+                // lazy butterflies (Harvey): tile values live in [0, 2r); the difference needs no comparison and the
+                // product no final subtraction -- its result is below 2r for an operand below 4r
+                const Fr sum = Fr::add_lazy(u[q], v[q]);
+                Fr dif = Fr::sub_lazy(u[q], v[q]);
+                if (ex[q]) dif = Fr::mul_lazy(dif, tw[q]);
+                else Fr::final_sub2(dif);
                 tl.put(e0[q], sum);
                 tl.put(e1[q], dif);
             }
@@ -191,29 +196,59 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_ntt_pass(NttPas
 
     // ---- store: X[k] is at bit-reversed position; apply inter-digit twiddle / scaling --------
     if (p.mode == 0) {
-        // thread keeps its column t fixed and walks k; twiddle w^(k*col) advances by w^(dk*col)
+        // thread keeps its column t fixed and walks k
         const uint32_t t = tid & (T - 1);
         const uint32_t col = col0 + t;
         const uint32_t k0 = tid >> p.log_t, dk = NTT_THREADS >> p.log_t;
-        const uint32_t mask = (1u << NTT_MAX_LOG) - 1u;
-        uint32_t e_w = (uint32_t)((((uint64_t)k0 * col) << p.tw_shift) & mask);
-        uint32_t e_s = (uint32_t)((((uint64_t)dk * col) << p.tw_shift) & mask);
-        if (p.inverse) { e_w = ((1u << NTT_MAX_LOG) - e_w) & mask; e_s = ((1u << NTT_MAX_LOG) - e_s) & mask; }
-        Fr w = tw_lookup(tw_root, e_w);
-        const Fr step = tw_lookup(tw_root, e_s);
-        for (uint32_t k = k0; k < R; k += dk) {
-            Fr v = tl.get(bitrev(k, p.log_r) * T + t);
-            if (col) v = v * w;
-            st_fr(out + out_base + (size_t)k * out_k_stride + t, v);
-            w = w * step;
+        if (p.tw_full) {
+            // inter-digit twiddle w^(k*col), w of order R*M, read from the table of all powers: one product per
+            // element instead of two (apply + advance a running power), and no serial chain between iterations.
+            // The table loads are scattered 32-byte reads; the pass is issue-bound with DRAM nearly idle.
+            const uint32_t up = p.full_log - (p.log_r + p.log_m), fmask = (1u << p.full_log) - 1u;
+            constexpr uint32_t U = 4;
+            for (uint32_t k = k0; k < R; k += U * dk) {
+                Fr w[U];
+#pragma unroll
+                for (uint32_t q = 0; q < U; q++) {
+                    const uint32_t kk = k + q * dk;
+                    uint32_t e = (kk * col) << up;                       // kk * col < R * M <= 2^full_log
+                    if (p.inverse) e = ((1u << p.full_log) - e) & fmask;
+                    if (kk < R && e) w[q] = ld_fr(p.tw_full + e);
+                    else w[q] = Fr::one();
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < U; q++) {
+                    const uint32_t kk = k + q * dk;
+                    if (kk >= R) break;
+                    Fr v = tl.get(bitrev(kk, p.log_r) * T + t);
+                    if (col) v = Fr::mul_lazy(v, w[q]);                  // intermediate passes hand on values in [0, 2r)
+                    st_fr(out + out_base + (size_t)kk * out_k_stride + t, v);
+                }
+            }
+        } else {
+            // twiddle w^(k*col) advances by w^(dk*col)
+            const uint32_t mask = (1u << NTT_MAX_LOG) - 1u;
+            uint32_t e_w = (uint32_t)((((uint64_t)k0 * col) << p.tw_shift) & mask);
+            uint32_t e_s = (uint32_t)((((uint64_t)dk * col) << p.tw_shift) & mask);
+            if (p.inverse) { e_w = ((1u << NTT_MAX_LOG) - e_w) & mask; e_s = ((1u << NTT_MAX_LOG) - e_s) & mask; }
+            Fr w = tw_lookup(tw_root, e_w);
+            const Fr step = tw_lookup(tw_root, e_s);
+            for (uint32_t k = k0; k < R; k += dk) {
+                Fr v = tl.get(bitrev(k, p.log_r) * T + t);
+                if (col) v = Fr::mul_lazy(v, w);
+                st_fr(out + out_base + (size_t)k * out_k_stride + t, v);
+                w = w * step;
+            }
         }
     } else {
         for (uint32_t idx = tid; idx < tile; idx += NTT_THREADS) {
             const uint32_t t = idx & (T - 1), k = idx >> p.log_t;
             Fr v = tl.get(bitrev(k, p.log_r) * Tp + t);
             const size_t go = out_base + (size_t)k * out_k_stride + (size_t)t * out_t_stride;
+            // v is in [0, 2r): a full product brings it back to the canonical range, otherwise one subtraction does
             if (p.post_coset) v = v * tw_lookup(tw_coset, (uint32_t)go);
             if (p.post_scale) v = v * p.scale;
+            if (!p.post_coset && !p.post_scale) v = Fr::reduce_lazy(v);
             st_fr(out + go, v);
         }
     }
@@ -226,6 +261,47 @@ __global__ void k_build_pow_table(Fr* __restrict__ tab, Fr b0, Fr b1, Fr b2) {
     const uint32_t l = i >> 10, j = i & 1023u;
     const Fr base = l == 0 ? b0 : (l == 1 ? b1 : b2);
     tab[i] = base.pow_u64(j);
+}
+
+// tab[i] = w^i for the 2^log_l-th root of unity w, from the three-level tables
+__global__ void k_build_full_table(Fr* __restrict__ tab, const Fr* __restrict__ tw_root, uint32_t log_l) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_l)) return;
+    st_fr(tab + i, tw_lookup(tw_root, (uint32_t)(i << (NTT_MAX_LOG - log_l))));
+}
+
+// Direct twiddle table for transforms of up to 2^log_n points (32 B << log_n of device memory: 2 GiB at 2^26), grown on
+// demand; SWB_NTT_TABLE_MAX_LOG caps it (0 switches it off).  Returns the table's log size or 0 (running products).
+static uint32_t ntt_full_table(swb_ctx* c, uint32_t log_n) {
+    static const uint32_t cap = [] {
+        const char* e = getenv("SWB_NTT_TABLE_MAX_LOG");
+        const long v = e ? atol(e) : 26;
+        return (uint32_t)(v < 0 ? 0 : (v > 27 ? 27 : v));
+    }();
+    if (log_n > cap || c->tw_full_failed) return 0;
+    if (c->tw_full && c->tw_full_log >= log_n) return c->tw_full_log;
+    if (c->tw_full) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->tw_full);
+        c->tw_full = nullptr;
+        c->tw_full_log = 0;
+    }
+    if (cudaMalloc(&c->tw_full, sizeof(Fr) << log_n) != cudaSuccess) {
+        cudaGetLastError();
+        c->tw_full = nullptr;
+        c->tw_full_failed = true;
+        return 0;
+    }
+    k_build_full_table<<<(unsigned)((((size_t)1 << log_n) + 255) / 256), 256, 0, c->stream>>>(c->tw_full, c->tw_root, log_n);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) {
+        cudaFree(c->tw_full);
+        c->tw_full = nullptr;
+        c->tw_full_failed = true;
+        return 0;
+    }
+    c->tw_full_log = log_n;
+    return log_n;
 }
 
 // widest digit of the automatic plan (SWB_NTT_MAX_DIGIT overrides: tuning aid)
@@ -321,6 +397,7 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
         Fr ti = host_fr_const(two_inv);
         for (uint32_t i = 0; i < log_n; i++) scale = scale * ti;
     }
+    const uint32_t full_log = m > 1 ? ntt_full_table(c, log_n) : 0;
     uint32_t log_m = log_n;   // trailing block size before pass s
     static const char* const pass_names[8] = {"pass0", "pass1", "pass2", "pass3", "pass4", "pass5", "pass6", "pass7"};
     StageTimer tm(c, "ntt");
@@ -344,6 +421,8 @@ static int ntt_run(swb_ctx* c, Fr* data, uint32_t log_n, size_t batch, int inver
             p.mode = 0;
             p.log_m = log_m;
             p.tw_shift = NTT_MAX_LOG - (dig[s] + log_m);
+            p.tw_full = full_log ? c->tw_full : nullptr;
+            p.full_log = full_log;
             log_t = NTT_TILE_LOG - dig[s];
             if (log_t > log_m) log_t = log_m;
             blocks = n >> (dig[s] + log_t);
