@@ -29,6 +29,9 @@ constexpr int NTT_THREADS = NTT_THREADS_DEF;
 #endif
 constexpr int NTT_TILE_LOG = NTT_TILE_LOG_DEF;   // R*T = 2048 elements = 64 KB of shared memory
 constexpr uint32_t NTT_MAX_LOG = 30;
+#ifndef NTT_RADIX4
+#define NTT_RADIX4 1                        // stage pairs in registers (0: one stage per shared-memory round trip)
+#endif
 #ifndef NTT_BF_ILP
 #define NTT_BF_ILP 1                        // butterflies in flight per thread
 #endif
@@ -152,7 +155,52 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_ntt_pass(NttPas
     // element (j,t) sits at j*Tp + t
     const uint32_t js = Tp, ts = 1u;
     const uint32_t nbf = tile >> 1;
-    for (uint32_t s = 0; s < p.log_r; s++) {
+    uint32_t s = 0;
+#if NTT_RADIX4
+    // two stages per trip through shared memory: a thread holds the four elements {j0, j0 + q, j0 + 2q, j0 + 3q}
+    // (q = quarter of the current block) in registers, runs the stage-s butterflies (j0, j0 + 2q), (j0 + q, j0 + 3q)
+    // and then the stage-(s+1) butterflies (j0, j0 + q), (j0 + 2q, j0 + 3q): same products, half the shared-memory
+    // traffic and half the barriers.  An odd number of stages leaves the last one to the radix-2 loop below.
+    for (; s + 2 <= p.log_r; s += 2) {
+        const uint32_t log_q = p.log_r - 2 - s, q = 1u << log_q;
+        const uint32_t sh = NTT_MAX_LOG - p.log_r, emask = (1u << NTT_MAX_LOG) - 1u;
+        for (uint32_t id = tid; id < (tile >> 2); id += NTT_THREADS) {
+            const uint32_t t = id & (T - 1), b = id >> p.log_t;
+            const uint32_t pos = b & (q - 1), grp = b >> log_q;
+            const uint32_t j0 = (grp << (log_q + 2)) + pos;
+            const uint32_t i0 = j0 * js + t * ts, i1 = i0 + q * js, i2 = i1 + q * js, i3 = i2 + q * js;
+            uint32_t ex0 = ((pos << s) << sh), ex1 = (((pos + q) << s) << sh), ex2 = ((pos << (s + 1)) << sh);
+            if (p.inverse) {
+                ex0 = ((1u << NTT_MAX_LOG) - ex0) & emask;
+                ex1 = ((1u << NTT_MAX_LOG) - ex1) & emask;
+                ex2 = ((1u << NTT_MAX_LOG) - ex2) & emask;
+            }
+            Fr a0 = tl.get(i0), a2 = tl.get(i2);
+            Fr b0 = Fr::add_lazy(a0, a2);
+            Fr b2 = Fr::sub_lazy(a0, a2);
+            if (ex0) b2 = Fr::mul_lazy(b2, tw_lookup(tw_root, ex0));
+            else Fr::final_sub2(b2);
+            Fr a1 = tl.get(i1), a3 = tl.get(i3);
+            Fr b1 = Fr::add_lazy(a1, a3);
+            Fr b3 = Fr::mul_lazy(Fr::sub_lazy(a1, a3), tw_lookup(tw_root, ex1));     // w^(R/4) * ...: never trivial
+            Fr c1 = Fr::sub_lazy(b0, b1), c3 = Fr::sub_lazy(b2, b3);
+            if (ex2) {
+                const Fr w2 = tw_lookup(tw_root, ex2);
+                c1 = Fr::mul_lazy(c1, w2);
+                c3 = Fr::mul_lazy(c3, w2);
+            } else {
+                Fr::final_sub2(c1);
+                Fr::final_sub2(c3);
+            }
+            tl.put(i0, Fr::add_lazy(b0, b1));
+            tl.put(i1, c1);
+            tl.put(i2, Fr::add_lazy(b2, b3));
+            tl.put(i3, c3);
+        }
+        __syncthreads();
+    }
+#endif
+    for (; s < p.log_r; s++) {
         const uint32_t log_half = p.log_r - 1 - s, half = 1u << log_half;
         // two butterflies per iteration, loaded before either is computed: their Montgomery products are
         // independent dependency chains that the scheduler interleaves (one chain alone leaves the multiplier idle
@@ -372,6 +420,16 @@ static int plan_digits(uint32_t log_n, uint32_t* dig) {
     const uint32_t maxd = ntt_max_digit();
     int m = (int)((log_n + maxd - 1) / maxd);
     for (int s = 0; s < m; s++) dig[s] = log_n / m + ((uint32_t)s < log_n % m ? 1 : 0);
+    // the butterfly network runs its stages in pairs (NTT_RADIX4), an odd digit leaves a single stage with a barrier of
+    // its own: trade one stage between two odd digits (2^26: 9,9,8 -> 10,8,8 16.84 -> 16.46 ms; 2^22: 8,7,7 -> 8,8,6)
+    for (;;) {
+        int a = -1, b = -1;
+        for (int s = 0; s < m; s++)
+            if (dig[s] & 1u) { if (a < 0) a = s; else if (b < 0) b = s; }
+        if (b < 0 || dig[a] + 1 > maxd || dig[b] < 2) break;
+        dig[a]++;
+        dig[b]--;
+    }
     return m;
 }
 
