@@ -188,6 +188,9 @@ def marlin_gpu_run(be, lg, proofs):
     for _ in range(proofs + 1):
         ta = time.perf_counter(); proof = m.generate_proof(cs, pk, Rng()); ts.append(time.perf_counter() - ta)
     tune_s = ts[0] - min(ts[1:])
+    tab_c, tab_w = m.srs_table_info(srs)
+    if tab_w == 0:
+        raise RuntimeError("the SRS window tables were not built (device memory?): prove_s would repeat the plain path")
     m.profile(True)                      # one more proof for the per-phase breakdown (host wall-clock per phase)
     m.generate_proof(cs, pk, Rng())
     phases = m.last_phases()
@@ -196,7 +199,7 @@ def marlin_gpu_run(be, lg, proofs):
     return {"log_constraints": lg, "setup_s": t1 - t0, "index_s": t3 - t2, "index_s_first_call": index_first_s,
             "index_first_call_phases_ms": index_first_phases, "prove_s": min(ts[1:]), "prove_s_all": ts[1:],
             "prove_s_plain_msm_path": min(ts_plain), "prove_s_plain_all": ts_plain, "srs_window_tables_build_s": tune_s,
-            "index_phases_ms": index_phases, "prove_phases_ms": phases,
+            "index_phases_ms": index_phases, "prove_phases_ms": phases, "srs_window_tables": {"window_bits": tab_c, "levels": tab_w},
             "prove_s_note": "prove_s: SRS powers with window tables (swb_srs_set_tune_after; automatic after ~20 proofs), "
                             "prove_s_plain_msm_path: before them",
             "verify_s": tv, "verified": bool(ok), "proofs_per_s": 1.0 / min(ts[1:]), "proof_bytes": len(proof)}, proof
@@ -587,6 +590,7 @@ def main():
         try:
             be.set_msm_bucket_shard(0, 1)
             bases.free()
+            be.trim()
             r, proof_single = marlin_gpu_run(be, args.marlin_log_n, 2)
             mine = r["prove_s"]
         except Exception as e:     # every rank still joins the collective below
@@ -755,6 +759,11 @@ def main():
                 bases.free()
                 del scalars_dev, flush
                 torch.cuda.empty_cache()
+                # the MSM arenas (pair sums, sort buffers: ~100 GB after the 2^26 steps) go back to the driver, so that
+                # the prover's SRS finds room for its window tables (they are skipped below half of the free memory)
+                free_before = torch.cuda.mem_get_info()[0]
+                be.trim()
+                extra["device_free_gb"] = {"before_trim": free_before / 1e9, "after_trim": torch.cuda.mem_get_info()[0] / 1e9}
                 extra["marlin"] = marlin_extra(be, args, progress)
             except Exception as e:     # the headline must not die with the side measurement
                 extra["marlin"] = {"error": repr(e)}

@@ -49,7 +49,12 @@ enum { SWB_OK = 0, SWB_ECUDA = 1, SWB_EARG = 2, SWB_ENOMEM = 3, SWB_EINTERNAL = 
 /* ---- context ---------------------------------------------------------------------------- */
 int  swb_init(int device, swb_ctx** out);
 void swb_destroy(swb_ctx*);
-const char* swb_last_error(const swb_ctx*);      /* NULL ctx -> last error of a failed swb_init */
+const char* swb_last_error(const swb_ctx*);
+/* Hands back every device allocation the context only keeps for reuse: the scratch arenas of MSM / NTT / sort (they
+ * grow to the largest call seen: 90 GB after a 2^26-point MSM), the cache of released vectors and the NTT twiddle
+ * table.  Nothing a live handle owns is touched; the next call allocates again.  Waits for all work of the context
+ * first; fails while an MSM begun with the asynchronous interface has not been collected. */
+int  swb_trim(swb_ctx*);      /* NULL ctx -> last error of a failed swb_init */
 /* run all work of this context on an existing CUDA stream (cudaStream_t), e.g. the caller's
  * current stream so that its events time the kernels and its later work is ordered after ours;
  * NULL is the CUDA legacy default stream.  swb_reset_stream returns to the context's own
@@ -261,6 +266,9 @@ size_t swb_srs_max_degree(const swb_srs*);
  * proofs).  Default 400, i.e. some twenty proofs (SWB_MARLIN_TABLES overrides), 0 = never, 1 = at the
  * first commitment.  Proof bytes do not depend on it. */
 int  swb_srs_set_tune_after(swb_srs*, long n_msms);
+/* window tables of the SRS powers: digit width and number of levels, both 0 while the plain path is in use (the
+ * tables are skipped when they would not fit in half of the free device memory). */
+int  swb_srs_table_info(const swb_srs*, int* window_bits, int* levels);
 /* Handle lifetimes: a proving key keeps its SRS alive (reference counted), so swb_srs_free and swb_pk_free
  * may come in either order; every SRS, proving key and bases handle must be freed BEFORE swb_destroy of the
  * context it was created on, and is only valid on that context (other contexts are refused with SWB_EARG). */

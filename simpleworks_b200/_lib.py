@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SWB_LIB") or os.path.join(_HERE, "libswb200.so")
 # every symbol include/swb200.h declares; tests/test_abi.py checks the header against this list
 # and that the built library exports each one.
 SYMBOLS = [
-    "swb_init", "swb_destroy", "swb_last_error", "swb_set_stream", "swb_reset_stream", "swb_sync", "swb_device_info",
+    "swb_init", "swb_destroy", "swb_last_error", "swb_trim", "swb_set_stream", "swb_reset_stream", "swb_sync", "swb_device_info",
     "swb_launch_count", "swb_dev_alloc", "swb_dev_free", "swb_h2d", "swb_d2h",
     "swb_fr_mul_vec_dev", "swb_fr_add_vec_dev", "swb_fr_sub_vec_dev",
     "swb_fq_mul_vec_dev", "swb_fq_add_vec_dev", "swb_fq_sub_vec_dev",
@@ -30,7 +30,7 @@ SYMBOLS = [
     "swb_rng_test_rng", "swb_rng_from_seed", "swb_rng_from_entropy", "swb_rng_next_u64", "swb_rng_free",
     "swb_r1cs_new", "swb_r1cs_builtin", "swb_r1cs_add_constraint", "swb_r1cs_set_assignment", "swb_r1cs_is_satisfied",
     "swb_r1cs_free",
-    "swb_marlin_profile_enable", "swb_marlin_last_phases", "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_set_tune_after", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
+    "swb_marlin_profile_enable", "swb_marlin_last_phases", "swb_marlin_universal_setup", "swb_srs_max_degree", "swb_srs_set_tune_after", "swb_srs_table_info", "swb_srs_free", "swb_marlin_index", "swb_pk_free", "swb_vk_free",
     "swb_marlin_prove", "swb_marlin_verify", "swb_bytes_free",
     "swb_vk_serialize", "swb_vk_deserialize", "swb_proof_deserialize", "swb_proof_serialize", "swb_proof_free", "swb_marlin_verify_proof", "swb_pk_serialize", "swb_pk_deserialize", "swb_r1cs_read", "swb_r1cs_write",
 ]
@@ -57,6 +57,7 @@ def load() -> ctypes.CDLL:
         "swb_init": (i32, [i32, pvp]),
         "swb_destroy": (None, [vp]),
         "swb_last_error": (ctypes.c_char_p, [vp]),
+        "swb_trim": (i32, [vp]),
         "swb_set_stream": (i32, [vp, vp]),
         "swb_reset_stream": (i32, [vp]),
         "swb_sync": (i32, [vp]),
@@ -76,6 +77,7 @@ def load() -> ctypes.CDLL:
         "swb_bases_load": (i32, [vp, vp, sz, pvp]),
         "swb_bases_load_dev": (i32, [vp, vp, sz, pvp]),
         "swb_srs_set_tune_after": (i32, [vp, ctypes.c_long]),
+        "swb_srs_table_info": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
         "swb_marlin_profile_enable": (i32, [i32]),
         "swb_marlin_last_phases": (sz, [ctypes.c_char_p, sz]),
         "swb_bases_precompute": (i32, [vp, vp, i32]),

@@ -193,6 +193,11 @@ class Backend:
         self._check(self._lib.swb_measure_imad_peak(self._h, {"lo": 0, "wide": 1, "wide_carry": 2, "addc": 3}[kind], iters, ctypes.byref(ops)))
         return ops.value
 
+    def trim(self):
+        """swb_trim: hands back the scratch arenas, the vector cache and the NTT twiddle table (device memory kept
+        only for reuse); handles stay valid"""
+        self._check(self._lib.swb_trim(self._h))
+
     def profile(self, on: bool = True):
         self._check(self._lib.swb_profile_enable(self._h, int(on)))
 
@@ -527,6 +532,12 @@ class Marlin:
     def srs_set_tune_after(self, srs, n_msms: int):
         """After n_msms commit/open MSMs the SRS powers get window tables (0 = never, 1 = at once)."""
         self.be._check(self._lib.swb_srs_set_tune_after(srs, n_msms))
+
+    def srs_table_info(self, srs):
+        """(window bits, levels) of the SRS powers' window tables; (0, 0) on the plain path"""
+        c, w = ctypes.c_int32(), ctypes.c_int32()
+        self.be._check(self._lib.swb_srs_table_info(srs, ctypes.byref(c), ctypes.byref(w)))
+        return c.value, w.value
 
     def generate_proving_and_verifying_keys(self, srs, cs: ConstraintSystem):
         pk, vk = _Handle(), _Handle()

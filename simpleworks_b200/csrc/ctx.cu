@@ -189,6 +189,25 @@ void swb_destroy(swb_ctx* c) {
     delete c;
 }
 
+int swb_trim(swb_ctx* c) {
+    if (!c) return SWB_EARG;
+    for (auto& sl : c->msm_slot)
+        if (sl.active) return swb::set_err(c, SWB_EARG, "trim: an MSM is still in flight");
+    cudaSetDevice(c->device);
+    swb::sync_all_streams(c);
+    for (auto& kv : c->scratch)
+        if (kv.second.p) cudaFree(kv.second.p);
+    c->scratch.clear();
+    for (auto& kv : c->vec_cache) cudaFree(kv.second);
+    c->vec_cache.clear();
+    c->vec_cache_bytes = 0;
+    if (c->tw_full) cudaFree(c->tw_full);
+    c->tw_full = nullptr;
+    c->tw_full_log = 0;
+    c->tw_full_failed = false;
+    return SWB_OK;
+}
+
 const char* swb_last_error(const swb_ctx* c) {
     if (c) return c->err.c_str();
     std::lock_guard<std::mutex> g(g_init_mu);

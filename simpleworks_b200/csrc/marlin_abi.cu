@@ -410,8 +410,14 @@ struct GpuEngine {
         const size_t W = (253 + best - 1) / best;
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(c->device);
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || swb_bases_len(b) * W * 96 > free_b / 2) return;
-        if (swb_bases_precompute(c, b, best) != SWB_OK) cudaGetLastError();   // keep going on the plain path
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || swb_bases_len(b) * W * 96 > free_b / 2) {
+            if (c->trace) fprintf(stderr, "[swb trace] SRS window tables skipped: %zu B needed, %zu B free\n", swb_bases_len(b) * W * 96, free_b);
+            return;
+        }
+        if (swb_bases_precompute(c, b, best) != SWB_OK) {                     // keep going on the plain path
+            cudaGetLastError();
+            if (c->trace) fprintf(stderr, "[swb trace] SRS window tables not built: %s\n", swb_last_error(c));
+        }
     }
     // Independent MSMs (the commitments of a round, the parts of an opening) are submitted first and
     // collected later: two of them are in flight on the library's MSM slots, so the latency-bound
@@ -706,6 +712,10 @@ int swb_srs_set_tune_after(swb_srs* s, long n_msms) {
     if (!s || n_msms < 0) return SWB_EARG;
     s->h->srs->tune_after = n_msms;
     return SWB_OK;
+}
+int swb_srs_table_info(const swb_srs* s, int* window_bits, int* levels) {
+    if (!s) return SWB_EARG;
+    return swb_bases_table_info(static_cast<const swb_bases*>(s->h->srs->powers_of_g), window_bits, levels);
 }
 void swb_srs_free(swb_srs* s) { srs_release(s); }
 int swb_marlin_index(swb_ctx* c, const swb_srs* srs, const swb_r1cs* cs, swb_pk** pk, swb_vk** vk) {

@@ -84,6 +84,16 @@ static int slot_prepare(swb_ctx* c, int slot) {
     return SWB_OK;
 }
 
+// smallest number of sorted pairs from which pair sums run automatically (SWB_PAIR_MIN_LOG: tuning aid)
+static size_t msm_pair_min_total() {
+    static const size_t v = [] {
+        const char* e = getenv("SWB_PAIR_MIN_LOG");
+        const long l = e ? atol(e) : 24;
+        return (size_t)1 << (l >= 10 && l <= 40 ? l : 24);
+    }();
+    return v;
+}
+
 static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, const MsmBatch& batch, int montgomery);
 
 // can these vectors run as ONE batched MSM (one bucket set each over the handle's window tables)?
@@ -289,10 +299,11 @@ static int msm_enqueue(swb_ctx* c, int slot, const swb_bases* bases, const MsmBa
         const double per_bucket = pl.nb ? (double)pl.total / (double)pl.nb : 0.0;
         int levels = 0;
         if (c->msm_pair_policy >= 2) levels = c->msm_pair_policy - 1;                 // forced: policy - 1 levels
-        else if (c->msm_pair_policy == 1 &&
-                 (pl.total >= ((size_t)1 << 27) || (pl.total >= ((size_t)1 << 26) && per_bucket >= 128.0))) {
-            // measured: +9 % at 2^24 points, +12 % at 2^26, nothing at 2^22; a 1/8 bucket share of 2^26 (92 M pairs, 176 per
-            // bucket) still gains 3-7 %
+        else if (c->msm_pair_policy == 1 && pl.total >= msm_pair_min_total()) {
+            // measured: +9 % at 2^24 points, +12 % at 2^26, a 1/8 bucket share of 2^26 (92 M pairs) +3-7 %; the batched and
+            // single MSMs of a 2^20-constraint prover (17-160 M pairs, 26-100 per bucket) 0.334 -> 0.327 s with tables and
+            // 0.402 -> 0.375 s without; below 2^24 pairs the fixed cost of the block-wide inversions loses (2^16
+            // constraints: 44 -> 51 ms with the threshold at 2^22)
             // a level pays while most aligned blocks of 2^L positions still lie inside one bucket
             while (levels < MSM_PAIR_MAX_LEVELS && per_bucket >= (double)(8u << levels)) levels++;
         }

@@ -167,6 +167,12 @@ def test_tuned_srs_gives_the_same_proofs(gpu):
         pk, vk = gpu.generate_proving_and_verifying_keys(srs, cs)
         proof = gpu.generate_proof(cs, pk, rng)
         assert gpu.verify_proof(vk, O.fr_mont([7]), proof)
+        tab_c, tab_w = gpu.srs_table_info(srs)                   # swb_srs_table_info: (0, 0) on the plain path
+        assert (tab_w > 0 and tab_c > 0) if tune else (tab_c, tab_w) == (0, 0)
+        if tune:
+            before = gpu.generate_proof(cs, pk, Rng())
+            gpu.be.trim()                                        # swb_trim between proofs: scratch is re-grown, bytes stay
+            assert gpu.generate_proof(cs, pk, Rng()) == before
         out.append((proof, gpu.serialize_verifying_key(vk)))
     assert out[0] == out[1]
     assert hashlib.sha256(out[1][0]).hexdigest() == case["proof_sha256"]

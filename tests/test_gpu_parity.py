@@ -485,6 +485,29 @@ def test_msm_wide_window_tables_vs_oracle(be, c):
         bases.free()
 
 
+def test_trim_keeps_results(be, srs_points):
+    """swb_trim: scratch arenas, vector cache and the NTT twiddle table go back to the driver; the same calls then
+    give the same bytes (everything is re-allocated and the table rebuilt), also when nothing was allocated yet."""
+    import torch
+    n = 5000
+    bases = be.load_bases(srs_points[:n])
+    scalars = _uniform_mod_r(n, 99)
+    x = be.to_device(_rand_fr(1 << 13, 7))
+    try:
+        be.trim()
+        want_msm = be.msm(bases, scalars)
+        want_ntt = be.ntt_(x.clone(), 13)
+        free0 = torch.cuda.mem_get_info()[0]
+        be.trim()
+        be.trim()
+        assert torch.cuda.mem_get_info()[0] >= free0
+        assert np.array_equal(be.msm(bases, scalars), want_msm)
+        assert torch.equal(be.ntt_(x.clone(), 13), want_ntt)
+        assert torch.equal(be.ntt_(be.ntt_(x.clone(), 13, coset=True), 13, inverse=True, coset=True), x)
+    finally:
+        bases.free()
+
+
 @pytest.mark.parametrize("log_n", [25, 26])
 def test_ntt_four_pass_sizes(be, log_n):
     """log n >= 25 (more passes than anything the oracle comparison reaches): inverse(forward(x)) == x with and
