@@ -98,6 +98,38 @@ int main() {
         if (!Fq::zero().inverse_bingcd().is_zero()) bad++;
         printf("inverse mismatches: %d\n", bad - before);
     }
+    // lazy range [0, 2p) used by the NTT butterflies: add_lazy / sub_lazy / mul_lazy / final_sub2 against the canonical
+    // operators, on values pushed to the top of their ranges (a + p < 2p, u - v + 2p close to 4p)
+    {
+        int before = bad;
+        Fr p_minus_1 = Fr::zero() - Fr::one();                    // p - 1 as a Montgomery value: any canonical pattern works
+        for (int it = 0; it < 4000; it++) {
+            Fr a, b, w;
+            for (int i = 0; i < 8; i++) { a.l[i] = (uint32_t)rng(); b.l[i] = (uint32_t)rng(); w.l[i] = (uint32_t)rng(); }
+            a.l[7] &= 0x0fffffffu; b.l[7] &= 0x0fffffffu; w.l[7] &= 0x0fffffffu;
+            if (it % 5 == 0) a = p_minus_1;
+            if (it % 7 == 0) b = Fr::zero();
+            if (it % 11 == 0) b = p_minus_1;
+            // lift a and b into [p, 2p) half of the time: same residues, the other representative
+            Fr al = a, bl = b;
+            auto lift = [](Fr& x) {                                // x + p without reduction (fits: p < 2^253)
+                uint64_t c = 0;
+                for (int i = 0; i < 8; i++) { c += (uint64_t)x.l[i] + FrParams::mod(i); x.l[i] = (uint32_t)c; c >>= 32; }
+            };
+            if (it & 1) lift(al);
+            if (it & 2) lift(bl);
+            const Fr s = Fr::reduce_lazy(Fr::add_lazy(al, bl));
+            if (!(s == a + b)) bad++;
+            Fr d = Fr::sub_lazy(al, bl);                           // in (0, 4p)
+            const Fr dm = Fr::reduce_lazy(Fr::mul_lazy(d, w));
+            if (!(dm == (a - b) * w)) bad++;
+            Fr::final_sub2(d);                                     // in [0, 2p)
+            if (!(Fr::reduce_lazy(d) == a - b)) bad++;
+            const Fr m2 = Fr::reduce_lazy(Fr::mul_lazy(al, w));
+            if (!(m2 == a * w)) bad++;
+        }
+        printf("lazy-range mismatches: %d\n", bad - before);
+    }
     printf("total mismatches: %d\n", bad);
     return bad != 0;
 }
