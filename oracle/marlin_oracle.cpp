@@ -229,6 +229,33 @@ int orc_pairing_selftest() {
     if (!(final_exponentiation(ml) == plain * plain * plain)) bad |= 8192;
     const Fq12 plain2 = final_exponentiation_plain(a12);
     if (!(final_exponentiation(a12) == plain2 * plain2 * plain2)) bad |= 16384;
+    // the Miller loop on the twist (Fq2 steps, sparse lines) gives the values of the loop over E(Fq12), bit for bit
+    for (int k = 0; k < 3; k++) {
+        const G1Point pk = g1_mul_fr(g, rand_fr(rng));
+        const G2Point qk = g2_mul_fr(h, rand_fr(rng));
+        const Fq12 plain_k = miller_loop_plain(pk, qk);
+        if (!(miller_loop_affine(pk, qk) == plain_k)) bad |= 32768;
+        // the projective loop scales its lines by Fq2 factors: equal after the final exponentiation
+        if (!(final_exponentiation(miller_loop(pk, qk)) == final_exponentiation(plain_k))) bad |= 65536;
+        const Fq12 sq = plain_k.sqr();
+        if (!(sq == plain_k * plain_k)) bad |= 131072;
+    }
+    // subgroup membership by the endomorphism agrees with [r]P == O: on multiples of the generator, on random curve
+    // points (outside G1 with overwhelming probability: the cofactor has 125 bits) and on their cofactor-cleared images
+    {
+        int inside = 0, outside = 0;
+        for (int k = 0; k < 12; k++) {
+            G1Point c;
+            Fq xk = rand_fq(rng);
+            if (!g1_point_from_x(xk, (k & 1) != 0, &c)) continue;
+            const bool a1 = g1_in_subgroup(c), a2 = g1_in_subgroup_plain(c);
+            if (a1 != a2) bad |= 262144;
+            (a2 ? inside : outside)++;
+            const G1Point m = g1_mul_fr(g, rand_fr(rng));
+            if (!g1_in_subgroup(m) || !g1_in_subgroup_plain(m)) bad |= 524288;
+        }
+        if (outside == 0) bad |= 1048576;                      // the test must have seen points outside G1
+    }
     return bad;
 }
 

@@ -1109,59 +1109,51 @@ inline bool verify(const VerifyingKey& vk, const std::vector<Fr>& public_input_u
     if (vk.index_comms.size() != 6) return false;
     for (int i = 0; i < 6; i++) comm[ix[i]] = &vk.index_comms[i];
     if (!comm["g_1"]->has_shifted || !comm["g_2"]->has_shifted) return false;
-    auto lc_comm = [&](const LinComb& lc) {
-        G1Xyzz acc = G1Xyzz::identity();
-        for (auto& t : lc.terms) {
-            G1Point p = g1_mul_fr(comm.at(t.second)->comm, t.first);
-            if (!p.infinity) acc.add_affine(p.x, p.y);
-        }
-        Commitment c;
-        c.comm = to_affine(acc);
-        return c;
-    };
-    const Commitment outer_c = lc_comm(outer), inner_c = lc_comm(inner);
-    struct Item { const Commitment* c; Fr value; bool bounded; size_t bound; };
+    struct Item { const Commitment* c; const LinComb* lc; Fr value; bool bounded; size_t bound; };
     // kzg10::batch_check: total_c = sum r_i (C_i - v_i g - v'_i gamma_g + z_i W_i), total_w = sum r_i W_i,
-    // r_0 = 1, r_i = u128::rand(rng); accept iff e(total_c, h) == e(total_w, beta_h)
-    G1Xyzz total_c = G1Xyzz::identity(), total_w = G1Xyzz::identity();
+    // r_0 = 1, r_i = u128::rand(rng); accept iff e(total_c, h) == e(total_w, beta_h).
+    // Every C_i is itself a combination of commitments (accumulate_commitments_and_values with the per-polynomial
+    // opening challenge powers; the two virtual commitments are linear combinations of index and prover commitments),
+    // so both sums are flattened into ONE list of (point, scalar) terms each and evaluated by a single host MSM with
+    // shared doublings: the group elements are the ones the nested scalar multiplications would give.
+    std::vector<std::pair<G1Point, Fr>> terms_c, terms_w;
     bool ok = true;
-    auto add_scaled_to = [&](G1Xyzz& acc, const G1Point& p, const Fr& s) {
-        G1Point t = g1_mul_fr(p, s);
-        if (!t.infinity) acc.add_affine(t.x, t.y);
-    };
     auto accumulate_point = [&](const std::vector<Item>& items, const Fr& z, const PcProof& pr, const Fr& randomizer) {
-        // accumulate_commitments_and_values (per-polynomial opening challenge powers)
-        G1Xyzz cc = G1Xyzz::identity();
         Fr cv = Fr::zero(), chal = Fr::one();
         for (auto& it : items) {
-            add_scaled_to(cc, it.c->comm, chal);
+            const Fr s = chal * randomizer;
+            if (it.lc) {
+                for (auto& t : it.lc->terms) terms_c.push_back({comm.at(t.second)->comm, t.first * s});
+            } else {
+                terms_c.push_back({it.c->comm, s});
+            }
             cv = cv + it.value * chal;
             chal = chal * ch.xi;
             if (it.bounded) {
                 // (shifted_comm - value * beta^(D - bound) g) * next challenge power
                 const G1Point* sp = vk.shift_power(it.bound);
                 if (!sp) { ok = false; return; }
-                add_scaled_to(cc, it.c->shifted, chal);
-                add_scaled_to(cc, *sp, (it.value * chal).neg());
+                terms_c.push_back({it.c->shifted, chal * randomizer});
+                terms_c.push_back({*sp, (it.value * chal * randomizer).neg()});
                 chal = chal * ch.xi;
             }
         }
-        add_scaled_to(cc, vk.g, cv.neg());
-        if (pr.has_random_v) add_scaled_to(cc, vk.gamma_g, pr.random_v.neg());
-        add_scaled_to(cc, pr.w, z);
-        add_scaled_to(total_c, to_affine(cc), randomizer);
-        add_scaled_to(total_w, pr.w, randomizer);
+        terms_c.push_back({vk.g, (cv * randomizer).neg()});
+        if (pr.has_random_v) terms_c.push_back({vk.gamma_g, (pr.random_v * randomizer).neg()});
+        terms_c.push_back({pr.w, z * randomizer});
+        terms_w.push_back({pr.w, randomizer});
     };
-    std::vector<Item> at_beta = {{comm["g_1"], in.g1_beta, true, H.n - 2},
-                                 {&outer_c, outer.constant.neg(), false, 0},
-                                 {comm["t"], in.t_beta, false, 0},
-                                 {comm["z_b"], in.zb_beta, false, 0}};
-    std::vector<Item> at_gamma = {{comm["g_2"], in.g2_gamma, true, K.n - 2}, {&inner_c, inner.constant.neg(), false, 0}};
+    std::vector<Item> at_beta = {{comm["g_1"], nullptr, in.g1_beta, true, H.n - 2},
+                                 {nullptr, &outer, outer.constant.neg(), false, 0},
+                                 {comm["t"], nullptr, in.t_beta, false, 0},
+                                 {comm["z_b"], nullptr, in.zb_beta, false, 0}};
+    std::vector<Item> at_gamma = {{comm["g_2"], nullptr, in.g2_gamma, true, K.n - 2}, {nullptr, &inner, inner.constant.neg(), false, 0}};
     accumulate_point(at_beta, ch.beta, proof.pc_proofs[0], Fr::one());
     uint64_t rw[2];
     rng.next_u128(rw);
     accumulate_point(at_gamma, ch.gamma, proof.pc_proofs[1], fr_from_u128(rw));
     if (!ok) return false;
+    const G1Xyzz total_c = g1_msm_host(terms_c), total_w = g1_msm_host(terms_w);
     return pairing_product_is_one({{to_affine(total_c), vk.h}, {g1_neg(to_affine(total_w)), vk.beta_h}});
 }
 

@@ -55,7 +55,7 @@ struct Fq2 {
     Fq2 scale(const Fq& s) const { return {c0 * s, c1 * s}; }
     Fq norm() const { return c0.sqr() + mul5(c1.sqr()); }
     Fq2 inverse() const {
-        Fq ni = norm().inverse();
+        Fq ni = norm().inverse_bingcd();
         return {c0 * ni, (c1 * ni).neg()};
     }
     Fq2 mul_by_u() const { return {mul5(c1).neg(), c0}; }   // (c0 + c1 u) u = -5 c1 + c0 u
@@ -103,7 +103,23 @@ struct Fq12 {
         return {a + b.mul_by_v(), (c0 + c1) * (o.c0 + o.c1) - a - b};
     }
     Fq12 conj() const { return {c0, c1.neg()}; }            // the q^6-power Frobenius
-    Fq12 sqr() const { return (*this) * (*this); }
+    Fq12 sqr() const {                                      // complex squaring: 2 Fq6 products
+        const Fq6 ab = c0 * c1;
+        const Fq6 t = (c0 + c1) * (c0 + c1.mul_by_v()) - ab - ab.mul_by_v();      // c0^2 + v c1^2
+        return {t, ab + ab};
+    }
+    // times the sparse element a + (b + c v) w, a, b, c in Fq2 -- the shape of a line of the Miller loop
+    // (arkworks' mul_by_034)
+    Fq12 mul_by_line(const Fq2& a, const Fq2& b, const Fq2& c) const {
+        auto mul_b_c = [](const Fq6& x, const Fq2& p, const Fq2& q) {             // x * (p + q v): 5 Fq2 products
+            const Fq2 t0 = x.c0 * p, t1 = x.c1 * q;
+            return Fq6{t0 + (x.c2 * q).mul_by_u(), (x.c0 + x.c1) * (p + q) - t0 - t1, x.c2 * p + t1};
+        };
+        const Fq6 t0 = c0.scale2(a);                        // c0 * a
+        const Fq6 t1 = mul_b_c(c1, b, c);                   // c1 * (b + c v)
+        const Fq6 mid = mul_b_c(c0 + c1, a + b, c);         // (c0 + c1) * (a + b + c v)
+        return {t0 + t1.mul_by_v(), mid - t0 - t1};
+    }
     Fq12 inverse() const {
         Fq6 d = (c0 * c0 - (c1 * c1).mul_by_v()).inverse();
         return {c0 * d, (c1 * d).neg()};
@@ -254,8 +270,82 @@ inline E12Point untwist(const G2Point& q) {
     r.y.c1.c1 = q.y;        // y' * v w (w^3 = v w)
     return r;
 }
-// Miller function f_{x,Q}(P) (denominators omitted: they lie in Fq6 and die in the final exponentiation)
+// Miller function f_{x,Q}(P) with T on the twist in homogeneous projective coordinates (Costello-Lange-Naehrig, the
+// formulas of ark-ec 0.3 models/bls12/g2.rs for a D-type twist): no inversion at all, lines scaled by Fq2 factors
+// that the final exponentiation removes.  A doubling step costs 2 products + 7 squarings in Fq2, an addition step
+// 11 products + 2 squarings; the line a + (b + c v) w = (-2YZ py) + (3X^2 px) w + (3b'Z^2 - Y^2) v w multiplies f
+// sparsely.  Checked against miller_loop_affine / miller_loop_plain after the final exponentiation
+// (orc_pairing_selftest).
 inline Fq12 miller_loop(const G1Point& p, const G2Point& q) {
+    if (p.infinity || q.infinity) return Fq12::one();
+    static const Fq two_inv = fq_small(2).inverse();
+    static const Fq2 bt = g2_coeff_b();
+    Fq2 X = q.x, Y = q.y, Z = Fq2::one();
+    Fq12 f = Fq12::one();
+    const uint64_t x = SWB_BLS_X;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) {
+        {   // doubling step
+            const Fq2 a = (X * Y).scale(two_inv), b = Y.sqr(), c = Z.sqr();
+            const Fq2 e = bt * (c + c + c), f3 = e + e + e;
+            const Fq2 g = (b + f3).scale(two_inv), h = (Y + Z).sqr() - (b + c), i2 = e - b, j = X.sqr(), e2 = e.sqr();
+            X = a * (b - f3);
+            Y = g.sqr() - (e2 + e2 + e2);
+            Z = b * h;
+            f = f.sqr().mul_by_line(h.neg().scale(p.y), (j + j + j).scale(p.x), i2);
+        }
+        if ((x >> i) & 1) {   // addition step: T <- T + Q
+            const Fq2 theta = Y - q.y * Z, lambda = X - q.x * Z;
+            const Fq2 c = theta.sqr(), d = lambda.sqr(), e = lambda * d, ff = Z * c, g = X * d;
+            const Fq2 h = e + ff - (g + g);
+            X = lambda * h;
+            Y = theta * (g - h) - e * Y;
+            Z = Z * e;
+            const Fq2 j = theta * q.x - lambda * q.y;
+            f = f.mul_by_line(lambda.scale(p.y), theta.neg().scale(p.x), j);
+        }
+    }
+    return f;
+}
+// The same Miller function with T kept
+// on the TWIST in affine Fq2 coordinates.  The untwisted point is (x' w^2, y' w^3), so a slope on E is lambda' w
+// with lambda' = 3 x'^2 / (2 y') (or the chord's) in Fq2, the new point is (lambda'^2 - x1' - x2',
+// lambda' (x1' - x3') - y1') again on the twist, and the line through T evaluated at P = (px, py) is
+//     py - lambda' px * w + (lambda' x' - y') * w^3,
+// i.e. the Fq12 element c0 = (py, 0, 0), c1 = (-lambda' px, lambda' x' - y', 0) -- the same VALUES as the loop
+// over E(Fq12) below produces (miller_loop_plain, kept as the reference; tests compare the two bit for bit), at
+// one Fq2 inversion and a handful of Fq2 products per step instead of an Fq12 inversion and five Fq12 products.
+inline Fq12 miller_loop_affine(const G1Point& p, const G2Point& q) {
+    if (p.infinity || q.infinity) return Fq12::one();
+    Fq2 tx = q.x, ty = q.y;
+    Fq12 f = Fq12::one();
+    const uint64_t x = SWB_BLS_X;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    auto line_and_step = [&](const Fq2& lam, const Fq2& ax) {
+        Fq12 l = Fq12::zero();
+        l.c0.c0.c0 = p.y;
+        l.c1.c0 = lam.scale(p.x).neg();
+        l.c1.c1 = lam * tx - ty;
+        const Fq2 nx = lam.sqr() - tx - ax;
+        ty = lam * (tx - nx) - ty;
+        tx = nx;
+        return l;
+    };
+    for (int i = top - 1; i >= 0; i--) {
+        const Fq2 xx = tx.sqr();
+        const Fq2 lam = (xx + xx + xx) * (ty + ty).inverse();
+        f = f.sqr() * line_and_step(lam, tx);
+        if ((x >> i) & 1) {
+            const Fq2 lam2 = (q.y - ty) * (q.x - tx).inverse();
+            f = f * line_and_step(lam2, q.x);
+        }
+    }
+    return f;
+}
+// the same function computed over E(Fq12) with nothing curve-specific in it
+inline Fq12 miller_loop_plain(const G1Point& p, const G2Point& q) {
     if (p.infinity || q.infinity) return Fq12::one();
     const E12Point Q = untwist(q);
     const Fq12 px = Fq12::from_fq(p.x), py = Fq12::from_fq(p.y);
