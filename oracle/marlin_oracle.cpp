@@ -240,6 +240,18 @@ int orc_pairing_selftest() {
         const Fq12 sq = plain_k.sqr();
         if (!(sq == plain_k * plain_k)) bad |= 131072;
     }
+    // the projective G2 ladder gives the affine ladder's points (cofactor-sized and field-sized scalars, small ones, zero)
+    {
+        static const uint32_t cof[SWB_G2_COFACTOR_WORDS] = SWB_G2_COFACTOR_INIT;
+        if (!(g2_mul_words(h, cof, SWB_G2_COFACTOR_WORDS) == g2_mul_words_affine(h, cof, SWB_G2_COFACTOR_WORDS))) bad |= 2097152;
+        for (uint32_t kk = 0; kk < 6; kk++) {
+            uint32_t w[8] = {kk, 0, 0, 0, 0, 0, 0, 0};
+            if (kk == 5) for (int i = 0; i < 8; i++) w[i] = rw[i] - (i == 0 ? 1u : 0u);          // r - 1: -Q
+            if (!(g2_mul_words(h, w, 8) == g2_mul_words_affine(h, w, 8))) bad |= 2097152;
+        }
+        const Fr kf = rand_fr(rng).to_canonical();
+        if (!(g2_mul_words(h, kf.l, 8) == g2_mul_words_affine(h, kf.l, 8))) bad |= 2097152;
+    }
     // subgroup membership by the endomorphism agrees with [r]P == O: on multiples of the generator, on random curve
     // points (outside G1 with overwhelming probability: the cofactor has 125 bits) and on their cofactor-cleared images
     {
