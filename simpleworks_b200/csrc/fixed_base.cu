@@ -6,8 +6,8 @@
 // Marlin::universal_setup <- reference src/marlin/mod.rs:52, simple_merkle_tree.rs:39 (1 572 862
 // points per table for the (100000, 25000, 300000) bound every non-toy example uses).
 //
-// Device schedule: a 32 x 256 table of d * 2^(8o) * g (8-bit windows, affine), then one thread
-// per group of 8 consecutive powers: 32 mixed additions each, one shared inversion to affine.
+// Device schedule: a 22 x 4096 table of d * 2^(12 o) * g (12-bit windows, affine), then one thread
+// per group of 8 consecutive powers: 22 mixed additions each, one shared inversion to affine.
 // Affine results are unique, so they equal arkworks' bit for bit.
 #define SWB_FP_NOINLINE_MUL
 #include "ctx.hpp"
@@ -15,8 +15,9 @@
 
 namespace swb {
 
-constexpr int FB_WINDOW = 8;
-constexpr int FB_OUTER = 32;
+constexpr int FB_WINDOW = 12;                         // 22 windows x 4096 entries: 8.6 MB of table, L2-resident
+constexpr int FB_OUTER = (253 + FB_WINDOW - 1) / FB_WINDOW;
+constexpr int FB_ENTRIES = 1 << FB_WINDOW;
 
 __device__ __forceinline__ G1Aff xyzz_to_affine(const G1Xyzz& p) {
     G1Aff a;
@@ -25,17 +26,17 @@ __device__ __forceinline__ G1Aff xyzz_to_affine(const G1Xyzz& p) {
         a.y = Fq::zero();
         return a;
     }
-    Fq inv = (p.zz * p.zzz).inverse();
+    Fq inv = (p.zz * p.zzz).inverse_bingcd();
     a.x = p.x * (p.zzz * inv);
     a.y = p.y * (p.zz * inv);
     return a;
 }
 
-// table[o*256 + d] = d * 2^(8o) * g from pow2[k] = 2^k * g
+// table[o*4096 + d] = d * 2^(12 o) * g from pow2[k] = 2^k * g
 __global__ void __launch_bounds__(128) k_fb_table(G1Aff* __restrict__ table, const G1Aff* __restrict__ pow2) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= FB_OUTER * 256) return;
-    const uint32_t o = e >> 8, d = e & 255u;
+    if (e >= FB_OUTER * FB_ENTRIES) return;
+    const uint32_t o = e >> FB_WINDOW, d = e & (FB_ENTRIES - 1u);
     G1Xyzz acc = G1Xyzz::identity();
     for (int b = 0; b < FB_WINDOW; b++) {
         if ((d >> b) & 1u) {
@@ -48,8 +49,8 @@ __global__ void __launch_bounds__(128) k_fb_table(G1Aff* __restrict__ table, con
 
 // RECORD = 104: ABI GroupAffine records (x | y | infinity flag); RECORD = 96: resident base layout.
 // A thread produces `group` consecutive powers (beta^(i+1) = beta^i * beta) and normalises them with
-// ONE inversion (Montgomery's trick over zz * zzz): the Fermat inversion is 565 Fq products, more than
-// the 32 mixed additions of a power, so sharing it more than halves the work.
+// ONE inversion (Montgomery's trick over zz * zzz, binary-GCD inversion): an inversion costs about as much as the
+// 22 mixed additions of a power, so sharing it nearly halves the work.
 constexpr int FB_GROUP = 8;
 template <int RECORD>
 __global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, const G1Aff* __restrict__ table, Fr beta, size_t n,
@@ -65,9 +66,12 @@ __global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, co
         bp = bp * beta;
         G1Xyzz acc = G1Xyzz::identity();
         for (int o = 0; o < FB_OUTER; o++) {
-            const uint32_t d = (s.l[o >> 2] >> ((o & 3) * 8)) & 255u;
+            const int bit = o * FB_WINDOW, limb = bit >> 5, off = bit & 31;
+            uint32_t d = s.l[limb] >> off;
+            if (off + FB_WINDOW > 32 && limb + 1 < 8) d |= s.l[limb + 1] << (32 - off);
+            d &= FB_ENTRIES - 1u;
             if (d) {
-                G1Aff p = table[o * 256 + d];
+                G1Aff p = table[o * FB_ENTRIES + d];
                 if (!p.is_identity()) acc.add_affine(p.x, p.y);
             }
         }
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(128) k_fb_powers(uint8_t* __restrict__ out, co
         pre[g] = run;
         run = run * (zz[g] * zzz[g]);
     }
-    Fq inv = run.inverse();
+    Fq inv = run.inverse_bingcd();
     for (int g = cnt; g-- > 0;) {
         const Fq tinv = inv * pre[g];            // (zz_g * zzz_g)^-1
         inv = inv * (zz[g] * zzz[g]);
@@ -163,7 +167,7 @@ using namespace swb;
 // builds the window table for g on the device; returns it in *table
 static int fb_prepare(swb_ctx* c, const swb_g1_jacobian* g_host, const swb_fr* beta_host, G1Aff** table, Fr* beta) {
     SWB_CUDA(c, cudaSetDevice(c->device));
-    // host: 2^k * g for k < 256, affine
+    // host: 2^k * g for k < FB_OUTER * FB_WINDOW, affine
     G1Xyzz p;
     Fq z;
     memcpy(p.x.l, g_host->x.l, 48);
@@ -174,25 +178,39 @@ static int fb_prepare(swb_ctx* c, const swb_g1_jacobian* g_host, const swb_fr* b
         p.zz = z.sqr();
         p.zzz = p.zz * z;
     }
+    // 2^k * g for every bit position, normalised with ONE inversion (Montgomery's trick; a host inversion per
+    // point was 15-25 ms of every setup)
     std::vector<G1Aff> pow2(FB_OUTER * FB_WINDOW);
-    for (size_t k = 0; k < pow2.size(); k++) {
-        if (p.is_identity()) {
-            pow2[k].x = Fq::zero();
-            pow2[k].y = Fq::zero();
-        } else {
-            Fq inv = (p.zz * p.zzz).inverse();
-            pow2[k].x = p.x * (p.zzz * inv);
-            pow2[k].y = p.y * (p.zz * inv);
+    {
+        std::vector<G1Xyzz> pts(pow2.size());
+        std::vector<Fq> pre(pow2.size());
+        Fq run = Fq::one();
+        for (size_t k = 0; k < pts.size(); k++) {
+            pts[k] = p;
+            pre[k] = run;
+            if (!p.is_identity()) run = run * (p.zz * p.zzz);
+            p = p.dbl();
         }
-        p = p.dbl();
+        Fq inv = run.inverse_bingcd();
+        for (size_t k = pts.size(); k-- > 0;) {
+            if (pts[k].is_identity()) {
+                pow2[k].x = Fq::zero();
+                pow2[k].y = Fq::zero();
+                continue;
+            }
+            const Fq tinv = inv * pre[k];                  // (zz_k * zzz_k)^-1
+            inv = inv * (pts[k].zz * pts[k].zzz);
+            pow2[k].x = pts[k].x * (pts[k].zzz * tinv);
+            pow2[k].y = pts[k].y * (pts[k].zz * tinv);
+        }
     }
     memcpy(beta->l, beta_host->l, 32);
     G1Aff* d_pow2 = (G1Aff*)get_scratch(c, "fb_pow2", sizeof(G1Aff) * pow2.size());
-    G1Aff* d_table = (G1Aff*)get_scratch(c, "fb_table", sizeof(G1Aff) * FB_OUTER * 256);
+    G1Aff* d_table = (G1Aff*)get_scratch(c, "fb_table", sizeof(G1Aff) * FB_OUTER * FB_ENTRIES);
     if (!d_pow2 || !d_table) return SWB_ENOMEM;
     SWB_CUDA(c, cudaMemcpyAsync(d_pow2, pow2.data(), sizeof(G1Aff) * pow2.size(), cudaMemcpyHostToDevice, c->stream));
     SWB_CUDA(c, cudaStreamSynchronize(c->stream));   // pow2 is a local
-    k_fb_table<<<FB_OUTER * 256 / 128, 128, 0, c->stream>>>(d_table, d_pow2);
+    k_fb_table<<<FB_OUTER * FB_ENTRIES / 128, 128, 0, c->stream>>>(d_table, d_pow2);
     SWB_LAUNCH_CHECK(c, "k_fb_table");
     *table = d_table;
     return SWB_OK;
