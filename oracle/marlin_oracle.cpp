@@ -252,6 +252,26 @@ int orc_pairing_selftest() {
         const Fr kf = rand_fr(rng).to_canonical();
         if (!(g2_mul_words(h, kf.l, 8) == g2_mul_words_affine(h, kf.l, 8))) bad |= 2097152;
     }
+    // the verifier's host MSM (Straus, shared doublings) equals the sum of separate scalar multiplications, with
+    // zero scalars, the identity, repeated and negated points among the terms
+    {
+        std::vector<std::pair<G1Point, Fr>> terms;
+        G1Xyzz want = G1Xyzz::identity();
+        for (int k = 0; k < 9; k++) {
+            G1Point pt = k == 3 ? G1Point::identity() : g1_mul_fr(g, rand_fr(rng));
+            if (k == 5) pt = terms[1].first;
+            if (k == 6) pt = g1_neg(terms[1].first);
+            Fr sc = k == 2 ? Fr::zero() : rand_fr(rng);
+            if (k == 6) sc = terms[5].second;                      // cancels term 5
+            if (k == 7) sc = Fr::one();
+            if (k == 8) sc = Fr::zero() - Fr::one();               // r - 1
+            terms.push_back({pt, sc});
+            const G1Point part = g1_mul_fr(pt, sc);
+            if (!part.infinity) want.add_affine(part.x, part.y);
+        }
+        if (!(to_affine(g1_msm_host(terms)) == to_affine(want))) bad |= 4194304;
+        if (!g1_msm_host({}).is_identity()) bad |= 4194304;
+    }
     // subgroup membership by the endomorphism agrees with [r]P == O: on multiples of the generator, on random curve
     // points (outside G1 with overwhelming probability: the cofactor has 125 bits) and on their cofactor-cleared images
     {
