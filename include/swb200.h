@@ -200,7 +200,10 @@ int  swb_fixed_base_powers(swb_ctx*, const swb_g1_jacobian* g_host, const swb_fr
 
 /* ---- radix-2 NTT over Fr, natural order in and out, in place ------------------------------ */
 /* inverse: uses w^-1 and scales by n^-1.  coset: multiplies by 22^j before a forward transform,
- * by 22^-j after an inverse one.  log_n <= 30 (Fr two-adicity is 47; bounded here by tables).  */
+ * by 22^-j after an inverse one.  log_n <= 30 (Fr two-adicity is 47; bounded here by tables).
+ * Inputs are Montgomery-form field elements below r, as every ark_ff Fr is; outputs are canonical again
+ * (inside, the butterflies work in the lazy range [0, 2r)).  Transforms of more than one pass keep a table of
+ * all powers of the root for the largest size seen (32 B << log_n, at most 2 GiB; swb_trim releases it). */
 int  swb_ntt_fr(swb_ctx*, swb_fr* inout_host, uint32_t log_n, int inverse, int coset);
 int  swb_ntt_fr_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, int inverse, int coset);
 int  swb_ntt_fr_batch_dev(swb_ctx*, swb_fr* inout_dev, uint32_t log_n, size_t batch, int inverse, int coset);
