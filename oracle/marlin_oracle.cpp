@@ -252,6 +252,13 @@ int orc_pairing_selftest() {
         const Fr kf = rand_fr(rng).to_canonical();
         if (!(g2_mul_words(h, kf.l, 8) == g2_mul_words_affine(h, kf.l, 8))) bad |= 2097152;
     }
+    // the shared-squaring loop over several pairs is the product of the single loops
+    {
+        const G1Point p1 = g1_mul_fr(g, rand_fr(rng)), p2 = g1_mul_fr(g, rand_fr(rng));
+        const G2Point q1 = g2_mul_fr(h, rand_fr(rng)), q2 = g2_mul_fr(h, rand_fr(rng));
+        if (!(miller_loop_multi({{p1, q1}, {p2, q2}, {G1Point::identity(), q1}}) == miller_loop(p1, q1) * miller_loop(p2, q2))) bad |= 8388608;
+        if (!(miller_loop_multi({}) == Fq12::one())) bad |= 8388608;
+    }
     // the verifier's host MSM (Straus, shared doublings) equals the sum of separate scalar multiplications, with
     // zero scalars, the identity, repeated and negated points among the terms
     {

@@ -320,38 +320,49 @@ inline E12Point untwist(const G2Point& q) {
 // 11 products + 2 squarings; the line a + (b + c v) w = (-2YZ py) + (3X^2 px) w + (3b'Z^2 - Y^2) v w multiplies f
 // sparsely.  Checked against miller_loop_affine / miller_loop_plain after the final exponentiation
 // (orc_pairing_selftest).
-inline Fq12 miller_loop(const G1Point& p, const G2Point& q) {
-    if (p.infinity || q.infinity) return Fq12::one();
+// prod_k f_{x,Q_k}(P_k): the squarings of f are shared by all pairs (a batch check has two)
+inline Fq12 miller_loop_multi(const std::vector<std::pair<G1Point, G2Point>>& pairs) {
     static const Fq two_inv = fq_small(2).inverse();
     static const Fq2 bt = g2_coeff_b();
-    Fq2 X = q.x, Y = q.y, Z = Fq2::one();
+    struct T { Fq2 X, Y, Z; const G1Point* p; const G2Point* q; };
+    std::vector<T> ts;
+    for (auto& pq : pairs)
+        if (!pq.first.infinity && !pq.second.infinity) ts.push_back({pq.second.x, pq.second.y, Fq2::one(), &pq.first, &pq.second});
     Fq12 f = Fq12::one();
+    if (ts.empty()) return f;
     const uint64_t x = SWB_BLS_X;
     int top = 63;
     while (!((x >> top) & 1)) top--;
     for (int i = top - 1; i >= 0; i--) {
-        {   // doubling step
+        f = f.sqr();
+        for (auto& t : ts) {   // doubling step
+            Fq2 &X = t.X, &Y = t.Y, &Z = t.Z;
             const Fq2 a = (X * Y).scale(two_inv), b = Y.sqr(), c = Z.sqr();
             const Fq2 e = bt * (c + c + c), f3 = e + e + e;
             const Fq2 g = (b + f3).scale(two_inv), h = (Y + Z).sqr() - (b + c), i2 = e - b, j = X.sqr(), e2 = e.sqr();
             X = a * (b - f3);
             Y = g.sqr() - (e2 + e2 + e2);
             Z = b * h;
-            f = f.sqr().mul_by_line(h.neg().scale(p.y), (j + j + j).scale(p.x), i2);
+            f = f.mul_by_line(h.neg().scale(t.p->y), (j + j + j).scale(t.p->x), i2);
         }
-        if ((x >> i) & 1) {   // addition step: T <- T + Q
-            const Fq2 theta = Y - q.y * Z, lambda = X - q.x * Z;
-            const Fq2 c = theta.sqr(), d = lambda.sqr(), e = lambda * d, ff = Z * c, g = X * d;
-            const Fq2 h = e + ff - (g + g);
-            X = lambda * h;
-            Y = theta * (g - h) - e * Y;
-            Z = Z * e;
-            const Fq2 j = theta * q.x - lambda * q.y;
-            f = f.mul_by_line(lambda.scale(p.y), theta.neg().scale(p.x), j);
+        if ((x >> i) & 1) {
+            for (auto& t : ts) {   // addition step: T <- T + Q
+                Fq2 &X = t.X, &Y = t.Y, &Z = t.Z;
+                const G2Point& q = *t.q;
+                const Fq2 theta = Y - q.y * Z, lambda = X - q.x * Z;
+                const Fq2 c = theta.sqr(), d = lambda.sqr(), e = lambda * d, ff = Z * c, g = X * d;
+                const Fq2 h = e + ff - (g + g);
+                X = lambda * h;
+                Y = theta * (g - h) - e * Y;
+                Z = Z * e;
+                const Fq2 j = theta * q.x - lambda * q.y;
+                f = f.mul_by_line(lambda.scale(t.p->y), theta.neg().scale(t.p->x), j);
+            }
         }
     }
     return f;
 }
+inline Fq12 miller_loop(const G1Point& p, const G2Point& q) { return miller_loop_multi({{p, q}}); }
 // The same Miller function with T kept
 // on the TWIST in affine Fq2 coordinates.  The untwisted point is (x' w^2, y' w^3), so a slope on E is lambda' w
 // with lambda' = 3 x'^2 / (2 y') (or the chord's) in Fq2, the new point is (lambda'^2 - x1' - x2',
@@ -512,9 +523,7 @@ inline Fq12 final_exponentiation(const Fq12& f) {
 inline Fq12 pairing(const G1Point& p, const G2Point& q) { return final_exponentiation(miller_loop(p, q)); }
 // prod_i e(P_i, Q_i) == 1 ?
 inline bool pairing_product_is_one(const std::vector<std::pair<G1Point, G2Point>>& pairs) {
-    Fq12 f = Fq12::one();
-    for (auto& pq : pairs) f = f * miller_loop(pq.first, pq.second);
-    return final_exponentiation(f) == Fq12::one();
+    return final_exponentiation(miller_loop_multi(pairs)) == Fq12::one();
 }
 
 }  // namespace marlin
