@@ -252,6 +252,16 @@ int orc_pairing_selftest() {
         const Fr kf = rand_fr(rng).to_canonical();
         if (!(g2_mul_words(h, kf.l, 8) == g2_mul_words_affine(h, kf.l, 8))) bad |= 2097152;
     }
+    // cyclotomic squaring equals the plain one on the cyclotomic subgroup (elements after the easy part)
+    {
+        Fq12 c = a12.conj() * a12.inverse();
+        c = frobenius(c, 2) * c;
+        for (int k = 0; k < 4; k++) {
+            if (!(c.cyclotomic_sqr() == c.sqr())) bad |= 16777216;
+            c = c * c.sqr();
+        }
+        if (!(exp_by_x(c, true) == exp_by_x(c, false))) bad |= 16777216;
+    }
     // the shared-squaring loop over several pairs is the product of the single loops
     {
         const G1Point p1 = g1_mul_fr(g, rand_fr(rng)), p2 = g1_mul_fr(g, rand_fr(rng));

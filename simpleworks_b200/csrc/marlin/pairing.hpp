@@ -113,6 +113,32 @@ struct Fq12 {
         const Fq6 t = (c0 + c1) * (c0 + c1.mul_by_v()) - ab - ab.mul_by_v();      // c0^2 + v c1^2
         return {t, ab + ab};
     }
+    // squaring of an element of the cyclotomic subgroup (anything after the easy part of the final exponentiation):
+    // Granger-Scott, "Faster squaring in the cyclotomic subgroup of sixth degree extensions" -- three Fq4 squarings
+    // (6 Fq2 products) instead of 12; ark-ff's cyclotomic_square for this tower.  Wrong outside the subgroup; the
+    // self-test compares it with sqr() on subgroup elements.
+    Fq12 cyclotomic_sqr() const {
+        const Fq2 &r0 = c0.c0, &r4 = c0.c1, &r3 = c0.c2, &r2 = c1.c0, &r1 = c1.c1, &r5 = c1.c2;
+        auto fq4_sqr = [](const Fq2& a, const Fq2& b, Fq2* t0, Fq2* t1) {     // (a + b y)^2, y^2 = u
+            const Fq2 ab = a * b;
+            *t0 = (a + b) * (b.mul_by_u() + a) - ab - ab.mul_by_u();
+            *t1 = ab + ab;
+        };
+        Fq2 t0, t1, t2, t3, t4, t5;
+        fq4_sqr(r0, r1, &t0, &t1);
+        fq4_sqr(r2, r3, &t2, &t3);
+        fq4_sqr(r4, r5, &t4, &t5);
+        auto three_minus_two = [](const Fq2& t, const Fq2& z) { Fq2 x = t - z; x = x + x; return x + t; };   // 3t - 2z
+        auto three_plus_two = [](const Fq2& t, const Fq2& z) { Fq2 x = t + z; x = x + x; return x + t; };    // 3t + 2z
+        Fq12 r;
+        r.c0.c0 = three_minus_two(t0, r0);
+        r.c1.c1 = three_plus_two(t1, r1);
+        r.c1.c0 = three_plus_two(t5.mul_by_u(), r2);
+        r.c0.c2 = three_minus_two(t4, r3);
+        r.c0.c1 = three_minus_two(t2, r4);
+        r.c1.c2 = three_plus_two(t3, r5);
+        return r;
+    }
     // times the sparse element a + (b + c v) w, a, b, c in Fq2 -- the shape of a line of the Miller loop
     // (arkworks' mul_by_034)
     Fq12 mul_by_line(const Fq2& a, const Fq2& b, const Fq2& c) const {
@@ -477,13 +503,14 @@ inline Fq12 final_exponentiation_plain(const Fq12& f) {
     Fq12 g = f.conj() * f.inverse();
     return g.pow_words(e, SWB_FINAL_EXP_WORDS);
 }
-inline Fq12 exp_by_x(const Fq12& f) {                       // f^x, x = 0x8508c00000000001 (positive)
+// f^x, x = 0x8508c00000000001 (positive); cyclotomic: f lies in the cyclotomic subgroup (cheaper squarings)
+inline Fq12 exp_by_x(const Fq12& f, bool cyclotomic = false) {
     const uint64_t x = SWB_BLS_X;
     Fq12 acc = f;
     int top = 63;
     while (!((x >> top) & 1)) top--;
     for (int i = top - 1; i >= 0; i--) {
-        acc = acc.sqr();
+        acc = cyclotomic ? acc.cyclotomic_sqr() : acc.sqr();
         if ((x >> i) & 1) acc = acc * f;
     }
     return acc;
@@ -496,15 +523,15 @@ inline Fq12 exp_by_x(const Fq12& f) {                       // f^x, x = 0x8508c0
 inline Fq12 final_exponentiation(const Fq12& f) {
     Fq12 r = f.conj() * f.inverse();                        // f^(q^6 - 1)
     r = frobenius(r, 2) * r;                                // ^(q^2 + 1): now in the cyclotomic subgroup, inverse = conj
-    Fq12 y0 = r.sqr().conj();
-    Fq12 y5 = exp_by_x(r);
-    Fq12 y1 = y5.sqr();
+    Fq12 y0 = r.cyclotomic_sqr().conj();
+    Fq12 y5 = exp_by_x(r, true);
+    Fq12 y1 = y5.cyclotomic_sqr();
     Fq12 y3 = y0 * y5;
-    y0 = exp_by_x(y3);
-    const Fq12 y2 = exp_by_x(y0);
-    Fq12 y4 = exp_by_x(y2);
+    y0 = exp_by_x(y3, true);
+    const Fq12 y2 = exp_by_x(y0, true);
+    Fq12 y4 = exp_by_x(y2, true);
     y4 = y4 * y1;
-    y1 = exp_by_x(y4);
+    y1 = exp_by_x(y4, true);
     y3 = y3.conj();
     y1 = y1 * y3;
     y1 = y1 * r;
