@@ -15,8 +15,8 @@
 // factors); orc_pairing_selftest checks both, and bilinearity, on random points.  The final exponentiation uses the
 // BLS12 decomposition (checked against the plain 2009-bit exponentiation).  Verification checks pairing *equations*,
 // for which any bilinear non-degenerate pairing gives the same verdict as arkworks' own.  It stays on the host:
-// 8 ms per proof on the GPU box (two Miller loops 2 x 2 ms, final exponentiation 3 ms, subgroup tests and the
-// commitment combination 1 ms each).
+// 7.4 ms per proof on the GPU box (the two Miller loops share their squarings, the hard part of the final
+// exponentiation squares cyclotomically; the rest is subgroup tests of the proof's points and the commitment MSM).
 #pragma once
 #include "curve_host.hpp"
 
