@@ -160,7 +160,9 @@ def synth_scalars_host(n: int, seed: int) -> np.ndarray:
 def workload_config(log_n: int) -> dict:
     """the part of the JSON line's config both arms (libswb200 and --impl reference) share"""
     return {"workload": f"bls12-377 G1 variable-base MSM 2^{log_n}", "scalars": "uniform in [0, r)",
-            "bases": "SRS powers beta^i*G"}
+            "bases": "SRS powers beta^i*G",
+            "l2": "a 256 MiB buffer is rewritten between timed steps and the inputs (2 GiB of scalars, 66 GiB of table "
+                  "records at 2^26) exceed the 126 MB L2 anyway"}
 
 
 def marlin_gpu_run(be, lg, proofs):
