@@ -321,11 +321,10 @@ __global__ void k_build_full_table(Fr* __restrict__ tab, const Fr* __restrict__ 
 // Direct twiddle table for transforms of up to 2^log_n points (32 B << log_n of device memory: 2 GiB at 2^26), grown on
 // demand; SWB_NTT_TABLE_MAX_LOG caps it (0 switches it off).  Returns the table's log size or 0 (running products).
 static uint32_t ntt_full_table(swb_ctx* c, uint32_t log_n) {
-    static const uint32_t cap = [] {
-        const char* e = getenv("SWB_NTT_TABLE_MAX_LOG");
-        const long v = e ? atol(e) : 26;
-        return (uint32_t)(v < 0 ? 0 : (v > 27 ? 27 : v));
-    }();
+    // read at every call (a getenv is nothing beside a transform), so that tests can compare both twiddle paths
+    const char* env = getenv("SWB_NTT_TABLE_MAX_LOG");
+    const long capv = env ? atol(env) : 26;
+    const uint32_t cap = (uint32_t)(capv < 0 ? 0 : (capv > 27 ? 27 : capv));
     if (log_n > cap || c->tw_full_failed) return 0;
     if (c->tw_full && c->tw_full_log >= log_n) return c->tw_full_log;
     if (c->tw_full) {

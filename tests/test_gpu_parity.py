@@ -508,6 +508,29 @@ def test_trim_keeps_results(be, srs_points):
         bases.free()
 
 
+@pytest.mark.parametrize("log_n", [11, 14, 17, 21, 23])
+def test_ntt_twiddle_paths_agree(be, log_n, monkeypatch):
+    """Inter-digit twiddles by table lookup (default) and by running powers (SWB_NTT_TABLE_MAX_LOG=0: the path of
+    transforms above 2^26 points and of a refused table allocation) give the same bytes, forward, inverse and on the
+    coset; odd and even digit plans (a leftover radix-2 stage beside the stage pairs)."""
+    import torch
+    n = 1 << log_n
+    x = torch.randint(-2 ** 63, 2 ** 63 - 1, (n, 4), dtype=torch.int64, device=f"cuda:{be.device}")
+    x[:, 3] &= 0x0FFFFFFFFFFFFFFF
+    outs = {}
+    for cap in ("26", "0"):
+        monkeypatch.setenv("SWB_NTT_TABLE_MAX_LOG", cap)
+        be.trim()                                            # drops the table, so the cap decides again
+        f = be.ntt_(x.clone(), log_n)
+        outs[cap] = (f, be.ntt_(x.clone(), log_n, inverse=True), be.ntt_(x.clone(), log_n, coset=True),
+                     be.ntt_(x.clone(), log_n, inverse=True, coset=True))
+        assert torch.equal(be.ntt_(f.clone(), log_n, inverse=True), x)
+    for a, b in zip(outs["26"], outs["0"]):
+        assert torch.equal(a, b)
+    monkeypatch.delenv("SWB_NTT_TABLE_MAX_LOG")
+    be.trim()
+
+
 @pytest.mark.parametrize("log_n", [25, 26])
 def test_ntt_four_pass_sizes(be, log_n):
     """log n >= 25 (more passes than anything the oracle comparison reaches): inverse(forward(x)) == x with and
